@@ -1,0 +1,112 @@
+// C-ABI entry points (include/probunet_b200.h) for the primitive ops + shared host helpers.
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pub {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int conv_forward(const ConvParams& p, int dtype, int backend, cudaStream_t s) {
+  if (backend == PUB_BACKEND_TCGEN05) {
+    PUB_REQUIRE(conv_tc_supported(p, dtype), "tcgen05 conv backend does not support this shape/dtype "
+                "(c0=%d c1=%d cout=%d H=%d W=%d ks=%d dtype=%d)", p.c0, p.c1, p.cout, p.H, p.W, p.ks, dtype);
+    return conv_tc(p, s);
+  }
+  if (backend == PUB_BACKEND_AUTO && conv_tc_supported(p, dtype)) return conv_tc(p, s);
+  return conv_simt(p, dtype, s);
+}
+
+size_t wgrad_workspace(const WgradParams& p, int dtype, int backend) {
+  size_t a = wgrad_simt_workspace(p);
+  if (backend != PUB_BACKEND_SIMT && wgrad_tc_supported(p, dtype)) {
+    size_t b = wgrad_tc_workspace(p);
+    if (b > a) a = b;
+  }
+  return a;
+}
+
+int wgrad(const WgradParams& p, int dtype, int backend, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
+  if (backend == PUB_BACKEND_TCGEN05) {
+    PUB_REQUIRE(wgrad_tc_supported(p, dtype), "tcgen05 wgrad backend does not support this shape/dtype");
+    return wgrad_tc(p, ws, ws_bytes, accumulate, s);
+  }
+  if (backend == PUB_BACKEND_AUTO && wgrad_tc_supported(p, dtype)) return wgrad_tc(p, ws, ws_bytes, accumulate, s);
+  return wgrad_simt(p, dtype, ws, ws_bytes, accumulate, s);
+}
+
+static ConvParams to_params(const pub_conv_args* a) {
+  ConvParams p{};
+  p.x0 = a->x0; p.x1 = a->x1; p.c0 = a->c0; p.c1 = a->x1 ? a->c1 : 0; p.ld0 = a->ld0; p.ld1 = a->ld1;
+  p.w = a->w; p.bias = a->bias; p.res = a->res; p.ld_res = a->ld_res; p.mask = a->mask; p.ld_mask = a->ld_mask;
+  p.y = a->y; p.ldy = a->ldy; p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.ks = a->ksize; p.relu = a->relu;
+  return p;
+}
+static WgradParams to_params(const pub_wgrad_args* a) {
+  WgradParams p{};
+  p.x0 = a->x0; p.x1 = a->x1; p.c0 = a->c0; p.c1 = a->x1 ? a->c1 : 0; p.ld0 = a->ld0; p.ld1 = a->ld1;
+  p.dy = a->dy; p.ld_dy = a->ld_dy; p.dw = a->dw; p.dbias = a->dbias;
+  p.B = a->B; p.H = a->H; p.W = a->W; p.cout = a->cout; p.ks = a->ksize;
+  return p;
+}
+
+}  // namespace pub
+
+using namespace pub;
+
+extern "C" {
+
+const char* pub_last_error(void) { return g_err.c_str(); }
+int pub_version(void) { return 100; }
+
+int pub_conv2d_forward(const pub_conv_args* a, pub_stream_t s) {
+  PUB_REQUIRE(a && a->x0 && a->w && a->y, "pub_conv2d_forward: null argument");
+  PUB_REQUIRE(a->ksize == 1 || a->ksize == 3, "pub_conv2d_forward: ksize must be 1 or 3");
+  PUB_REQUIRE(a->dtype == PUB_F32 || a->dtype == PUB_BF16, "pub_conv2d_forward: bad dtype");
+  return conv_forward(to_params(a), a->dtype, a->backend, (cudaStream_t)s);
+}
+
+int pub_pack_conv_weight(const float* w, void* packed, int cout, int cin, int ksize, int dtype, int tflip,
+                         pub_stream_t s) {
+  PUB_REQUIRE(w && packed, "pub_pack_conv_weight: null argument");
+  return pack_weight(w, packed, cout, cin, ksize, dtype, tflip, (cudaStream_t)s);
+}
+
+size_t pub_conv2d_wgrad_workspace(const pub_wgrad_args* a) { return wgrad_workspace(to_params(a), a->dtype, a->backend); }
+
+int pub_conv2d_wgrad(const pub_wgrad_args* a, pub_stream_t s) {
+  PUB_REQUIRE(a && a->x0 && a->dy && a->dw && a->workspace, "pub_conv2d_wgrad: null argument");
+  return wgrad(to_params(a), a->dtype, a->backend, a->workspace, a->workspace_bytes, a->accumulate, (cudaStream_t)s);
+}
+
+int pub_nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, int ldy, int B, int H, int W, int dtype,
+                     pub_stream_t s) {
+  return nchw_to_nhwc(x0, c0, x1, x1 ? c1 : 0, y, ldy, B, H, W, dtype, (cudaStream_t)s);
+}
+int pub_nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, int dtype, int accumulate,
+                     pub_stream_t s) {
+  return nhwc_to_nchw(x, ld, C, y, B, H, W, dtype, accumulate, (cudaStream_t)s);
+}
+
+}  // extern "C"

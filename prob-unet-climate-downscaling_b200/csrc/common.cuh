@@ -1,0 +1,152 @@
+// Shared device/host helpers for the probunet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/probunet_b200.h"
+
+namespace pub {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+
+#define PUB_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::pub::set_error(__VA_ARGS__);      \
+      return -1;                          \
+    }                                     \
+  } while (0)
+
+#define PUB_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      ::pub::set_error("%s -> %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return -2;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+#define PUB_LAUNCH_CHECK() PUB_CUDA(cudaGetLastError())
+
+#define PUB_TRY(expr)        \
+  do {                       \
+    int r__ = (expr);        \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t dtype_size(int dt) { return dt == PUB_BF16 ? 2 : 4; }
+int num_sms();
+
+// ---------------------------------------------------------------- scalar conversion
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8 consecutive channels of an NHWC tensor <-> 8 floats (16 B of bf16 / 32 B of f32)
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum, result valid in thread 0 (deterministic: fixed shuffle tree + fixed order)
+template <int NT> __device__ __forceinline__ float block_sum(float v, float* smem /* >= NT/32 floats */) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = (l < NT / 32) ? smem[l] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  static __device__ __forceinline__ uint4 gen(uint64_t seed, uint64_t subseq, uint64_t ctr) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)subseq, c3 = (uint32_t)(subseq >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  static __device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad_f(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+// ---------------------------------------------------------------- bump allocator over a caller workspace
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0, cap = 0;
+  bool dry = true;  // dry run: only measure
+  Arena() {}
+  Arena(void* p, size_t c) : base((char*)p), cap(c), dry(p == nullptr) {}
+  void* take(size_t bytes) {
+    off = align_up(off, 1024);
+    void* r = dry ? nullptr : (void*)(base + off);
+    off += bytes;
+    return r;
+  }
+  template <typename U> U* take_n(size_t n) { return (U*)take(n * sizeof(U)); }
+  bool ok() const { return dry || off <= cap; }
+};
+
+}  // namespace pub

@@ -1,0 +1,331 @@
+// fp32-FMA implicit-GEMM convolution family (any shape, f32 or bf16 storage, f32 accumulate).
+// This is the PARITY path (fp32 rel-err <= 1e-4 vs the reference) and the fallback for the
+// shapes the tcgen05 kernels do not take (Cin = 3/6 first layers).  Replaces F.conv2d at
+// src/networks.py:89 / src/prob_unet.py:41-46 and convolution_backward's weight gradient.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pub {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+template <typename T>
+__device__ __forceinline__ float load2src(const T* x0, const T* x1, int c0, int cin, int ld0, int ld1,
+                                          int64_t pix, int c) {
+  if (c < c0) return to_f<T>(x0[pix * ld0 + c]);
+  if (c < cin) return to_f<T>(x1[pix * ld1 + (c - c0)]);
+  return 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const T* x0 = (const T*)p.x0;
+  const T* x1 = (const T*)p.x1;
+  const T* w = (const T*)p.w;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int cin = p.c0 + p.c1;
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  // this thread's load coordinates
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int64_t lm = m0 + lr;
+  int lb = 0, ly = 0, lx = 0;
+  const bool lvalid = lm < M;
+  if (lvalid) { lx = (int)(lm % p.W); ly = (int)((lm / p.W) % p.H); lb = (int)(lm / ((int64_t)p.W * p.H)); }
+  const int ln = n0 + lr;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int taps = p.ks * p.ks, half = p.ks / 2;
+  const int kchunks = (cin + BK - 1) / BK;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int yy = ly + tap / p.ks - half, xx = lx + tap % p.ks - half;
+    const bool inb = lvalid && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+    const int64_t sp = ((int64_t)lb * p.H + yy) * p.W + xx;
+    for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = kc * BK + lk + j;
+        As[lk + j][lr] = inb ? load2src<T>(x0, x1, p.c0, cin, p.ld0, p.ld1, sp, c) : 0.f;
+        Bs[lk + j][lr] = (ln < p.cout && c < cin) ? to_f<T>(w[((int64_t)tap * p.cout + ln) * cin + c]) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  T* y = (T*)p.y;
+  const T* res = (const T*)p.res;
+  const T* mask = (const T*)p.mask;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.cout) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      if (res) v += to_f<T>(res[m * p.ld_res + n]);
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (mask && !(to_f<T>(mask[m * p.ld_mask + n]) > 0.f)) v = 0.f;
+      y[m * p.ldy + n] = from_f<T>(v);
+    }
+  }
+}
+
+// dW[tap][co][ci] partial over a pixel range:  sum_p dy[p][co] * x[p + tap][ci]
+template <typename T>
+__global__ void __launch_bounds__(NT) wgrad_simt_kernel(WgradParams p, float* __restrict__ part, int nsplit,
+                                                        int pix_per_split) {
+  __shared__ float As[BK][BM + 4];  // [pixel][co]
+  __shared__ float Bs[BK][BN + 4];  // [pixel][ci]
+  const T* x0 = (const T*)p.x0;
+  const T* x1 = (const T*)p.x1;
+  const T* dy = (const T*)p.dy;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int cin = p.c0 + p.c1;
+  const int taps = p.ks * p.ks, half = p.ks / 2;
+  const int tap = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
+  const int ddy = tap / p.ks - half, ddx = tap % p.ks - half;
+  const int co0 = blockIdx.y * BM, ci0 = blockIdx.x * BN;
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int64_t pbeg = (int64_t)split * pix_per_split;
+  const int64_t pend = min(M, pbeg + pix_per_split);
+  const int lp = tid >> 4, lc = (tid & 15) * 4;  // load: pixel lp, channels lc..lc+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t pb = pbeg; pb < pend; pb += BK) {
+    const int64_t m = pb + lp;
+    const bool v = m < pend;
+    int x = 0, y = 0, b = 0;
+    if (v) { x = (int)(m % p.W); y = (int)((m / p.W) % p.H); b = (int)(m / ((int64_t)p.W * p.H)); }
+    const int yy = y + ddy, xx = x + ddx;
+    const bool inb = v && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+    const int64_t sp = ((int64_t)b * p.H + yy) * p.W + xx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + lc + j, ci = ci0 + lc + j;
+      As[lp][lc + j] = (v && co < p.cout) ? to_f<T>(dy[m * p.ld_dy + co]) : 0.f;
+      Bs[lp][lc + j] = inb ? load2src<T>(x0, x1, p.c0, cin, p.ld0, p.ld1, sp, ci) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= p.cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci >= cin) continue;
+      part[(((int64_t)split * taps + tap) * p.cout + co) * cin + ci] = acc[i][j];
+    }
+  }
+}
+
+// sum the split partials in a fixed order -> OIHW f32 gradient (deterministic split-K)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int taps,
+                                    int cout, int cin, int accumulate) {
+  const int64_t n = (int64_t)taps * cout * cin;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * n + i];
+  const int64_t o = ((int64_t)co * cin + ci) * taps + tap;  // OIHW with (ky,kx) == tap
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
+// column sums over pixels: partial[chunk][C]
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int C, int64_t M, int rows_per_chunk,
+                                      float* __restrict__ part) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += to_f<T>(x[r * ld + c]);
+  part[(int64_t)blockIdx.x * C + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nchunk, int C, float* __restrict__ out,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < nchunk; ++k) s += (double)part[(int64_t)k * C + c];
+  out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int ks,
+                                   int tflip) {
+  const int taps = ks * ks;
+  const int64_t n = (int64_t)taps * cout * cin;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!tflip) {  // out[tap][co][ci]
+    const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
+    out[i] = from_f<T>(w[((int64_t)co * cin + ci) * taps + tap]);
+  } else {  // out[tap][ci][co] = w[co][ci][mirror(tap)]
+    const int co = (int)(i % cout), ci = (int)((i / cout) % cin), tap = (int)(i / ((int64_t)cin * cout));
+    out[i] = from_f<T>(w[((int64_t)co * cin + ci) * taps + (taps - 1 - tap)]);
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
+                                    T* __restrict__ y, int ldy, int B, int64_t HW) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * HW) return;
+  const int64_t b = i / HW, p = i % HW;
+  for (int c = 0; c < c0; ++c) y[i * ldy + c] = from_f<T>(x0[(b * c0 + c) * HW + p]);
+  for (int c = 0; c < c1; ++c) y[i * ldy + c0 + c] = from_f<T>(x1[(b * c1 + c) * HW + p]);
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ld, int C, float* __restrict__ y, int B, int64_t HW,
+                                    int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * HW) return;
+  const int64_t b = i / HW, p = i % HW;
+  for (int c = 0; c < C; ++c) {
+    const float v = to_f<T>(x[i * ld + c]);
+    float* o = y + (b * C + c) * HW + p;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+}  // namespace
+
+int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  dim3 grid(cdiv(M, BM), cdiv(p.cout, BN));
+  if (dtype == PUB_BF16) conv_simt_kernel<bf16><<<grid, NT, 0, s>>>(p);
+  else conv_simt_kernel<float><<<grid, NT, 0, s>>>(p);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+static void wgrad_simt_plan(const WgradParams& p, int& nsplit, int& pps) {
+  const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int tiles = cdiv(cin, BN) * cdiv(p.cout, BM) * taps;
+  int want = cdiv(4 * num_sms(), tiles);
+  const int maxs = (int)((M + 511) / 512);
+  nsplit = want < 1 ? 1 : (want > maxs ? maxs : want);
+  if (nsplit < 1) nsplit = 1;
+  pps = (int)(((M + nsplit - 1) / nsplit + BK - 1) / BK * BK);
+  nsplit = cdiv(M, pps);
+}
+
+size_t wgrad_simt_workspace(const WgradParams& p) {
+  int nsplit, pps;
+  wgrad_simt_plan(p, nsplit, pps);
+  const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const size_t a = (size_t)nsplit * taps * p.cout * cin * sizeof(float);
+  const size_t b = (size_t)cdiv(M, 1024) * p.cout * sizeof(float);
+  return align_up(a, 256) + align_up(b, 256);
+}
+
+int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, float* out, int accumulate,
+           cudaStream_t s) {
+  const int rows = 1024;
+  const int nchunk = cdiv(M, rows);
+  dim3 grid(nchunk, cdiv(C, 64));
+  if (dtype == PUB_BF16) colsum_partial_kernel<bf16><<<grid, 64, 0, s>>>((const bf16*)x, ld, C, M, rows, part);
+  else colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)x, ld, C, M, rows, part);
+  PUB_LAUNCH_CHECK();
+  colsum_final_kernel<<<cdiv(C, 128), 128, 0, s>>>(part, nchunk, C, out, accumulate);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
+  int nsplit, pps;
+  wgrad_simt_plan(p, nsplit, pps);
+  const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
+  PUB_REQUIRE(ws_bytes >= wgrad_simt_workspace(p), "wgrad workspace too small (%zu < %zu)", ws_bytes,
+              wgrad_simt_workspace(p));
+  float* part = (float*)ws;
+  dim3 grid(cdiv(cin, BN), cdiv(p.cout, BM), taps * nsplit);
+  if (dtype == PUB_BF16) wgrad_simt_kernel<bf16><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
+  else wgrad_simt_kernel<float><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
+  PUB_LAUNCH_CHECK();
+  const int64_t n = (int64_t)taps * p.cout * cin;
+  wgrad_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part, p.dw, nsplit, taps, p.cout, cin, accumulate);
+  PUB_LAUNCH_CHECK();
+  if (p.dbias) {
+    float* bpart = (float*)((char*)ws + align_up((size_t)nsplit * n * sizeof(float), 256));
+    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, p.dbias, accumulate, s));
+  }
+  return 0;
+}
+
+int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype, int tflip, cudaStream_t s) {
+  const int64_t n = (int64_t)ks * ks * cout * cin;
+  if (dtype == PUB_BF16) pack_weight_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(w, (bf16*)out, cout, cin, ks, tflip);
+  else pack_weight_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(w, (float*)out, cout, cin, ks, tflip);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, int ldy, int B, int H, int W, int dtype,
+                 cudaStream_t s) {
+  const int64_t n = (int64_t)B * H * W;
+  if (dtype == PUB_BF16)
+    nchw_to_nhwc_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(x0, c0, x1, c1, (bf16*)y, ldy, B, (int64_t)H * W);
+  else
+    nchw_to_nhwc_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(x0, c0, x1, c1, (float*)y, ldy, B, (int64_t)H * W);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, int dtype, int accumulate,
+                 cudaStream_t s) {
+  const int64_t n = (int64_t)B * H * W;
+  if (dtype == PUB_BF16)
+    nhwc_to_nchw_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>((const bf16*)x, ld, C, y, B, (int64_t)H * W, accumulate);
+  else
+    nhwc_to_nchw_kernel<float><<<cdiv(n, 256), 256, 0, s>>>((const float*)x, ld, C, y, B, (int64_t)H * W, accumulate);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace pub

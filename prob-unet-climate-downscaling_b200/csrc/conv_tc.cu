@@ -1,0 +1,644 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (bf16 in, f32 accumulate).
+//
+//  conv_tc   : y[p][n] = sum_{tap,c} x[p+tap][c] * w[tap][n][c]   (3x3 / 1x1, stride 1, same pad)
+//              M = 128 output pixels (a TW x TH x TB patch), N = BN output channels, K = taps*Cin.
+//              A tiles are fetched by 4-D *tiled* TMA loads with the tap offset folded into the box
+//              coordinates -- out-of-bounds rows/cols are zero-filled by the TMA unit, which IS the
+//              same-padding; no im2col buffer exists.  B tiles ([tap][N][K], K-major) by 3-D TMA.
+//              Also runs the data gradient (weights packed transposed+mirrored) and the virtual
+//              channel concat (two A tensor maps, src/networks.py:329).
+//  wgrad_tc  : dW[tap][co][ci] = sum_p dy[p][co] * x[p+tap][ci]; K = pixels, both operands MN-major
+//              (channels contiguous) straight from the same NHWC TMA boxes; 9 tap accumulators live
+//              in TMEM side by side; split-K partials are reduced in a fixed order (deterministic).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warps 2..5 =
+// epilogue (tcgen05.ld -> registers -> global).  mbarrier ring between producer and issuer,
+// tcgen05.commit releases stages and publishes the accumulator.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pub {
+
+namespace {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("probunet_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> f32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive f32 columns -> 32 registers per thread (thread t <-> lane base+t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ descriptors
+// smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), majors (15,16), N>>3 (17..22),
+// M>>4 (24..28)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int NTHREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+struct TcConvArgs {
+  int c0, c1;                  // channels of source 0 / 1
+  int taps, ks;                // 1 or 9
+  int B, H, W;
+  int TW, TH, TB;              // 128-pixel patch
+  int tiles_x, tiles_y;        // patches per image row / column
+  int BN;                      // output channels per CTA (multiple of 32, <= 256)
+  int cout;                    // total output channels
+  int stages;
+  const float* bias;
+  const bf16* res; int ld_res;
+  const bf16* mask; int ld_mask;
+  bf16* y; int ldy;
+  int relu;
+};
+
+// ------------------------------------------------------------------ forward / dgrad kernel
+template <int KC>  // channels per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
+__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                           const __grid_constant__ CUtensorMap tmA1,
+                                                           const __grid_constant__ CUtensorMap tmW, TcConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t ROWB = KC * 2;                   // bytes per smem row
+  constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t SBO = 8 * ROWB;                  // 8-row core-matrix group pitch
+  constexpr uint32_t A_BYTES = 128 * ROWB;
+  const uint32_t B_BYTES = (uint32_t)a.BN * ROWB;
+  const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]),
+                 accbar = smem_u32(&bars[2 * MAX_STAGES]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cblk0 = a.c0 / KC, cblk = (a.c0 + a.c1) / KC;
+  const int num_kb = a.taps * cblk;
+  uint32_t ncols = 32;
+  while ((int)ncols < a.BN) ncols <<= 1;
+
+  // patch coordinates
+  int t = blockIdx.x;
+  const int tx = t % a.tiles_x; t /= a.tiles_x;
+  const int ty = t % a.tiles_y; t /= a.tiles_y;
+  const int b0 = t * a.TB, y0 = ty * a.TH, x0 = tx * a.TW;
+  const int n0 = blockIdx.y * a.BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmW);
+    if (a.c1) prefetch_tmap(&tmA1);
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      const int half = a.ks / 2;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / cblk, cb = kb % cblk;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+        const int dy = tap / a.ks - half, dx = tap % a.ks - half;
+        if (cb < cblk0) tma_load_4d(sa, &tmA0, full0 + 8 * stage, cb * KC, x0 + dx, y0 + dy, b0);
+        else tma_load_4d(sa, &tmA1, full0 + 8 * stage, (cb - cblk0) * KC, x0 + dx, y0 + dy, b0);
+        tma_load_3d(sb, &tmW, full0 + 8 * stage, cb * KC, n0, tap);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      const uint32_t idesc = make_idesc(128, a.BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+        const uint64_t ad = make_desc(sa, 16, SBO, LAYOUT), bd = make_desc(sb, 16, SBO, LAYOUT);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k)  // +32 B per 16-element K step inside the swizzled row
+          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(accbar);  // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int xl = row % a.TW, yl = (row / a.TW) % a.TH, bl = row / (a.TW * a.TH);
+    const int bb = b0 + bl, yy = y0 + yl, xx = x0 + xl;
+    const bool valid = bb < a.B && yy < a.H && xx < a.W;
+    const int64_t pix = ((int64_t)bb * a.H + yy) * a.W + xx;
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < a.BN; cb += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r);
+      if (valid) {
+        const int n = n0 + cb;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
+        }
+        if (a.res) {
+          const bf16* rp = a.res + pix * a.ld_res + n;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            Vec8<bf16>::load(rp + g * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.mask) {
+          const bf16* mp = a.mask + pix * a.ld_mask + n;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            Vec8<bf16>::load(mp + g * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
+          }
+        }
+        bf16* yp = a.y + pix * a.ldy + n;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
+          Vec8<bf16>::store(yp + g * 8, f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------ weight-gradient kernel
+struct TcWgradArgs {
+  int c0, c1, cout;
+  int taps, ks;
+  int B, H, W;
+  int TW, TH;             // K tile = TW*TH = 64 pixels of one image
+  int tiles_x, tiles_y;   // per image
+  int tiles_total, tiles_per_split;
+  int stages;
+  float* part;            // [split][tap][cout][cin] f32
+};
+
+constexpr int WG_P = 64;                         // pixels (K) per stage
+constexpr uint32_t WG_GROUP_BYTES = WG_P * 64;   // one 32-channel x 64-pixel SWIZZLE_64B box
+constexpr uint32_t WG_A_BYTES = 4 * WG_GROUP_BYTES;
+
+__global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
+                                                            const __grid_constant__ CUtensorMap tmX1,
+                                                            const __grid_constant__ CUtensorMap tmDY,
+                                                            TcWgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]),
+                 accbar = smem_u32(&bars[2 * MAX_STAGES]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t B_BYTES = (uint32_t)a.taps * WG_GROUP_BYTES;
+  const uint32_t STAGE_BYTES = WG_A_BYTES + B_BYTES;
+  uint32_t ncols = 32;
+  while ((int)ncols < a.taps * 32) ncols <<= 1;
+
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 128, split = blockIdx.z;
+  const int cin = a.c0 + a.c1;
+  const int ngroups = min(4, (a.cout - co0) / 32);  // real 32-channel groups of dy in this co block
+  const int t_beg = split * a.tiles_per_split;
+  const int t_end = min(a.tiles_total, t_beg + a.tiles_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmX0);
+    prefetch_tmap(&tmDY);
+    if (a.c1) prefetch_tmap(&tmX1);
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int half = a.ks / 2;
+      const bool src1 = ci0 >= a.c0;
+      const CUtensorMap* tmX = src1 ? &tmX1 : &tmX0;
+      const int cx = src1 ? ci0 - a.c0 : ci0;
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t_beg; t < t_end; ++t) {
+        int r = t;
+        const int tx = r % a.tiles_x; r /= a.tiles_x;
+        const int ty = r % a.tiles_y; r /= a.tiles_y;
+        const int b = r, y0 = ty * a.TH, x0 = tx * a.TW;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + WG_A_BYTES;
+        mbar_expect_tx(full0 + 8 * stage, (uint32_t)(ngroups + a.taps) * WG_GROUP_BYTES);
+        for (int g = 0; g < ngroups; ++g)
+          tma_load_4d(sa + g * WG_GROUP_BYTES, &tmDY, full0 + 8 * stage, co0 + g * 32, x0, y0, b);
+        for (int tap = 0; tap < a.taps; ++tap)
+          tma_load_4d(sb + tap * WG_GROUP_BYTES, tmX, full0 + 8 * stage, cx, x0 + tap % a.ks - half,
+                      y0 + tap / a.ks - half, b);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A = dy  [K=64 px][M=128 co]  MN-major SWIZZLE_64B: 4 groups of 32 channels, LBO = group pitch,
+      //                               SBO = 8 pixel rows * 64 B
+      // B = x   [K=64 px][N=32 ci]   MN-major SWIZZLE_64B
+      const uint32_t idesc = make_idesc(128, 32, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (int t = t_beg; t < t_end; ++t) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + WG_A_BYTES;
+        for (int tap = 0; tap < a.taps; ++tap) {
+#pragma unroll
+          for (int k = 0; k < WG_P / 16; ++k) {  // 16 pixel rows * 64 B = 1024 B per K step
+            const uint64_t ad = make_desc(sa + k * 1024, WG_GROUP_BYTES, 512, 4u);
+            const uint64_t bd = make_desc(sb + tap * WG_GROUP_BYTES + k * 1024, WG_GROUP_BYTES, 512, 4u);
+            umma_bf16(tmem_base + (uint32_t)(tap * 32), ad, bd, idesc, (!first || k != 0) ? 1u : 0u);
+          }
+        }
+        first = false;
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(accbar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    const bool has_work = t_end > t_beg;
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    for (int tap = 0; tap < a.taps; ++tap) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * 32), r);
+      if (co < a.cout) {
+        float* o = a.part + (((int64_t)split * a.taps + tap) * a.cout + co) * cin + ci0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = has_work ? make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(o + j) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int taps,
+                                       int cout, int cin, int accumulate) {
+  const int64_t n = (int64_t)taps * cout * cin;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * n + i];
+  const int64_t o = ((int64_t)co * cin + ci) * taps + tap;
+  dw[o] = accumulate ? dw[o] + s : s;
+}
+
+// ------------------------------------------------------------------ host side: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// NHWC bf16 activation view [B][H][W][C] with pixel stride ld; box = (cbox, tw, th, tb)
+int make_act_map(CUtensorMap* tm, const void* ptr, int C, int ld, int B, int H, int W, int cbox, int tw, int th,
+                 int tb, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  PUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cbox, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d) -> %d",
+              C, ld, B, H, W, cbox, tw, th, tb, (int)r);
+  return 0;
+}
+
+int make_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int taps, int kbox, int nbox,
+                    CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  PUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kbox, (cuuint32_t)nbox, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights K=%d N=%d taps=%d box=%d,%d) -> %d", K, N, taps, kbox,
+              nbox, (int)r);
+  return 0;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int pick_bn(int n) {
+  for (int bn : {256, 128, 64, 32})
+    if (n % bn == 0) return bn;
+  return 0;
+}
+
+// a 128-pixel patch (tw x th x tb) that tiles [B][H][W] exactly in y and x
+bool pick_patch(int H, int W, int target, int& tw, int& th, int& tb) {
+  tw = W < 16 ? W : 16;
+  if (W % tw) return false;
+  th = target / tw;
+  if (th > H) th = H;
+  if (H % th) return false;
+  tb = target / (tw * th);
+  return tw * th * tb == target && tb >= 1;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvParams& p, int dtype) {
+  if (dtype != PUB_BF16) return false;
+  if (p.ks != 1 && p.ks != 3) return false;
+  const int cin = p.c0 + p.c1;
+  if (p.c0 % 32 || p.c1 % 32 || cin < 32 || pick_bn(p.cout) == 0) return false;
+  if (p.ld0 % 8 || (p.x1 && p.ld1 % 8) || p.ldy % 8) return false;
+  if (!aligned16(p.x0) || !aligned16(p.x1) || !aligned16(p.w) || !aligned16(p.y)) return false;
+  if ((p.res && (p.ld_res % 8 || !aligned16(p.res))) || (p.mask && (p.ld_mask % 8 || !aligned16(p.mask))))
+    return false;
+  int tw, th, tb;
+  if (!pick_patch(p.H, p.W, 128, tw, th, tb)) return false;
+  if (tb > 1 && tb > 256) return false;
+  return true;
+}
+
+int conv_tc(const ConvParams& p, cudaStream_t s) {
+  PUB_REQUIRE(conv_tc_supported(p, PUB_BF16), "conv_tc: unsupported shape (c0=%d c1=%d cout=%d H=%d W=%d ks=%d)", p.c0,
+              p.c1, p.cout, p.H, p.W, p.ks);
+  const int cin = p.c0 + p.c1;
+  const int KC = (p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32;
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  TcConvArgs a{};
+  a.c0 = p.c0; a.c1 = p.c1; a.ks = p.ks; a.taps = p.ks * p.ks;
+  a.B = p.B; a.H = p.H; a.W = p.W;
+  pick_patch(p.H, p.W, 128, a.TW, a.TH, a.TB);
+  a.tiles_x = p.W / a.TW; a.tiles_y = p.H / a.TH;
+  a.BN = pick_bn(p.cout); a.cout = p.cout;
+  a.bias = p.bias; a.res = (const bf16*)p.res; a.ld_res = p.ld_res;
+  a.mask = (const bf16*)p.mask; a.ld_mask = p.ld_mask;
+  a.y = (bf16*)p.y; a.ldy = p.ldy; a.relu = p.relu;
+  const size_t stage_bytes = (size_t)(128 + a.BN) * KC * 2;
+  int stages = (int)(98304 / stage_bytes);
+  if (stages < 2) stages = 2;
+  if (stages > 6) stages = 6;
+  a.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024;
+
+  CUtensorMap tmA0, tmA1, tmW;
+  PUB_TRY(make_act_map(&tmA0, p.x0, p.c0, p.ld0, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
+  if (p.c1) PUB_TRY(make_act_map(&tmA1, p.x1, p.c1, p.ld1, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
+  else tmA1 = tmA0;
+  PUB_TRY(make_weight_map(&tmW, p.w, cin, p.cout, a.taps, KC, a.BN, sw));
+
+  dim3 grid(cdiv(p.B, a.TB) * a.tiles_x * a.tiles_y, p.cout / a.BN);
+  if (KC == 64) {
+    static bool attr = false;
+    if (!attr) { PUB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    conv_tc_kernel<64><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  } else {
+    static bool attr = false;
+    if (!attr) { PUB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    conv_tc_kernel<32><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  }
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------ wgrad host side
+namespace {
+struct WgPlan { int tw, th, tiles_x, tiles_y, tiles_total, nsplit, tiles_per_split, stages; size_t smem; };
+bool wgrad_plan(const WgradParams& p, WgPlan& pl) {
+  int tb;
+  if (!pick_patch(p.H, p.W, WG_P, pl.tw, pl.th, tb) || tb != 1) return false;
+  pl.tiles_x = p.W / pl.tw; pl.tiles_y = p.H / pl.th;
+  pl.tiles_total = p.B * pl.tiles_x * pl.tiles_y;
+  const int cin = p.c0 + p.c1;
+  const int ctas = (cin / 32) * cdiv(p.cout, 128);
+  int want = cdiv(2 * num_sms(), ctas);
+  if (want < 1) want = 1;
+  int max_split = pl.tiles_total / 4;  // at least 4 K tiles per CTA
+  if (max_split < 1) max_split = 1;
+  if (want > max_split) want = max_split;
+  pl.tiles_per_split = cdiv(pl.tiles_total, want);
+  pl.nsplit = cdiv(pl.tiles_total, pl.tiles_per_split);
+  const size_t stage = WG_A_BYTES + (size_t)p.ks * p.ks * WG_GROUP_BYTES;
+  pl.stages = (int)((200 * 1024) / stage);
+  if (pl.stages > 6) pl.stages = 6;
+  pl.smem = pl.stages * stage + 1024;
+  return pl.stages >= 2;
+}
+}  // namespace
+
+bool wgrad_tc_supported(const WgradParams& p, int dtype) {
+  if (dtype != PUB_BF16) return false;
+  if (p.ks != 1 && p.ks != 3) return false;
+  if (p.c0 % 32 || p.c1 % 32 || p.c0 + p.c1 < 32 || p.cout % 32) return false;
+  if (p.ld0 % 8 || (p.x1 && p.ld1 % 8) || p.ld_dy % 8) return false;
+  if (!aligned16(p.x0) || !aligned16(p.x1) || !aligned16(p.dy)) return false;
+  WgPlan pl;
+  return wgrad_plan(p, pl);
+}
+
+size_t wgrad_tc_workspace(const WgradParams& p) {
+  WgPlan pl;
+  if (!wgrad_plan(p, pl)) return 0;
+  const int64_t n = (int64_t)p.ks * p.ks * p.cout * (p.c0 + p.c1);
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  return align_up((size_t)pl.nsplit * n * sizeof(float), 256) + align_up((size_t)cdiv(M, 1024) * p.cout * 4, 256);
+}
+
+int wgrad_tc(const WgradParams& p, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
+  WgPlan pl;
+  PUB_REQUIRE(wgrad_tc_supported(p, PUB_BF16) && wgrad_plan(p, pl), "wgrad_tc: unsupported shape");
+  PUB_REQUIRE(ws_bytes >= wgrad_tc_workspace(p), "wgrad_tc: workspace too small");
+  const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
+  TcWgradArgs a{};
+  a.c0 = p.c0; a.c1 = p.c1; a.cout = p.cout; a.taps = taps; a.ks = p.ks;
+  a.B = p.B; a.H = p.H; a.W = p.W; a.TW = pl.tw; a.TH = pl.th;
+  a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
+  a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages;
+  a.part = (float*)ws;
+  CUtensorMap tmX0, tmX1, tmDY;
+  PUB_TRY(make_act_map(&tmX0, p.x0, p.c0, p.ld0, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, p.c1, p.ld1, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  else tmX1 = tmX0;
+  PUB_TRY(make_act_map(&tmDY, p.dy, p.cout, p.ld_dy, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  static bool attr = false;
+  if (!attr) { PUB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+  dim3 grid(cin / 32, cdiv(p.cout, 128), pl.nsplit);
+  wgrad_tc_kernel<<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
+  PUB_LAUNCH_CHECK();
+  const int64_t n = (int64_t)taps * p.cout * cin;
+  wgrad_tc_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(a.part, p.dw, pl.nsplit, taps, p.cout, cin, accumulate);
+  PUB_LAUNCH_CHECK();
+  if (p.dbias) {
+    float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * n * sizeof(float), 256));
+    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, PUB_BF16, bpart, p.dbias, accumulate, s));
+  }
+  return 0;
+}
+
+}  // namespace pub

@@ -1,0 +1,84 @@
+// Internal launcher interface shared by the engine (.cu) files.  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace pub {
+
+struct ConvParams {
+  const void* x0; const void* x1; int c0, c1, ld0, ld1;
+  const void* w; const float* bias;
+  const void* res; int ld_res;
+  const void* mask; int ld_mask;
+  void* y; int ldy;
+  int B, H, W, cout, ks, relu;
+};
+
+struct WgradParams {
+  const void* x0; const void* x1; int c0, c1, ld0, ld1;
+  const void* dy; int ld_dy;
+  float* dw; float* dbias;
+  int B, H, W, cout, ks;
+};
+
+// ---- conv_simt.cu
+int conv_simt(const ConvParams& p, int dtype, cudaStream_t s);
+size_t wgrad_simt_workspace(const WgradParams& p);
+int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, float* out, int accumulate, cudaStream_t s);
+int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype, int tflip, cudaStream_t s);
+int nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, int ldy, int B, int H, int W, int dtype,
+                 cudaStream_t s);
+int nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, int dtype, int accumulate, cudaStream_t s);
+
+// ---- conv_tc.cu (tcgen05 / TMEM / TMA)
+bool conv_tc_supported(const ConvParams& p, int dtype);
+int conv_tc(const ConvParams& p, cudaStream_t s);
+bool wgrad_tc_supported(const WgradParams& p, int dtype);
+size_t wgrad_tc_workspace(const WgradParams& p);
+int wgrad_tc(const WgradParams& p, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+
+// dispatchers (api.cu)
+int conv_forward(const ConvParams& p, int dtype, int backend, cudaStream_t s);
+size_t wgrad_workspace(const WgradParams& p, int dtype, int backend);
+int wgrad(const WgradParams& p, int dtype, int backend, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+
+// ---- norm.cu : GroupNorm (+FiLM) + SiLU (+dropout) (+2x resample), forward and backward
+struct GnParams {
+  const void* x0; const void* x1; int c0, c1, ld0, ld1;  // GN input (virtual concat), at the INPUT resolution
+  int B, H, W, groups;                                    // input resolution
+  const float* gamma; const float* beta;                  // [C]
+  const float* film;                                      // [2C] (scale | shift) or nullptr
+  int resample;                                           // 0 none, 1 down (2x2 mean), 2 up (nearest 2x)
+  float p_drop; uint64_t seed; uint64_t subseq;           // dropout on the activated output (p_drop = 0: off)
+  float* stats;                                           // [B][G][2] mean, rstd   (saved for backward)
+  float* coef;                                            // [B][C][2] scratch: per-(b,c) affine a,b
+  float* partial;                                         // scratch for the two-stage reductions
+};
+size_t gn_partial_floats(int B, int C, int H, int W);
+// y [B,H',W',C] NHWC dt (contiguous, ld = C)
+int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s);
+// dy: gradient wrt y (at the OUTPUT resolution, contiguous ld = C).  dx [B,H,W,C] contiguous; addend
+// (optional, NHWC dt, ld_add) is added to dx.  dgamma/dbeta [C], dfilm [2C] overwritten.
+int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend, int ld_add, float* dgamma,
+                float* dbeta, float* dfilm, int dtype, cudaStream_t s);
+
+// ---- elementwise.cu
+int resample2x(const void* x, int ld, int C, void* y, int B, int H, int W, int mode, int dtype, cudaStream_t s);
+// backward of resample2x: dx (input res [B,H,W,C]) from dy (output res); mode as forward
+int resample2x_bwd(const void* dy, int ld, int C, void* dx, int B, int H, int W, int mode, int dtype, cudaStream_t s);
+int add_views(const void* a, int lda, const void* b, int ldb, void* y, int ldy, int C, int64_t M, int dtype,
+              cudaStream_t s);
+int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cudaStream_t s);
+// dx[b,y,x,c] = dy[b,y/2,x/2,c] if x is the (first) argmax of its window and mask_src>0 ... see elementwise.cu
+int maxpool2_bwd(const void* x, const void* yp, const void* dy, void* dx, int C, int B, int H, int W, int dtype,
+                 cudaStream_t s);
+int relu_mask_inplace(void* dy, const void* y, int64_t n, int dtype, cudaStream_t s);
+int global_mean(const void* x, int C, int B, int64_t HW, float* out, float* partial, int dtype, cudaStream_t s);
+int global_mean_bwd(const float* dmean, const void* y_mask, int C, int B, int64_t HW, void* dx, int dtype,
+                    cudaStream_t s);
+int fill_zero(void* p, size_t bytes, cudaStream_t s);
+
+}  // namespace pub

@@ -1,0 +1,196 @@
+"""Probabilistic U-Net -- host-side mirror of the reference's ``prob_unet.py`` module API.
+
+Drop-in for /root/reference/src/prob_unet.py: same classes, constructor signature,
+sub-module / parameter names (391-entry ``state_dict``), attributes and ``forward`` /
+``elbo`` call conventions, so ``train_prob_unet_model.py`` and the latent-exploration
+scripts run unchanged.  All arithmetic is done by hand-written sm_100a kernels behind
+the C-ABI in ``include/probunet_b200.h``; there is no CPU fallback -- a missing
+``libprobunet_b200.so`` or a CPU tensor raises.
+
+Additive API (not in the reference): ``loss_type`` attribute selecting the ELBO variant
+(SURVEY.md 3.4 B1), ``sample(x, n)`` (U-Net + prior once, ``fcomb`` n times) and
+``compute_dtype``.
+"""
+import torch
+import torch.nn as nn
+from torch.distributions import Independent, Normal
+
+import _native
+from networks import UNet
+from prob_unet_utils import init_weights, afcrps_loss, crps_loss, wmse_ms_ssim_loss  # noqa: F401
+
+device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+
+
+class LatentGaussian(Independent):
+    """``Independent(Normal(loc, scale), 1)`` whose reparameterised draw is our Philox kernel.
+
+    Keeps the torch.distributions surface the reference scripts use (``.base_dist.loc``,
+    ``.base_dist.scale``, ``.rsample()``, ``kl_divergence``; src/latent_exploration_posterior.py:260-261)."""
+
+    def __init__(self, loc, scale):
+        super().__init__(Normal(loc=loc, scale=scale, validate_args=False), 1, validate_args=False)
+
+    def rsample(self, sample_shape=torch.Size(), eps=None):
+        if len(sample_shape) > 1:
+            raise NotImplementedError("rsample supports () or (n,) sample shapes")
+        n = sample_shape[0] if len(sample_shape) else None
+        z = _native.rsample(self.base_dist.loc, self.base_dist.scale, n or 1, eps)
+        return z if n is not None else z[0]
+
+    def sample(self, sample_shape=torch.Size()):
+        with torch.no_grad():
+            return self.rsample(sample_shape)
+
+
+class AxisAlignedConvGaussian(nn.Module):
+    """src/prob_unet.py:12-85: VGG-style conv encoder -> global mean -> (mu, log sigma) heads."""
+
+    def __init__(self, input_channels, num_filters, latent_dim, posterior=False, compute_dtype=None):
+        super().__init__()
+        self.input_channels = input_channels
+        self.num_filters = num_filters
+        self.latent_dim = latent_dim
+        self.posterior = posterior
+        if self.posterior:
+            self.input_channels += input_channels
+        self.contracting_path = nn.ModuleList()
+        layers, width = [], self.input_channels
+        for i, nf in enumerate(self.num_filters):
+            if i != 0:
+                layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+            for _ in range(3):
+                layers.append(nn.Conv2d(width, nf, kernel_size=3, padding=1))
+                layers.append(nn.ReLU(inplace=True))
+                width = nf
+        self.encoder = nn.Sequential(*layers)      # parameter container: indices 0,2,4,7,... as the reference
+        self.conv_mu = nn.Conv2d(num_filters[-1], latent_dim, kernel_size=1)
+        self.conv_log_sigma = nn.Conv2d(num_filters[-1], latent_dim, kernel_size=1)
+        self.apply(init_weights)
+        self.compute_dtype = compute_dtype
+        self._engine = None
+
+    def engine(self):
+        dt = _native.resolve_dtype(self.compute_dtype)
+        if self._engine is None or self._engine.dtype != dt:
+            self._engine = _native.EncoderEngine(self, dt)
+        return self._engine
+
+    def forward(self, x, target=None):
+        if not (self.posterior and target is not None):
+            target = None
+        mu, sigma = self.engine().forward(x, target)
+        return LatentGaussian(mu, sigma)
+
+
+class Fcomb(nn.Module):
+    """src/prob_unet.py:87-138: broadcast z over H,W, concat with the features, 3x 1x1 conv."""
+
+    def __init__(self, unet_output_channels, latent_dim, num_classes):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.num_classes = num_classes
+        self.channel_axis = 1
+        self.spatial_axes = [2, 3]
+        c = unet_output_channels
+        self.layers = nn.Sequential(
+            nn.Conv2d(c + latent_dim, c, kernel_size=1), nn.ReLU(inplace=True),
+            nn.Conv2d(c, c, kernel_size=1), nn.ReLU(inplace=True),
+            nn.Conv2d(c, num_classes, kernel_size=1))
+        self.apply(init_weights)
+
+    def tile(self, a, dim, n_tile):
+        """TensorFlow-style tile == repeat_interleave along ``dim`` (src/prob_unet.py:109-118).
+        Kept for the latent scripts (src/latent_exploration.py:524-525); not on the hot path."""
+        return torch.repeat_interleave(a, n_tile, dim=dim)
+
+    def forward(self, feature_map, z):
+        """feature_map [B,F,H,W] (may be a non-contiguous expand() view), z [B,L] -> [B,C,H,W]."""
+        return _native.fcomb_apply(self, feature_map, z.unsqueeze(0))[:, 0]
+
+    def forward_members(self, feature_map, z):
+        """z [M,B,L] -> [B,M,C,H,W]: one pass over the features for all M members."""
+        return _native.fcomb_apply(self, feature_map, z)
+
+
+class ProbabilisticUNet(nn.Module):
+    """src/prob_unet.py:140-381."""
+
+    def __init__(self, input_channels, num_classes, latent_dim, num_filters, model_channels, channel_mult,
+                 beta_0, beta_1, beta_2, loss_type="afcrps", compute_dtype=None):
+        super().__init__()
+        self.input_channels = input_channels
+        self.num_classes = num_classes
+        self.latent_dim = latent_dim
+        self.model_channels = model_channels
+        self.channel_mult = channel_mult
+        self.beta_0, self.beta_1, self.beta_2 = beta_0, beta_1, beta_2
+        self.loss_type = loss_type
+        self.unet = UNet(img_resolution=(128, 128), in_channels=input_channels, out_channels=num_filters[0],
+                         label_dim=1, model_channels=model_channels, channel_mult=channel_mult,
+                         use_diffuse=False, compute_dtype=compute_dtype).to(device)
+        self.prior = AxisAlignedConvGaussian(input_channels, num_filters, latent_dim, posterior=False,
+                                             compute_dtype=compute_dtype).to(device)
+        self.posterior = AxisAlignedConvGaussian(input_channels, num_filters, latent_dim, posterior=True,
+                                                 compute_dtype=compute_dtype).to(device)
+        self.fcomb = Fcomb(num_filters[0], latent_dim, num_classes).to(device)
+        self.prior_latent_space = None
+        self.posterior_latent_space = None
+
+    def set_compute_dtype(self, name):
+        self.unet.compute_dtype = self.prior.compute_dtype = self.posterior.compute_dtype = name
+
+    # src/prob_unet.py:194-224
+    def forward(self, x, target=None, t=None, training=True, eps=None):
+        feat = self.unet(x, _nhwc_out=True)
+        if training and target is not None:
+            self.posterior_latent_space = self.posterior(x, target)
+            z = self.posterior_latent_space.rsample(eps=eps)
+        else:
+            self.prior_latent_space = self.prior(x)
+            z = self.prior_latent_space.rsample(eps=eps)
+        return _native.fcomb_apply(self.fcomb, feat, z.unsqueeze(0))[:, 0]
+
+    @torch.no_grad()
+    def sample(self, x, n, eps=None):
+        """n prior members per field: U-Net and prior run once, fcomb n times -> [B,n,C,H,W]."""
+        feat = self.unet(x, _nhwc_out=True)
+        self.prior_latent_space = self.prior(x)
+        z = self.prior_latent_space.rsample((n,), eps=eps)
+        return _native.fcomb_apply(self.fcomb, feat, z)
+
+    def elbo(self, x, target, t=None, M=None, alpha=0.95, alpha_w=0.007, beta_w=0.048, lam_w=0.0, eps=None):
+        """ELBO = beta_0*recon + beta_1*KL(q||p) [+ beta_2*KL(q||N(0,I))]; the reconstruction
+        term and the return tuple follow ``self.loss_type`` exactly as the three variants in
+        the reference (src/prob_unet.py:229-267 "mse+ssim", :273-317 "afcrps"/"crps", :325-381 "l1").
+        ``eps`` [M,B,L] optionally injects the N(0,1) draws (parity tests)."""
+        lt = self.loss_type
+        if M is None:
+            M = 5 if lt in ("afcrps", "crps") else 1
+        if lt in ("afcrps", "crps") and M < 2:
+            raise ValueError(f"M must be at least 2 to compute afCRPS but got M={M}")
+        feat = self.unet(x, _nhwc_out=True)
+        self.prior_latent_space = self.prior(x)
+        self.posterior_latent_space = self.posterior(x, target)
+        q, p = self.posterior_latent_space.base_dist, self.prior_latent_space.base_dist
+        kl_div = _native.kl_normal(q.loc, q.scale, p.loc, p.scale)
+        if lt == "l1":
+            z = self.posterior_latent_space.rsample((1,), eps=eps)
+            out = _native.fcomb_apply(self.fcomb, feat, z)
+            l1, per_var = _native.l1_loss(out[:, 0], target)
+            kl2 = _native.kl_normal(q.loc, q.scale, torch.zeros_like(q.loc), torch.ones_like(q.scale))
+            total = self.beta_0 * l1 + self.beta_1 * torch.mean(kl_div) + self.beta_2 * torch.mean(kl2)
+            return total, per_var.detach().tolist(), kl_div, kl2
+        z = self.posterior_latent_space.rsample((M,), eps=eps)
+        ens = _native.fcomb_apply(self.fcomb, feat, z)                 # [B,M,C,H,W]
+        if lt in ("afcrps", "crps"):
+            crps = _native.ensemble_loss(ens, target, kind=lt, alpha=alpha)
+            total = self.beta_0 * crps + self.beta_1 * kl_div.mean()
+            return total, [crps.item()], kl_div
+        if lt == "mse+ssim":
+            recs = [_native.wmse_ms_ssim(ens[:, m], target, alpha_w, beta_w, lam_w, None) for m in range(M)]
+            recon = torch.stack([r[0] for r in recs]).mean()
+            total = self.beta_0 * recon + self.beta_1 * kl_div.mean()
+            return (total, [recon.detach().cpu().item()], kl_div,
+                    recs[-1][1].detach().cpu().item(), recs[-1][2].detach().cpu().item())
+        raise ValueError(f"unknown loss_type {lt!r}")

@@ -1,0 +1,126 @@
+"""Op-level parity of the convolution family (C ABI: pub_conv2d_forward / pub_conv2d_wgrad).
+
+Reference op: torch.nn.functional.conv2d in fp32 (TF32 off) -- the call the reference makes at
+src/networks.py:89 and src/prob_unet.py:41-46 -- and its autograd weight/bias gradients.
+Tolerances: fp32 path rel-err <= 1e-4, bf16 path <= 1e-2 (BASELINE.json north_star).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _setup():
+    import _native as N
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return N
+
+
+def _ref_conv(x_nhwc, w, b, res=None, relu=False, mask=None):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w, b, padding=w.shape[-1] // 2)
+    if res is not None:
+        y = y + res.float().permute(0, 3, 1, 2)
+    if relu:
+        y = F.relu(y)
+    if mask is not None:
+        y = y * (mask.float().permute(0, 3, 1, 2) > 0)
+    return y.permute(0, 2, 3, 1)
+
+
+CASES = [
+    # B, H, W, c0, c1, cout, ks
+    (2, 16, 16, 3, 0, 32, 3),
+    (2, 16, 16, 6, 0, 32, 3),
+    (2, 32, 32, 32, 0, 32, 3),
+    (2, 32, 32, 64, 0, 64, 3),
+    (3, 16, 16, 128, 0, 128, 3),
+    (2, 16, 16, 256, 0, 256, 3),
+    (2, 16, 16, 256, 256, 256, 3),
+    (2, 16, 16, 256, 128, 256, 1),
+    (2, 32, 32, 64, 32, 32, 3),
+    (2, 32, 32, 32, 0, 64, 1),
+    (3, 8, 8, 256, 0, 256, 3),      # 128-pixel patch spans two images, odd batch -> OOB batch rows
+    (2, 16, 16, 256, 0, 512, 3),    # N tiled 2 x 256 (data-gradient of a 512-channel concat input)
+    (2, 16, 16, 128, 0, 384, 3),    # N tiled 3 x 128
+    (1, 128, 128, 32, 0, 32, 3),
+    (5, 4, 4, 64, 0, 64, 3),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16"])
+def test_conv_forward(case, mode):
+    N = _setup()
+    B, H, W, c0, c1, cout, ks = case
+    dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
+    backend = N.BACKEND_TCGEN05 if mode == "tc_bf16" else N.BACKEND_SIMT
+    if mode == "tc_bf16" and (c0 % 32 or c1 % 32):
+        pytest.skip("tcgen05 path needs Cin % 32 == 0 (first layers run on the SIMT kernel)")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    # inputs are channel slices of wider buffers -> exercises the pixel-stride (ld) handling
+    buf0 = torch.randn(B, H, W, c0 + 32, device="cuda", generator=g).to(dt)
+    x0 = buf0[..., :c0]
+    x1 = torch.randn(B, H, W, c1, device="cuda", generator=g).to(dt) if c1 else None
+    w = torch.randn(cout, c0 + c1, ks, ks, device="cuda", generator=g) / ((c0 + c1) * ks * ks) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    res = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
+    mask = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
+    wp = N.pack_conv_weight(w, N.BF16 if dt == torch.bfloat16 else N.F32)
+    xin = x0 if x1 is None else torch.cat([x0, x1], dim=3)
+    wq = wp.float().permute(1, 2, 0).reshape(cout, c0 + c1, ks, ks)   # the (rounded) weights the kernel sees
+    tol = 1e-4 if dt == torch.float32 else 1e-2
+    for kw in (dict(), dict(res=res), dict(relu=True), dict(res=res, mask=mask)):
+        y = N.conv2d_nhwc(x0, wp, b, x1=x1, ksize=ks, backend=backend, **kw)
+        ref = _ref_conv(xin, wq, b, **kw)
+        torch.cuda.synchronize()
+        e = rel_err(y.float(), ref)
+        assert e < tol, f"{mode} {case} {list(kw)} rel_err={e:.3e}"
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] * c[1] * c[2] <= 4096 * 4])
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16"])
+def test_conv_wgrad(case, mode):
+    N = _setup()
+    B, H, W, c0, c1, cout, ks = case
+    dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
+    backend = N.BACKEND_TCGEN05 if mode == "tc_bf16" else N.BACKEND_SIMT
+    if mode == "tc_bf16" and (c0 % 32 or c1 % 32 or (H * W) % 64):
+        pytest.skip("tcgen05 wgrad needs Cin % 32 == 0 and 64-pixel K tiles")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x0 = torch.randn(B, H, W, c0, device="cuda", generator=g).to(dt)
+    x1 = torch.randn(B, H, W, c1, device="cuda", generator=g).to(dt) if c1 else None
+    dy = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
+    dw, db = N.conv2d_wgrad_nhwc(x0, dy, ks, x1=x1, backend=backend)
+    xin = (x0 if x1 is None else torch.cat([x0, x1], dim=3)).float().permute(0, 3, 1, 2)
+    w = torch.zeros(cout, c0 + c1, ks, ks, device="cuda", requires_grad=True)
+    bb = torch.zeros(cout, device="cuda", requires_grad=True)
+    F.conv2d(xin, w, bb, padding=ks // 2).backward(dy.float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    tol = 1e-4 if dt == torch.float32 else 2e-3   # inputs are identical bf16 values; only f32 summation order differs
+    assert rel_err(dw, w.grad) < tol, f"{mode} {case} dw rel_err={rel_err(dw, w.grad):.3e}"
+    assert rel_err(db, bb.grad) < tol, f"{mode} {case} db rel_err={rel_err(db, bb.grad):.3e}"
+
+
+def test_dgrad_via_transposed_pack():
+    """Data gradient = forward kernel on mirrored/transposed weights (pub_pack_conv_weight transpose_flip=1)."""
+    N = _setup()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H, W, cin, cout = 2, 16, 16, 64, 128
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g, requires_grad=True)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / 24
+    dy = torch.randn(B, H, W, cout, device="cuda", generator=g)
+    F.conv2d(x, w, padding=1).backward(dy.permute(0, 3, 1, 2))
+    for dt, backend, tol in ((torch.float32, N.BACKEND_SIMT, 1e-4), (torch.bfloat16, N.BACKEND_SIMT, 1e-2),
+                             (torch.bfloat16, N.BACKEND_TCGEN05, 1e-2)):
+        wt = N.pack_conv_weight(w, N.BF16 if dt == torch.bfloat16 else N.F32, transpose_flip=True)
+        dx = N.conv2d_nhwc(dy.to(dt), wt, None, ksize=3, backend=backend)
+        torch.cuda.synchronize()
+        e = rel_err(dx.float().permute(0, 3, 1, 2), x.grad)
+        assert e < tol, f"dgrad {dt} backend={backend} rel_err={e:.3e}"
