@@ -1,0 +1,375 @@
+// GroupNorm (+FiLM scale/shift) + SiLU (+dropout) (+2x box resample), forward and backward, NHWC.
+// Replaces F.group_norm / silu / addcmul / F.dropout / the depthwise resample convs of
+// src/networks.py:105-107,166-177,83-87 and what autograd derives from them.
+//
+// All reductions are two-stage with a fixed summation order (per-chunk partials -> finalize in
+// double), so results are run-to-run deterministic (no float atomics).
+//
+// HBM-bound by construction: the apply/backward passes read each element once as 16 B (bf16) or
+// 32 B (f32) vectors and write once; statistics add one extra read of x.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pub {
+
+namespace {
+
+constexpr int GN_NT = 256;
+constexpr int GN_ROWS = 256;  // pixels per statistics chunk
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const GnParams& p, int64_t pix, int v, float (&f)[8]) {
+  const int c = v * 8;
+  if (c < p.c0) Vec8<T>::load((const T*)p.x0 + pix * p.ld0 + c, f);
+  else Vec8<T>::load((const T*)p.x1 + pix * p.ld1 + (c - p.c0), f);
+}
+
+// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0)
+__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint64_t subseq, int64_t e, float p, bool (&keep)[8]) {
+  const uint4 r0 = Philox::gen(seed, subseq, (uint64_t)(e >> 2));
+  const uint4 r1 = Philox::gen(seed, subseq, (uint64_t)(e >> 2) + 1);
+  keep[0] = Philox::u01(r0.x) >= p; keep[1] = Philox::u01(r0.y) >= p;
+  keep[2] = Philox::u01(r0.z) >= p; keep[3] = Philox::u01(r0.w) >= p;
+  keep[4] = Philox::u01(r1.x) >= p; keep[5] = Philox::u01(r1.y) >= p;
+  keep[6] = Philox::u01(r1.z) >= p; keep[7] = Philox::u01(r1.w) >= p;
+}
+
+// ---------------------------------------------------------------- per-channel two-value partial sums
+// MODE 0: (x, x^2)            -- forward statistics
+// MODE 1: (du, du * xhat)     -- backward; du = g_y * silu'(a x + b) with g_y rebuilt from dy
+template <typename T, int MODE>
+__global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* __restrict__ dy, float* __restrict__ part) {
+  extern __shared__ float sm[];  // [ppi][V][16]
+  const int C = p.c0 + p.c1, V = C / 8;
+  const int ppi = GN_NT / V;  // pixels per iteration
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int HW = p.H * p.W;
+  const int r0 = chunk * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+  const int t = threadIdx.x;
+  const int v = t % V, pr = t / V;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (pr < ppi) {
+    const int cpg = C / p.groups;
+    for (int r = r0 + pr; r < r1; r += ppi) {
+      const int64_t pix = (int64_t)b * HW + r;
+      float x[8];
+      load_vec<T>(p, pix, v, x);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] += x[j] * x[j]; }
+      } else {
+        // rebuild g_y (gradient wrt the activated output at input resolution)
+        float g[8];
+        const int yy = r / p.W, xx = r % p.W;
+        if (p.resample == 0) {
+          Vec8<T>::load(dy + pix * C + v * 8, g);
+        } else if (p.resample == 1) {  // forward was 2x2 mean
+          const int64_t q = ((int64_t)b * (p.H / 2) + yy / 2) * (p.W / 2) + xx / 2;
+          Vec8<T>::load(dy + q * C + v * 8, g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+        } else {  // forward was nearest 2x upsample
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = 0.f;
+          for (int d = 0; d < 4; ++d) {
+            const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
+            float h[8];
+            Vec8<T>::load(dy + q * C + v * 8, h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += h[j];
+          }
+        }
+        if (p.p_drop > 0.f) {
+          bool keep[8];
+          dropout_keep8(p.seed, p.subseq, pix * C + v * 8, p.p_drop, keep);
+          const float inv = 1.f / (1.f - p.p_drop);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = v * 8 + j;
+          const float2 ab = *reinterpret_cast<const float2*>(p.coef + ((int64_t)b * C + c) * 2);
+          const float2 st = *reinterpret_cast<const float2*>(p.stats + ((int64_t)b * p.groups + c / cpg) * 2);
+          const float du = g[j] * silu_grad_f(ab.x * x[j] + ab.y);
+          s1[j] += du;
+          s2[j] += du * (x[j] - st.x) * st.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sm[(pr * V + v) * 16 + j] = s1[j]; sm[(pr * V + v) * 16 + 8 + j] = s2[j]; }
+  }
+  __syncthreads();
+  // thread (v, j2) sums over pr in fixed order
+  for (int i = t; i < V * 16; i += GN_NT) {
+    float s = 0.f;
+    for (int q = 0; q < ppi; ++q) s += sm[q * V * 16 + i];
+    const int vv = i / 16, jj = i % 16;
+    const int c = vv * 8 + (jj & 7), which = jj >> 3;
+    part[(((int64_t)b * gridDim.x + chunk) * C + c) * 2 + which] = s;
+  }
+}
+
+// one warp per (b, g): mean / rstd, then the per-channel affine  y = silu(a x + b)
+__global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, int nchunk) {
+  const int C = p.c0 + p.c1, cpg = C / p.groups;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= p.B * p.groups) return;
+  const int b = wid / p.groups, g = wid % p.groups;
+  double s = 0.0, ss = 0.0;
+  for (int i = lane; i < nchunk * cpg; i += 32) {
+    const int k = i / cpg, c = g * cpg + i % cpg;
+    const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
+    s += (double)v.x; ss += (double)v.y;
+  }
+  s = warp_sum_d(s); ss = warp_sum_d(ss);
+  const double n = (double)cpg * p.H * p.W;
+  const double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+  const float meanf = (float)mean;
+  if (lane == 0) { p.stats[((int64_t)b * p.groups + g) * 2] = meanf; p.stats[((int64_t)b * p.groups + g) * 2 + 1] = rstd; }
+  for (int i = lane; i < cpg; i += 32) {
+    const int c = g * cpg + i;
+    const float sc = p.film ? 1.f + p.film[c] : 1.f, sh = p.film ? p.film[C + c] : 0.f;
+    const float ga = p.gamma[c], be = p.beta[c];
+    p.coef[((int64_t)b * C + c) * 2] = rstd * ga * sc;
+    p.coef[((int64_t)b * C + c) * 2 + 1] = (be - meanf * rstd * ga) * sc + sh;
+  }
+}
+
+// y = resample(dropout(silu(a x + b)))
+template <typename T>
+__global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restrict__ y) {
+  const int C = p.c0 + p.c1, V = C / 8;
+  const int HW = p.H * p.W;
+  const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+  if (p.resample != 1) {
+    const int64_t total = (int64_t)p.B * HW * V;
+    for (int64_t i = (int64_t)blockIdx.x * GN_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * GN_NT) {
+      const int v = (int)(i % V);
+      const int64_t pix = i / V;
+      const int b = (int)(pix / HW);
+      float x[8], o[8];
+      load_vec<T>(p, pix, v, x);
+      const float* cf = p.coef + ((int64_t)b * C + v * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = silu_f(cf[2 * j] * x[j] + cf[2 * j + 1]);
+      if (p.p_drop > 0.f) {
+        bool keep[8];
+        dropout_keep8(p.seed, p.subseq, pix * C + v * 8, p.p_drop, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
+      }
+      if (p.resample == 0) {
+        Vec8<T>::store(y + pix * C + v * 8, o);
+      } else {  // nearest 2x upsample: write the 2x2 children
+        const int r = (int)(pix % HW), yy = r / p.W, xx = r % p.W;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
+          Vec8<T>::store(y + q * C + v * 8, o);
+        }
+      }
+    }
+  } else {  // 2x2 mean of the activated values
+    const int Ho = p.H / 2, Wo = p.W / 2;
+    const int64_t total = (int64_t)p.B * Ho * Wo * V;
+    for (int64_t i = (int64_t)blockIdx.x * GN_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * GN_NT) {
+      const int v = (int)(i % V);
+      const int64_t q = i / V;
+      const int xo = (int)(q % Wo), yo = (int)((q / Wo) % Ho), b = (int)(q / ((int64_t)Wo * Ho));
+      const float* cf = p.coef + ((int64_t)b * C + v * 8) * 2;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t pix = ((int64_t)b * p.H + yo * 2 + (d >> 1)) * p.W + xo * 2 + (d & 1);
+        float x[8];
+        load_vec<T>(p, pix, v, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += silu_f(cf[2 * j] * x[j] + cf[2 * j + 1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
+      Vec8<T>::store(y + q * C + v * 8, o);
+    }
+  }
+}
+
+// backward finalize 1: per (b, g) -> bcoef[b][c] = (c1, c2, c3):  dx = c1*du + c2*x + c3
+__global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef) {
+  const int C = p.c0 + p.c1, cpg = C / p.groups;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= p.B * p.groups) return;
+  const int b = wid / p.groups, g = wid % p.groups;
+  double m1 = 0.0, m2 = 0.0;
+  for (int i = lane; i < nchunk * cpg; i += 32) {
+    const int k = i / cpg, c = g * cpg + i % cpg;
+    const float sc = p.film ? 1.f + p.film[c] : 1.f;
+    const double gp = (double)p.gamma[c] * sc;
+    const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
+    m1 += gp * (double)v.x; m2 += gp * (double)v.y;
+  }
+  m1 = warp_sum_d(m1); m2 = warp_sum_d(m2);
+  const double n = (double)cpg * p.H * p.W;
+  m1 /= n; m2 /= n;
+  const float mean = p.stats[((int64_t)b * p.groups + g) * 2], rstd = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
+  const float c2 = (float)(-(double)rstd * rstd * m2);
+  const float c3 = (float)(-(double)rstd * m1 + (double)rstd * rstd * m2 * mean);
+  for (int i = lane; i < cpg; i += 32) {
+    const int c = g * cpg + i;
+    const float sc = p.film ? 1.f + p.film[c] : 1.f;
+    float* o = bcoef + ((int64_t)b * C + c) * 3;
+    o[0] = rstd * p.gamma[c] * sc; o[1] = c2; o[2] = c3;
+  }
+}
+
+// backward finalize 2: per channel parameter gradients (sum over batch and chunks, fixed order)
+__global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, float* __restrict__ dfilm) {
+  const int C = p.c0 + p.c1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < p.B; ++b)
+    for (int k = 0; k < nchunk; ++k) {
+      const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
+      s1 += (double)v.x; s2 += (double)v.y;
+    }
+  const float sc = p.film ? 1.f + p.film[c] : 1.f;
+  dgamma[c] = (float)(s2 * sc);
+  dbeta[c] = (float)(s1 * sc);
+  if (dfilm) {
+    dfilm[c] = (float)((double)p.gamma[c] * s2 + (double)p.beta[c] * s1);  // d scale
+    dfilm[C + c] = (float)s1;                                              // d shift
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GN_NT) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
+                                                             const float* __restrict__ bcoef, T* __restrict__ dx,
+                                                             const T* __restrict__ addend, int ld_add) {
+  const int C = p.c0 + p.c1, V = C / 8;
+  const int HW = p.H * p.W;
+  const int64_t total = (int64_t)p.B * HW * V;
+  const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * GN_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * GN_NT) {
+    const int v = (int)(i % V);
+    const int64_t pix = i / V;
+    const int b = (int)(pix / HW), r = (int)(pix % HW), yy = r / p.W, xx = r % p.W;
+    float x[8], g[8];
+    load_vec<T>(p, pix, v, x);
+    if (p.resample == 0) {
+      Vec8<T>::load(dy + pix * C + v * 8, g);
+    } else if (p.resample == 1) {
+      const int64_t q = ((int64_t)b * (p.H / 2) + yy / 2) * (p.W / 2) + xx / 2;
+      Vec8<T>::load(dy + q * C + v * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
+        float h[8];
+        Vec8<T>::load(dy + q * C + v * 8, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += h[j];
+      }
+    }
+    if (p.p_drop > 0.f) {
+      bool keep[8];
+      dropout_keep8(p.seed, p.subseq, pix * C + v * 8, p.p_drop, keep);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
+    }
+    const float* cf = p.coef + ((int64_t)b * C + v * 8) * 2;
+    const float* bc = bcoef + ((int64_t)b * C + v * 8) * 3;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float du = g[j] * silu_grad_f(cf[2 * j] * x[j] + cf[2 * j + 1]);
+      o[j] = bc[3 * j] * du + bc[3 * j + 1] * x[j] + bc[3 * j + 2];
+    }
+    if (addend) {
+      float ad[8];
+      Vec8<T>::load(addend + pix * ld_add + v * 8, ad);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += ad[j];
+    }
+    Vec8<T>::store(dx + pix * C + v * 8, o);
+  }
+}
+
+int check(const GnParams& p) {
+  const int C = p.c0 + p.c1;
+  PUB_REQUIRE(C % 8 == 0 && p.c0 % 8 == 0 && C / 8 <= GN_NT, "GroupNorm kernel needs C %% 8 == 0 and C <= 2048 (C=%d c0=%d)", C, p.c0);
+  PUB_REQUIRE(p.groups > 0 && C % p.groups == 0, "GroupNorm: C=%d not divisible by groups=%d", C, p.groups);
+  PUB_REQUIRE(p.ld0 % 8 == 0 && (p.c1 == 0 || p.ld1 % 8 == 0), "GroupNorm: pixel strides must be multiples of 8");
+  PUB_REQUIRE(p.resample != 1 || (p.H % 2 == 0 && p.W % 2 == 0), "GroupNorm: 2x down needs even H, W");
+  return 0;
+}
+
+inline int nchunks(const GnParams& p) { return cdiv((int64_t)p.H * p.W, GN_ROWS); }
+inline int grid_for(int64_t n) {
+  int64_t g = (n + GN_NT - 1) / GN_NT;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(g < cap ? g : cap);
+}
+
+}  // namespace
+
+size_t gn_partial_floats(int B, int C, int H, int W) {
+  return (size_t)B * cdiv((int64_t)H * W, GN_ROWS) * C * 2 + (size_t)B * C * 3;
+}
+
+int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
+  PUB_TRY(check(p));
+  const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
+  const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
+  dim3 grid(nc, p.B);
+  if (dtype == PUB_BF16) gn_partial_kernel<bf16, 0><<<grid, GN_NT, smem, s>>>(p, nullptr, p.partial);
+  else gn_partial_kernel<float, 0><<<grid, GN_NT, smem, s>>>(p, nullptr, p.partial);
+  PUB_LAUNCH_CHECK();
+  gn_finalize_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc);
+  PUB_LAUNCH_CHECK();
+  const int64_t n = (int64_t)p.B * p.H * p.W * V / (p.resample == 1 ? 4 : 1);
+  if (dtype == PUB_BF16) gn_apply_kernel<bf16><<<grid_for(n), GN_NT, 0, s>>>(p, (bf16*)y);
+  else gn_apply_kernel<float><<<grid_for(n), GN_NT, 0, s>>>(p, (float*)y);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend, int ld_add, float* dgamma,
+                float* dbeta, float* dfilm, int dtype, cudaStream_t s) {
+  PUB_TRY(check(p));
+  const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
+  const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
+  float* bcoef = p.partial + (size_t)p.B * nc * C * 2;
+  dim3 grid(nc, p.B);
+  if (dtype == PUB_BF16) gn_partial_kernel<bf16, 1><<<grid, GN_NT, smem, s>>>(p, (const bf16*)dy, p.partial);
+  else gn_partial_kernel<float, 1><<<grid, GN_NT, smem, s>>>(p, (const float*)dy, p.partial);
+  PUB_LAUNCH_CHECK();
+  gn_bwd_group_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc, bcoef);
+  PUB_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<cdiv(C, 64), 64, 0, s>>>(p, p.partial, nc, dgamma, dbeta, dfilm);
+  PUB_LAUNCH_CHECK();
+  const int64_t n = (int64_t)p.B * p.H * p.W * V;
+  if (dx) {
+    if (dtype == PUB_BF16)
+      gn_bwd_apply_kernel<bf16><<<grid_for(n), GN_NT, 0, s>>>(p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
+    else
+      gn_bwd_apply_kernel<float><<<grid_for(n), GN_NT, 0, s>>>(p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
+    PUB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace pub
