@@ -221,3 +221,457 @@ def conv2d(x, weight, bias):
     xh = nchw_to_nhwc(x, dt)
     y = conv2d_nhwc(xh, pack_conv_weight(weight, dt), bias, ksize=weight.shape[-1])
     return nhwc_to_nchw(y)
+
+
+# ======================================================================================
+# Philox stream shared by rsample / dropout (seeded from torch's global seed on first use)
+# ======================================================================================
+class _Rng:
+    seed = None
+    offset = 0
+
+    @classmethod
+    def next(cls, n=1):
+        if cls.seed is None:
+            cls.seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        o = cls.offset
+        cls.offset += n
+        return cls.seed, o
+
+
+def manual_seed(seed):
+    """Re-seeds the engine's Philox streams (dropout masks, rsample eps)."""
+    _Rng.seed, _Rng.offset = int(seed) & 0x7FFFFFFFFFFFFFFF, 0
+
+
+# gradient-ready callback (set by parallel.GradSynchronizer): called with each engine's flat
+# gradient buffer right after its backward kernels have been enqueued
+grad_ready_callback = None
+
+
+def _flat_grads(params):
+    """One flat f32 buffer + per-parameter views (keeps a sub-network's gradients contiguous so
+    that they can be all-reduced with a single collective)."""
+    total = sum(p.numel() for p in params)
+    flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
+    views, off = [], 0
+    for p in params:
+        views.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+    return flat, views
+
+
+def _notify(flat):
+    if grad_ready_callback is not None:
+        grad_ready_callback(flat)
+
+
+# ======================================================================================
+# U-Net engine
+# ======================================================================================
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, training, nhwc_out, seed, nzero, *params):
+        B, _, H, W = x.shape
+        L = lib()
+        nbytes = L.pub_unet_workspace_bytes(eng.handle, B, H, W)
+        if nbytes == 0:
+            raise NativeError("pub_unet_workspace_bytes: " + L.pub_last_error().decode())
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        real = params[:len(params) - nzero]
+        if nhwc_out:
+            out = torch.empty(B, H, W, eng.out_ch, device=x.device, dtype=_TORCH_DT[eng.dtype])
+        else:
+            out = torch.empty(B, eng.out_ch, H, W, device=x.device, dtype=torch.float32)
+        xc = x.contiguous()
+        check(L.pub_unet_forward(eng.handle, B, H, W, ptr(xc), _ptr_table(real), ptr(out), int(not nhwc_out), ptr(ws),
+                                 C.c_size_t(nbytes), C.c_uint64(seed), int(training), _backend, stream()), "pub_unet_forward")
+        ctx.eng, ctx.ws, ctx.nbytes, ctx.shape = eng, ws, nbytes, (B, H, W)
+        ctx.training, ctx.nhwc_out, ctx.seed, ctx.nzero = training, nhwc_out, seed, nzero
+        ctx.x_req = ctx.needs_input_grad[1]
+        ctx.save_for_backward(*params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, (B, H, W) = ctx.eng, ctx.shape
+        params = ctx.saved_tensors
+        real = params[:len(params) - ctx.nzero]
+        zero = params[len(params) - ctx.nzero:]
+        flat, gviews = _flat_grads(list(real) + list(zero))
+        if ctx.nzero:
+            nz = sum(p.numel() for p in zero)
+            flat[flat.numel() - nz:].zero_()       # map_label / affine weights: exactly-zero gradients
+        dx = torch.empty(B, eng.in_ch, H, W, device=dout.device, dtype=torch.float32) if ctx.x_req else None
+        dout = dout.contiguous()
+        check(lib().pub_unet_backward(eng.handle, B, H, W, ptr(dout), int(not ctx.nhwc_out), _ptr_table(real),
+                                      _ptr_table(gviews[:len(real)]), ptr(dx), ptr(ctx.ws), C.c_size_t(ctx.nbytes),
+                                      C.c_uint64(ctx.seed), int(ctx.training), _backend, stream()), "pub_unet_backward")
+        ctx.ws = None
+        _notify(flat)
+        return (None, dx, None, None, None, None) + tuple(gviews)
+
+
+class UNetEngine:
+    """Owns the native plan of one networks.UNet module (block list + parameter order)."""
+
+    def __init__(self, module, dtype):
+        self.dtype = dtype
+        self.module = module
+        self.in_ch, self.out_ch = module.in_channels, module.out_channels
+        enc, dec = [], []
+        self.params, self.zero_params = [], []
+        self.block_keys = []
+        from networks import UNetBlock
+        for name, md, dst in ([(k, v, enc) for k, v in module.enc.items()] + [(k, v, dec) for k, v in module.dec.items()]):
+            d = UNetBlockDesc()
+            if isinstance(md, UNetBlock):
+                has_conv = md.skip is not None and md.skip.weight is not None
+                d.cin, d.cout, d.up, d.down = md.in_channels, md.out_channels, int(md.up), int(md.down)
+                d.has_skip_conv, d.is_conv = int(has_conv), 0
+                self.params += [md.norm0.weight, md.norm0.bias, md.conv0.weight, md.conv0.bias, md.affine.bias,
+                                md.norm1.weight, md.norm1.bias, md.conv1.weight, md.conv1.bias]
+                if has_conv:
+                    self.params += [md.skip.weight, md.skip.bias]
+                self.zero_params.append(md.affine.weight)
+            else:
+                d.cin, d.cout, d.is_conv = md.in_channels, md.out_channels, 1
+                self.params += [md.weight, md.bias]
+            dst.append(d)
+            self.block_keys.append(name)
+        self.params += [module.out_norm.weight, module.out_norm.bias, module.out_conv.weight, module.out_conv.bias]
+        if module.map_label is not None:
+            self.zero_params.append(module.map_label.weight)
+        h = C.c_void_p()
+        ea, da = (UNetBlockDesc * len(enc))(*enc), (UNetBlockDesc * len(dec))(*dec)
+        check(lib().pub_unet_create(ea, len(enc), da, len(dec), self.in_ch, self.out_ch, C.c_float(module.dropout),
+                                    dtype, C.byref(h)), "pub_unet_create")
+        self.handle = h
+        assert lib().pub_unet_num_params(h) == len(self.params)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and _lib is not None:
+                _lib.pub_unet_destroy(self.handle)
+        except Exception:
+            pass
+
+    def forward(self, x, training, nhwc_out=False, seed=None):
+        require_cuda(x, *self.params)
+        if x.dim() != 4 or x.shape[1] != self.in_ch:
+            raise ValueError(f"UNet expects [B,{self.in_ch},H,W], got {tuple(x.shape)}")
+        if seed is None:
+            seed = 0
+            if training and self.module.dropout > 0:
+                base, off = _Rng.next()
+                seed = (base * 0x9E3779B97F4A7C15 + off + 1) & 0x7FFFFFFFFFFFFFFF
+        self.last_seed = seed
+        return _UNetFn.apply(self, x.float(), bool(training), bool(nhwc_out), int(seed), len(self.zero_params),
+                             *self.params, *self.zero_params)
+
+    def dropout_mask(self, block_key, B, H, W, seed):
+        """Test hook: bool [B,C,h,w] keep-mask the engine uses in block `block_key` for `seed`."""
+        idx = self.block_keys.index(block_key)
+        md = {**dict(self.module.enc.items()), **dict(self.module.dec.items())}[block_key]
+        # output resolution of the block: walk the plan
+        h, w = H, W
+        for k in self.block_keys[:idx + 1]:
+            m = {**dict(self.module.enc.items()), **dict(self.module.dec.items())}[k]
+            if getattr(m, "down", False):
+                h, w = h // 2, w // 2
+            if getattr(m, "up", False):
+                h, w = h * 2, w * 2
+        out = torch.empty(B, md.out_channels, h, w, device="cuda", dtype=torch.uint8)
+        check(lib().pub_unet_dropout_mask(self.handle, idx, B, H, W, C.c_uint64(seed), ptr(out), stream()),
+              "pub_unet_dropout_mask")
+        return out.bool()
+
+
+# ======================================================================================
+# Gaussian encoder engine
+# ======================================================================================
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, target, *params):
+        B, cx, H, W = x.shape
+        L = lib()
+        nbytes = L.pub_encoder_workspace_bytes(eng.handle, B, H, W)
+        if nbytes == 0:
+            raise NativeError("pub_encoder_workspace_bytes: " + L.pub_last_error().decode())
+        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        mu = torch.empty(B, eng.latent, device=x.device, dtype=torch.float32)
+        sigma = torch.empty_like(mu)
+        xc = x.contiguous()
+        tc = target.contiguous() if target is not None else None
+        check(L.pub_encoder_forward(eng.handle, B, H, W, ptr(xc), cx, ptr(tc), tc.shape[1] if tc is not None else 0,
+                                    _ptr_table(params), ptr(mu), ptr(sigma), ptr(ws), C.c_size_t(nbytes), _backend,
+                                    stream()), "pub_encoder_forward")
+        ctx.eng, ctx.ws, ctx.nbytes, ctx.shape = eng, ws, nbytes, (B, H, W)
+        ctx.save_for_backward(*params)
+        return mu, sigma
+
+    @staticmethod
+    def backward(ctx, dmu, dsigma):
+        eng, (B, H, W) = ctx.eng, ctx.shape
+        params = ctx.saved_tensors
+        flat, gviews = _flat_grads(list(params))
+        dmu = (dmu if dmu is not None else torch.zeros(B, eng.latent, device=flat.device)).contiguous()
+        dsigma = (dsigma if dsigma is not None else torch.zeros(B, eng.latent, device=flat.device)).contiguous()
+        check(lib().pub_encoder_backward(eng.handle, B, H, W, ptr(dmu), ptr(dsigma), _ptr_table(params),
+                                         _ptr_table(gviews), ptr(ctx.ws), C.c_size_t(ctx.nbytes), _backend, stream()),
+              "pub_encoder_backward")
+        ctx.ws = None
+        _notify(flat)
+        return (None, None, None) + tuple(gviews)
+
+
+class EncoderEngine:
+    def __init__(self, module, dtype):
+        import torch.nn as nn
+        self.dtype, self.latent = dtype, module.latent_dim
+        convs = [m for m in module.encoder if isinstance(m, nn.Conv2d)]
+        self.params = []
+        for c in convs:
+            self.params += [c.weight, c.bias]
+        self.params += [module.conv_mu.weight, module.conv_mu.bias, module.conv_log_sigma.weight, module.conv_log_sigma.bias]
+        filt = (C.c_int32 * len(module.num_filters))(*module.num_filters)
+        h = C.c_void_p()
+        check(lib().pub_encoder_create(module.input_channels, filt, len(module.num_filters), module.latent_dim, dtype,
+                                       C.byref(h)), "pub_encoder_create")
+        self.handle = h
+        assert lib().pub_encoder_num_params(h) == len(self.params)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) is not None and _lib is not None:
+                _lib.pub_encoder_destroy(self.handle)
+        except Exception:
+            pass
+
+    def forward(self, x, target):
+        require_cuda(x, target, *self.params)
+        if x.requires_grad or (target is not None and target.requires_grad):
+            raise NativeError("gradients w.r.t. the encoder inputs are not implemented (the reference never needs them)")
+        return _EncoderFn.apply(self, x.float(), target.float() if target is not None else None, *self.params)
+
+
+# ======================================================================================
+# latent ops
+# ======================================================================================
+class _RsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, sigma, n, eps):
+        B, L = mu.shape
+        z = torch.empty(n, B, L, device=mu.device, dtype=torch.float32)
+        eps_out = torch.empty_like(z)
+        seed, off = _Rng.next()
+        e = eps.contiguous().float() if eps is not None else None
+        if e is not None and e.numel() != n * B * L:
+            raise ValueError(f"eps must have {n}x{B}x{L} elements")
+        check(lib().pub_rsample_forward(ptr(mu.contiguous()), ptr(sigma.contiguous()), ptr(e), C.c_uint64(seed),
+                                        C.c_uint64(off), n, B, L, ptr(z), ptr(eps_out), stream()), "pub_rsample_forward")
+        ctx.save_for_backward(eps_out)
+        ctx.dims = (n, B, L)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        (eps,) = ctx.saved_tensors
+        n, B, L = ctx.dims
+        dmu = torch.empty(B, L, device=dz.device, dtype=torch.float32)
+        dsig = torch.empty_like(dmu)
+        check(lib().pub_rsample_backward(ptr(dz.contiguous()), ptr(eps), n, B, L, ptr(dmu), ptr(dsig), stream()),
+              "pub_rsample_backward")
+        return dmu, dsig, None, None
+
+
+def rsample(mu, sigma, n, eps=None):
+    """z[n,B,L] = mu + sigma * eps, eps ~ N(0,1) from the engine's Philox stream (or injected)."""
+    require_cuda(mu, sigma)
+    return _RsampleFn.apply(mu, sigma, int(n), eps)
+
+
+class _KLFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mq, sq, mp, sp):
+        B, L = mq.shape
+        t = [a.contiguous().float() for a in (mq, sq, mp, sp)]
+        kl = torch.empty(B, device=mq.device, dtype=torch.float32)
+        check(lib().pub_kl_normal_forward(*[ptr(a) for a in t], B, L, ptr(kl), stream()), "pub_kl_normal_forward")
+        ctx.save_for_backward(*t)
+        return kl
+
+    @staticmethod
+    def backward(ctx, dkl):
+        t = ctx.saved_tensors
+        B, L = t[0].shape
+        outs = [torch.empty_like(t[0]) if ctx.needs_input_grad[i] else None for i in range(4)]
+        check(lib().pub_kl_normal_backward(ptr(dkl.contiguous()), *[ptr(a) for a in t], B, L, *[ptr(o) for o in outs],
+                                           stream()), "pub_kl_normal_backward")
+        return tuple(outs)
+
+
+def kl_normal(mq, sq, mp, sp):
+    """KL(N(mq,sq) || N(mp,sp)) summed over the latent axis -> [B]."""
+    require_cuda(mq, sq, mp, sp)
+    return _KLFn.apply(mq, sq, mp, sp)
+
+
+# ======================================================================================
+# fcomb
+# ======================================================================================
+def _fcomb_args(mod, feat, z, nhwc, out):
+    a = FcombArgs()
+    l0, l1, l2 = mod.layers[0], mod.layers[2], mod.layers[4]
+    M, B, L = z.shape
+    if nhwc:
+        _, H, W, F = feat.shape
+        a.feat_nchw, a.dtype = 0, (BF16 if feat.dtype == torch.bfloat16 else F32)
+    else:
+        _, F, H, W = feat.shape
+        a.feat_nchw, a.dtype = 1, F32
+        for i in range(4):
+            a.stride[i] = feat.stride(i)
+    a.feat, a.z = feat.data_ptr(), z.data_ptr()
+    a.w0, a.b0, a.w1, a.b1, a.w2, a.b2 = (t.data_ptr() for t in (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias))
+    a.out = out.data_ptr() if out is not None else None
+    a.B, a.H, a.W, a.F, a.L, a.C, a.M = B, H, W, F, L, l2.weight.shape[0], M
+    return a
+
+
+class _FcombFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, nhwc, feat, z, *params):
+        M, B, L = z.shape
+        H, W = (feat.shape[1], feat.shape[2]) if nhwc else (feat.shape[2], feat.shape[3])
+        if feat.shape[0] != B:
+            raise ValueError(f"feature batch {feat.shape[0]} != latent batch {B}")
+        if nhwc:
+            feat = feat.contiguous()
+        elif feat.dtype != torch.float32:
+            feat = feat.float()
+        z = z.contiguous().float()
+        out = torch.empty(B, M, mod.num_classes, H, W, device=z.device, dtype=torch.float32)
+        a = _fcomb_args(mod, feat, z, nhwc, out)
+        check(lib().pub_fcomb_forward(C.byref(a), stream()), "pub_fcomb_forward")
+        ctx.mod, ctx.nhwc = mod, nhwc
+        ctx.save_for_backward(feat, z, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, z, *params = ctx.saved_tensors
+        mod, nhwc = ctx.mod, ctx.nhwc
+        a = _fcomb_args(mod, feat, z, nhwc, None)
+        nbytes = lib().pub_fcomb_backward_workspace(C.byref(a))
+        ws = torch.empty(nbytes, device=z.device, dtype=torch.uint8)
+        flat, g = _flat_grads(params)
+        dz = torch.empty_like(z) if ctx.needs_input_grad[3] else None
+        dfeat = None
+        if ctx.needs_input_grad[2]:
+            dfeat = torch.empty(feat.shape, device=feat.device, dtype=feat.dtype)   # contiguous, same logical layout
+        check(lib().pub_fcomb_backward(C.byref(a), ptr(dout.contiguous()), ptr(dfeat), ptr(dz), ptr(g[0]), ptr(g[1]),
+                                       ptr(g[2]), ptr(g[3]), ptr(g[4]), ptr(g[5]), ptr(ws), C.c_size_t(nbytes), stream()),
+              "pub_fcomb_backward")
+        _notify(flat)
+        return (None, None, dfeat, dz) + tuple(g)
+
+
+def fcomb_apply(mod, feat, z, nhwc=False):
+    """feat: NHWC engine tensor (nhwc=True) or reference-layout [B,F,H,W] f32 (any strides);
+    z [M,B,L] -> [B,M,C,H,W] f32."""
+    require_cuda(feat, z, mod.layers[0].weight)
+    l0, l1, l2 = mod.layers[0], mod.layers[2], mod.layers[4]
+    return _FcombFn.apply(mod, bool(nhwc), feat, z, l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+
+
+# ======================================================================================
+# losses
+# ======================================================================================
+def _loss_ws(B, Cc, HW, device):
+    n = lib().pub_loss_workspace(B, Cc, HW)
+    return torch.empty(n, device=device, dtype=torch.uint8), n
+
+
+class _EnsLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ens, target, kind, alpha):
+        B, M, Cc, H, W = ens.shape
+        ens, target = ens.contiguous().float(), target.contiguous().float()
+        loss = torch.empty((), device=ens.device, dtype=torch.float32)
+        dens = torch.empty_like(ens) if ctx.needs_input_grad[0] else None
+        ws, n = _loss_ws(B, Cc, H * W, ens.device)
+        check(lib().pub_ensemble_loss(ptr(ens), ptr(target), B, M, Cc, H * W, kind, C.c_float(alpha), ptr(loss),
+                                      ptr(dens), ptr(ws), C.c_size_t(n), stream()), "pub_ensemble_loss")
+        ctx.dens = dens
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d, ctx.dens = ctx.dens, None
+        if d is None:
+            return None, None, None, None
+        check(lib().pub_scale_by_device_scalar(ptr(d), ptr(dloss.contiguous().float()), C.c_int64(d.numel()), stream()),
+              "pub_scale_by_device_scalar")
+        return d, None, None, None
+
+
+def ensemble_loss(ens, target, kind="afcrps", alpha=0.95):
+    require_cuda(ens, target)
+    if target.dim() != 4:
+        raise NotImplementedError("per-member targets ([B,M,C,H,W]) are not used by the reference elbo")
+    return _EnsLossFn.apply(ens, target, {"afcrps": 0, "crps": 1}[kind], float(alpha))
+
+
+class _L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, target):
+        B, Cc, H, W = out.shape
+        out, target = out.contiguous().float(), target.contiguous().float()
+        res = torch.empty(1 + Cc, device=out.device, dtype=torch.float32)
+        dout = torch.empty_like(out) if ctx.needs_input_grad[0] else None
+        ws, n = _loss_ws(B, Cc, H * W, out.device)
+        check(lib().pub_l1_loss(ptr(out), ptr(target), B, Cc, H * W, ptr(res), ptr(dout), ptr(ws), C.c_size_t(n),
+                                stream()), "pub_l1_loss")
+        ctx.dout = dout
+        loss, per_var = res[0], res[1:]
+        ctx.mark_non_differentiable(per_var)
+        return loss, per_var
+
+    @staticmethod
+    def backward(ctx, dl, _dpv):
+        d, ctx.dout = ctx.dout, None
+        if d is None:
+            return None, None
+        check(lib().pub_scale_by_device_scalar(ptr(d), ptr(dl.contiguous().float()), C.c_int64(d.numel()), stream()),
+              "pub_scale_by_device_scalar")
+        return d, None
+
+
+def l1_loss(out, target):
+    """-> (mean |out-target|, per-variable means [C])  (src/prob_unet.py:357-362)."""
+    require_cuda(out, target)
+    return _L1Fn.apply(out, target)
+
+
+def wmse_ms_ssim(pred, target, alpha, beta, lam, data_range):
+    raise NotImplementedError("the WMSE-MS-SSIM reconstruction term (src/prob_unet_utils.py:270-305) has no sm_100a "
+                              "kernel yet -- set model.loss_type to 'afcrps', 'crps' or 'l1' (see DESIGN.md, next rows)")
+
+
+# ======================================================================================
+# ensemble metrics
+# ======================================================================================
+def ensemble_metrics(preds, hr, lrinterp=None, std_hr=None):
+    """preds [T,M,3,H,W], hr [T,3,H,W] -> (crps [T,3], mae [T,3]) on the device.  With lrinterp/std_hr the
+    members are standardised residuals and are mapped to real units inside the kernel."""
+    require_cuda(preds, hr)
+    T, M, Cc, H, W = preds.shape
+    crps = torch.empty(T, Cc, device=preds.device, dtype=torch.float32)
+    mae = torch.empty_like(crps)
+    tr = lrinterp is not None
+    sh = std_hr.reshape(-1).contiguous().float() if tr else None
+    li = lrinterp.contiguous().float() if tr else None
+    check(lib().pub_ensemble_metrics(ptr(preds.contiguous().float()), ptr(hr.contiguous().float()), ptr(li), ptr(sh),
+                                     int(tr), T, M, Cc, H * W, ptr(crps), ptr(mae), stream()), "pub_ensemble_metrics")
+    return crps, mae

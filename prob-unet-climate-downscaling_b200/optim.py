@@ -1,0 +1,58 @@
+"""Fused multi-tensor AdamW: one kernel launch for all 391 tensors.
+
+Same update rule and defaults as ``torch.optim.AdamW`` which the reference constructs at
+src/main.py:103 and steps at src/train_prob_unet_model.py:139-141 (decoupled weight decay,
+bias correction, eps outside the sqrt).  ``grad_scale`` folds the 1/world_size of a
+data-parallel SUM all-reduce into the update.
+"""
+import ctypes as C
+
+import torch
+
+import _native as N
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.grad_scale = grad_scale
+        self._tables = {}
+
+    def _table(self, gi, plist):
+        """Device table of {p, g, m, v, n} rows; rebuilt only when a pointer changes."""
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
+        ent = self._tables.get(gi)
+        if ent is None or ent[0] != key:
+            rows = (N.AdamWEntry * len(plist))()
+            for i, p in enumerate(plist):
+                st = self.state[p]
+                rows[i].p, rows[i].g = p.data_ptr(), p.grad.data_ptr()
+                rows[i].m, rows[i].v, rows[i].n = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+            host = torch.frombuffer(bytearray(bytes(rows)), dtype=torch.uint8).pin_memory()
+            dev = host.to(plist[0].device, non_blocking=True)
+            ent = (key, dev, host, max(p.numel() for p in plist))
+            self._tables[gi] = ent
+        return ent
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for gi, group in enumerate(self.param_groups):
+            plist = [p for p in group["params"] if p.grad is not None]
+            if not plist:
+                continue
+            for p in plist:
+                N.require_cuda(p)
+                if not p.grad.is_contiguous() or p.grad.dtype != torch.float32 or not p.is_contiguous():
+                    raise N.NativeError("FusedAdamW needs contiguous f32 parameters and gradients")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+            group["step"] = group.get("step", 0) + 1
+            _, dev, _, maxn = self._table(gi, plist)
+            b1, b2 = group["betas"]
+            N.check(N.lib().pub_adamw_step(N.ptr(dev), len(plist), C.c_int64(maxn), C.c_float(group["lr"]), C.c_float(b1),
+                                           C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]),
+                                           int(group["step"]), C.c_float(self.grad_scale), N.stream()), "pub_adamw_step")
+        return loss

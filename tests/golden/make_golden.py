@@ -40,16 +40,8 @@ def import_reference():
     return prob_unet, prob_unet_utils
 
 
-def dezero(model, seed=43):
-    """SURVEY.md 8c oracle recipe step 2 (conv1 / out_conv weights are zero at init)."""
-    g = torch.Generator().manual_seed(seed)
-    with torch.no_grad():
-        for _, p in model.named_parameters():
-            if p.dim() > 1 and float(p.abs().sum()) == 0.0:
-                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
-        for n, p in model.named_parameters():
-            if n.endswith("affine.bias"):
-                p.add_(torch.randn(p.shape, generator=g) * 0.1)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import dezero  # noqa: E402
 
 
 class EpsInjector:
@@ -204,7 +196,8 @@ def main():
     out["B_wmse"], out["B_msssim_loss"] = float(wmse), float(msl)
     _, out["B_gradnorm"] = grads_summary(model)
     with torch.no_grad():
-        out["B_unet"] = model.unet(xb).numpy()
+        fb = model.unet(xb)
+        out["B_unet_sum"], out["B_unet_abssum"] = float(fb.double().sum()), float(fb.double().abs().sum())
 
     # ---- loss / metric known answers (in-tree reference functions) ----
     g = torch.Generator().manual_seed(47)

@@ -1,0 +1,131 @@
+"""The oracle (oracle/probunet_oracle.py) against the golden vectors generated from the REAL reference
+(tests/golden/make_golden.py).  CPU only.  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import canonical_model, rel_err, unpack_masks
+from oracle import probunet_oracle as O
+
+CFG = O.ProbUNetCfg()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    torch.set_num_threads(8)
+    m = canonical_model()
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def test_state_dict_matches_reference_init(golden):
+    import prob_unet
+    saved = prob_unet.device
+    prob_unet.device = torch.device("cpu")
+    try:
+        torch.manual_seed(42)
+        m = prob_unet.ProbabilisticUNet(3, 3, 32, [32, 64, 128, 256], 32, [1, 2, 4, 8], 1.0, 1.0, 0.0)
+    finally:
+        prob_unet.device = saved
+    sd0 = m.state_dict()
+    assert list(sd0.keys()) == list(golden["sd_keys"])                      # 391 entries, same order
+    assert len(sd0) == 391 and sum(p.numel() for p in m.parameters()) == 19351491
+    assert [v.numel() for v in sd0.values()] == list(golden["sd_numel"])
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd0.values()]), golden["sd_sum"])
+    np.testing.assert_array_equal(np.array([float(v.double().abs().sum()) for v in sd0.values()]), golden["sd_abssum"])
+
+
+def test_dezero_matches(golden, sd):
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd.values()]), golden["sd1_sum"])
+
+
+def test_submodules(golden, sd):
+    x, y = torch.from_numpy(golden["A_x"]), torch.from_numpy(golden["A_y"])
+    with torch.no_grad():
+        feat = O.unet_forward(sd, x, CFG.unet())
+        assert rel_err(feat, golden["A_unet"]) < 1e-5
+        mu, sig = O.gaussian_encoder(sd, "prior", x, None, CFG.num_filters)
+        assert rel_err(mu, golden["A_prior_mu"]) < 1e-5 and rel_err(sig, golden["A_prior_sigma"]) < 1e-5
+        mq, sq = O.gaussian_encoder(sd, "posterior", x, y, CFG.num_filters)
+        assert rel_err(mq, golden["A_post_mu"]) < 1e-5 and rel_err(sq, golden["A_post_sigma"]) < 1e-5
+        assert rel_err(O.kl_normal(mq, sq, mu, sig), golden["A_kl"]) < 1e-5
+        eps = torch.from_numpy(golden["A_eps"])
+        assert rel_err(O.fcomb(sd, feat, mq + sq * eps[2]), golden["A_fcomb"]) < 1e-5
+        assert rel_err(O.forward(sd, CFG, x, y, eps[0], training=True), golden["A_fwd_train"]) < 1e-5
+        assert rel_err(O.forward(sd, CFG, x, None, eps[1], training=False), golden["A_fwd_prior"]) < 1e-5
+
+
+def _grads(sd, fn):
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "resample_filter" not in k}
+    full = dict(sd)
+    full.update(leaves)
+    out = fn(full)
+    out[0].backward()
+    return out, leaves
+
+
+def test_elbo_afcrps_and_grads(golden, sd):
+    x, y, eps = (torch.from_numpy(golden[k]) for k in ("A_x", "A_y", "A_eps"))
+    out, leaves = _grads(sd, lambda s: O.elbo(s, CFG, x, y, eps, "afcrps"))
+    assert abs(float(out[0]) - float(golden["A_afcrps_total"])) / abs(float(golden["A_afcrps_total"])) < 1e-5
+    assert abs(float(out[1]) - float(golden["A_afcrps_crps"])) / abs(float(golden["A_afcrps_crps"])) < 1e-5
+    names, ref = list(golden["grad_names"]), golden["A_afcrps_gradnorm"]
+    for n, r in zip(names, ref):
+        g = leaves[n].grad
+        gn = 0.0 if g is None else float(g.double().norm())
+        assert abs(gn - r) <= 1e-4 * max(r, 1e-8) + 1e-10, (n, gn, r)
+    for k in golden.files:
+        if k.startswith("A_afcrps_grad::"):
+            assert rel_err(leaves[k.split("::")[1]].grad, golden[k]) < 1e-4, k
+
+
+def test_elbo_l1(golden, sd):
+    x, y, eps = (torch.from_numpy(golden[k]) for k in ("A_x", "A_y", "A_eps"))
+    out, leaves = _grads(sd, lambda s: O.elbo(s, CFG, x, y, eps[:1], "l1"))
+    assert abs(float(out[0]) - float(golden["A_l1_total"])) / abs(float(golden["A_l1_total"])) < 1e-5
+    for n, r in zip(golden["grad_names"], golden["A_l1_gradnorm"]):
+        g = leaves[n].grad
+        gn = 0.0 if g is None else float(g.double().norm())
+        assert abs(gn - r) <= 1e-4 * max(r, 1e-8) + 1e-10, (n, gn, r)
+
+
+def test_elbo_l1_with_injected_dropout(golden, sd):
+    x, y, eps = (torch.from_numpy(golden[k]) for k in ("A_x", "A_y", "A_eps"))
+    enc, dec = O.unet_topology(CFG.unet())
+    keys = [b.key for b in enc + dec if not b.is_conv]
+    masks = unpack_masks(golden, keys)
+    with torch.no_grad():
+        out = O.elbo(sd, CFG, x, y, eps[:1], "l1", drop_masks=masks)
+    assert abs(float(out[0]) - float(golden["A_drop_l1_total"])) / abs(float(golden["A_drop_l1_total"])) < 1e-5
+
+
+def test_elbo_msssim_variant(golden, sd):
+    """Pins the code AROUND ms_ssim (wmse, data_range, KL, return arity); ms_ssim itself is a restatement of the
+    absent third-party package (parity unpinned, see oracle header)."""
+    x, y, eps = (torch.from_numpy(golden[k]) for k in ("B_x", "B_y", "B_eps"))
+    with torch.no_grad():
+        out = O.elbo(sd, CFG, x, y, eps, "mse+ssim")
+    assert abs(float(out[0]) - float(golden["B_total"])) / abs(float(golden["B_total"])) < 1e-5
+    assert rel_err(out[2], golden["B_kl"]) < 1e-5
+    assert abs(float(out[3]) - float(golden["B_wmse"])) / float(golden["B_wmse"]) < 1e-5
+
+
+def test_losses_known_answers(golden):
+    e, t = torch.from_numpy(golden["L_ens"]), torch.from_numpy(golden["L_tgt"])
+    assert abs(float(O.afcrps_loss(e, t)) - float(golden["L_afcrps"])) < 1e-6
+    assert abs(float(O.crps_loss(e, t)) - float(golden["L_crps"])) < 1e-6
+    # three CRPS formulations agree (pairwise, sort-based, Hersbach): SURVEY.md 8c
+    ce = O.crps_empirical(e.permute(1, 0, 2, 3, 4).contiguous(), t)
+    assert abs(float(ce.mean()) - float(golden["L_crps"])) < 1e-6
+    if "L_crps_empirical_mean" in golden.files:
+        assert abs(float(ce.mean()) - float(golden["L_crps_empirical_mean"])) < 1e-6
+    h = np.mean([O.crps_hersbach_np(e[b, :, c].numpy(), t[b, c].numpy()) for b in range(2) for c in range(3)])
+    assert abs(h - float(golden["L_crps"])) < 1e-6
+
+
+def test_metrics_restatement_consistency():
+    g = torch.Generator().manual_seed(5)
+    preds, hr = torch.randn(3, 7, 3, 8, 8, generator=g), torch.randn(3, 3, 8, 8, generator=g)
+    c = O.crps_over_groundtruth(hr, preds)
+    ref = torch.stack([O.crps_empirical(preds[t], hr[t]).mean(dim=(1, 2)) for t in range(3)]).numpy()
+    np.testing.assert_allclose(c, ref, rtol=1e-5, atol=1e-6)
+    assert O.compute_mae(hr, preds).shape == (3, 3)
