@@ -37,6 +37,8 @@ typedef struct CUstream_st* pub_stream_t; /* == cudaStream_t */
 
 const char* pub_last_error(void);
 int pub_version(void);
+/* number of kernels this library has enqueued so far in this process (bench.py: gpu_launches) */
+unsigned long long pub_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Convolution primitives.  Replace torch.nn.functional.conv2d at src/networks.py:89

@@ -70,7 +70,7 @@ class AdamWEntry(C.Structure):
 
 # every symbol include/probunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "pub_last_error", "pub_version", "pub_conv2d_forward", "pub_pack_conv_weight", "pub_conv2d_wgrad_workspace",
+    "pub_last_error", "pub_version", "pub_launch_count", "pub_conv2d_forward", "pub_pack_conv_weight", "pub_conv2d_wgrad_workspace",
     "pub_conv2d_wgrad", "pub_nchw_to_nhwc", "pub_nhwc_to_nchw", "pub_unet_create", "pub_unet_destroy",
     "pub_unet_num_params", "pub_unet_workspace_bytes", "pub_unet_forward", "pub_unet_backward",
     "pub_unet_dropout_mask", "pub_encoder_create", "pub_encoder_destroy", "pub_encoder_num_params",
@@ -90,6 +90,7 @@ def lib():
                               "(there is no CPU / PyTorch fallback for the Prob U-Net hot path)")
         l = C.CDLL(_LIB_PATH)
         l.pub_last_error.restype = C.c_char_p
+        l.pub_launch_count.restype = C.c_ulonglong
         for name in ("pub_conv2d_wgrad_workspace", "pub_unet_workspace_bytes", "pub_encoder_workspace_bytes",
                      "pub_fcomb_backward_workspace", "pub_loss_workspace"):
             if hasattr(l, name):
@@ -323,7 +324,9 @@ class UNetEngine:
         self.params, self.zero_params = [], []
         self.block_keys = []
         from networks import UNetBlock
-        for name, md, dst in ([(k, v, enc) for k, v in module.enc.items()] + [(k, v, dec) for k, v in module.dec.items()]):
+        self.block_modules = []
+        for name, md, dst in ([("enc." + k, v, enc) for k, v in module.enc.items()] +
+                              [("dec." + k, v, dec) for k, v in module.dec.items()]):
             d = UNetBlockDesc()
             if isinstance(md, UNetBlock):
                 has_conv = md.skip is not None and md.skip.weight is not None
@@ -339,6 +342,7 @@ class UNetEngine:
                 self.params += [md.weight, md.bias]
             dst.append(d)
             self.block_keys.append(name)
+            self.block_modules.append(md)
         self.params += [module.out_norm.weight, module.out_norm.bias, module.out_conv.weight, module.out_conv.bias]
         if module.map_label is not None:
             self.zero_params.append(module.map_label.weight)
@@ -370,13 +374,12 @@ class UNetEngine:
                              *self.params, *self.zero_params)
 
     def dropout_mask(self, block_key, B, H, W, seed):
-        """Test hook: bool [B,C,h,w] keep-mask the engine uses in block `block_key` for `seed`."""
+        """Test hook: bool [B,C,h,w] keep-mask the engine uses in block `block_key` ("enc.<name>" /
+        "dec.<name>") for `seed`."""
         idx = self.block_keys.index(block_key)
-        md = {**dict(self.module.enc.items()), **dict(self.module.dec.items())}[block_key]
-        # output resolution of the block: walk the plan
-        h, w = H, W
-        for k in self.block_keys[:idx + 1]:
-            m = {**dict(self.module.enc.items()), **dict(self.module.dec.items())}[k]
+        md = self.block_modules[idx]
+        h, w = H, W                      # output resolution of the block: walk the plan
+        for m in self.block_modules[:idx + 1]:
             if getattr(m, "down", False):
                 h, w = h // 2, w // 2
             if getattr(m, "up", False):

@@ -8,6 +8,7 @@
 namespace pub {
 
 static thread_local std::string g_err;
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -79,6 +80,7 @@ extern "C" {
 
 const char* pub_last_error(void) { return g_err.c_str(); }
 int pub_version(void) { return 100; }
+unsigned long long pub_launch_count(void) { return g_launch_count; }
 
 int pub_conv2d_forward(const pub_conv_args* a, pub_stream_t s) {
   PUB_REQUIRE(a && a->x0 && a->w && a->y, "pub_conv2d_forward: null argument");

@@ -31,7 +31,12 @@ void set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
-#define PUB_LAUNCH_CHECK() PUB_CUDA(cudaGetLastError())
+extern unsigned long long g_launch_count;  // kernels enqueued by this library (bench.py's gpu_launches)
+#define PUB_LAUNCH_CHECK()          \
+  do {                              \
+    ++::pub::g_launch_count;        \
+    PUB_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define PUB_TRY(expr)        \
   do {                       \

@@ -149,7 +149,7 @@ class ProbabilisticUNet(nn.Module):
         else:
             self.prior_latent_space = self.prior(x)
             z = self.prior_latent_space.rsample(eps=eps)
-        return _native.fcomb_apply(self.fcomb, feat, z.unsqueeze(0))[:, 0]
+        return _native.fcomb_apply(self.fcomb, feat, z.unsqueeze(0), nhwc=True)[:, 0]
 
     @torch.no_grad()
     def sample(self, x, n, eps=None):
@@ -157,7 +157,7 @@ class ProbabilisticUNet(nn.Module):
         feat = self.unet(x, _nhwc_out=True)
         self.prior_latent_space = self.prior(x)
         z = self.prior_latent_space.rsample((n,), eps=eps)
-        return _native.fcomb_apply(self.fcomb, feat, z)
+        return _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)
 
     def elbo(self, x, target, t=None, M=None, alpha=0.95, alpha_w=0.007, beta_w=0.048, lam_w=0.0, eps=None):
         """ELBO = beta_0*recon + beta_1*KL(q||p) [+ beta_2*KL(q||N(0,I))]; the reconstruction
@@ -176,13 +176,13 @@ class ProbabilisticUNet(nn.Module):
         kl_div = _native.kl_normal(q.loc, q.scale, p.loc, p.scale)
         if lt == "l1":
             z = self.posterior_latent_space.rsample((1,), eps=eps)
-            out = _native.fcomb_apply(self.fcomb, feat, z)
+            out = _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)
             l1, per_var = _native.l1_loss(out[:, 0], target)
             kl2 = _native.kl_normal(q.loc, q.scale, torch.zeros_like(q.loc), torch.ones_like(q.scale))
             total = self.beta_0 * l1 + self.beta_1 * torch.mean(kl_div) + self.beta_2 * torch.mean(kl2)
             return total, per_var.detach().tolist(), kl_div, kl2
         z = self.posterior_latent_space.rsample((M,), eps=eps)
-        ens = _native.fcomb_apply(self.fcomb, feat, z)                 # [B,M,C,H,W]
+        ens = _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)      # [B,M,C,H,W]
         if lt in ("afcrps", "crps"):
             crps = _native.ensemble_loss(ens, target, kind=lt, alpha=alpha)
             total = self.beta_0 * crps + self.beta_1 * kl_div.mean()

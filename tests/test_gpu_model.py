@@ -133,8 +133,8 @@ def test_train_mode_dropout_matches_oracle_with_exported_masks(setup, golden):
             f = eng.forward(x, True, seed=1234)
         keys = [k for k in eng.block_keys if not k.endswith("_conv")]
         enc, dec = O.unet_topology(CFG.unet())
-        okeys = [b.key for b in enc + dec if not b.is_conv]
-        masks = {ok: eng.dropout_mask(k, 2, 64, 64, 1234).cpu() for k, ok in zip(keys, okeys)}
+        assert keys == [b.key for b in enc + dec if not b.is_conv]
+        masks = {k: eng.dropout_mask(k, 2, 64, 64, 1234).cpu() for k in keys}
         frac = np.mean([float(v.float().mean()) for v in masks.values()])
         assert abs(frac - 0.9) < 0.01                      # keep probability 1 - p
         with torch.no_grad():
