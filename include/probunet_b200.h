@@ -30,6 +30,7 @@ typedef struct CUstream_st* pub_stream_t; /* == cudaStream_t */
 
 #define PUB_F32 0
 #define PUB_BF16 1
+#define PUB_TF32 2 /* f32 storage whose values are rounded to tf32; convolutions use tcgen05 kind::tf32 */
 
 #define PUB_BACKEND_AUTO 0
 #define PUB_BACKEND_SIMT 1    /* fp32-FMA implicit GEMM (parity path, any shape)          */

@@ -15,10 +15,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libprobunet_b200.so")
 _lib = None
 
-F32, BF16 = 0, 1
+F32, BF16, TF32 = 0, 1, 2
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
-_DTYPE_NAMES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16}
-_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+_DTYPE_NAMES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16, "tf32": TF32}
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, TF32: torch.float32}
 
 # process-wide knobs (env vars so that the reference's drivers stay unchanged)
 _default_dtype = os.environ.get("PROBUNET_B200_DTYPE", "bf16")
@@ -112,6 +112,17 @@ def resolve_dtype(name):
     return _DTYPE_NAMES[(name or _default_dtype).lower()]
 
 
+def resolve_encoder_dtype(name):
+    """Precision of the two Gaussian encoders.  Their log-sigma head feeds exp(): an absolute error of d in
+    log sigma is a RELATIVE error d in sigma and in z = mu + sigma*eps, so with the U-Net in bf16 the encoders run
+    one notch higher (tf32 tensor cores, f32 storage) unless PROBUNET_B200_ENCODER_DTYPE overrides it."""
+    dt = resolve_dtype(name)
+    env = os.environ.get("PROBUNET_B200_ENCODER_DTYPE")
+    if env:
+        return _DTYPE_NAMES[env.lower()]
+    return TF32 if dt == BF16 else dt
+
+
 def set_default_dtype(name):
     global _default_dtype
     assert name.lower() in _DTYPE_NAMES
@@ -152,11 +163,12 @@ def pack_conv_weight(w, dtype, transpose_flip=False):
     return out
 
 
-def conv2d_nhwc(x0, w_packed, bias=None, x1=None, res=None, mask=None, relu=False, ksize=3, backend=None, out=None):
+def conv2d_nhwc(x0, w_packed, bias=None, x1=None, res=None, mask=None, relu=False, ksize=3, backend=None, out=None,
+                dtype=None):
     """x0/x1/res/mask: NHWC views [B,H,W,C] (last-dim-contiguous, arbitrary pixel stride)."""
     require_cuda(x0, w_packed)
     B, H, W, c0 = x0.shape
-    dt = BF16 if x0.dtype == torch.bfloat16 else F32
+    dt = dtype if dtype is not None else (BF16 if x0.dtype == torch.bfloat16 else F32)
     cout = w_packed.shape[1]
     y = out if out is not None else torch.empty(B, H, W, cout, device=x0.device, dtype=x0.dtype)
     a = ConvArgs()
@@ -176,9 +188,9 @@ def conv2d_nhwc(x0, w_packed, bias=None, x1=None, res=None, mask=None, relu=Fals
     return y
 
 
-def conv2d_wgrad_nhwc(x0, dy, ksize, x1=None, want_bias=True, backend=None):
+def conv2d_wgrad_nhwc(x0, dy, ksize, x1=None, want_bias=True, backend=None, dtype=None):
     B, H, W, c0 = x0.shape
-    dt = BF16 if x0.dtype == torch.bfloat16 else F32
+    dt = dtype if dtype is not None else (BF16 if x0.dtype == torch.bfloat16 else F32)
     cout = dy.shape[3]
     cin = c0 + (x1.shape[3] if x1 is not None else 0)
     dw = torch.empty(cout, cin, ksize, ksize, device=x0.device, dtype=torch.float32)

@@ -33,16 +33,18 @@ int conv_forward(const ConvParams& p, int dtype, int backend, cudaStream_t s) {
   if (backend == PUB_BACKEND_TCGEN05) {
     PUB_REQUIRE(conv_tc_supported(p, dtype), "tcgen05 conv backend does not support this shape/dtype "
                 "(c0=%d c1=%d cout=%d H=%d W=%d ks=%d dtype=%d)", p.c0, p.c1, p.cout, p.H, p.W, p.ks, dtype);
-    return conv_tc(p, s);
+    return conv_tc(p, dtype, s);
   }
-  if (backend == PUB_BACKEND_AUTO && conv_tc_supported(p, dtype)) return conv_tc(p, s);
-  return conv_simt(p, dtype, s);
+  if (backend == PUB_BACKEND_AUTO && conv_tc_supported(p, dtype)) return conv_tc(p, dtype, s);
+  ConvParams q = p;
+  q.round_tf32 = dtype == PUB_TF32;
+  return conv_simt(q, dtype, s);
 }
 
 size_t wgrad_workspace(const WgradParams& p, int dtype, int backend) {
   size_t a = wgrad_simt_workspace(p);
   if (backend != PUB_BACKEND_SIMT && wgrad_tc_supported(p, dtype)) {
-    size_t b = wgrad_tc_workspace(p);
+    size_t b = wgrad_tc_workspace(p, dtype);
     if (b > a) a = b;
   }
   return a;
@@ -51,9 +53,9 @@ size_t wgrad_workspace(const WgradParams& p, int dtype, int backend) {
 int wgrad(const WgradParams& p, int dtype, int backend, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
   if (backend == PUB_BACKEND_TCGEN05) {
     PUB_REQUIRE(wgrad_tc_supported(p, dtype), "tcgen05 wgrad backend does not support this shape/dtype");
-    return wgrad_tc(p, ws, ws_bytes, accumulate, s);
+    return wgrad_tc(p, dtype, ws, ws_bytes, accumulate, s);
   }
-  if (backend == PUB_BACKEND_AUTO && wgrad_tc_supported(p, dtype)) return wgrad_tc(p, ws, ws_bytes, accumulate, s);
+  if (backend == PUB_BACKEND_AUTO && wgrad_tc_supported(p, dtype)) return wgrad_tc(p, dtype, ws, ws_bytes, accumulate, s);
   return wgrad_simt(p, dtype, ws, ws_bytes, accumulate, s);
 }
 
@@ -85,7 +87,7 @@ unsigned long long pub_launch_count(void) { return g_launch_count; }
 int pub_conv2d_forward(const pub_conv_args* a, pub_stream_t s) {
   PUB_REQUIRE(a && a->x0 && a->w && a->y, "pub_conv2d_forward: null argument");
   PUB_REQUIRE(a->ksize == 1 || a->ksize == 3, "pub_conv2d_forward: ksize must be 1 or 3");
-  PUB_REQUIRE(a->dtype == PUB_F32 || a->dtype == PUB_BF16, "pub_conv2d_forward: bad dtype");
+  PUB_REQUIRE(a->dtype == PUB_F32 || a->dtype == PUB_BF16 || a->dtype == PUB_TF32, "pub_conv2d_forward: bad dtype");
   return conv_forward(to_params(a), a->dtype, a->backend, (cudaStream_t)s);
 }
 

@@ -131,6 +131,11 @@ struct Philox {
   static __device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 };
 
+__device__ __forceinline__ float round_tf32_f(float x) {  // round-to-nearest onto the 10-bit-mantissa tf32 grid
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float silu_grad_f(float x) {
   const float s = 1.f / (1.f + __expf(-x));

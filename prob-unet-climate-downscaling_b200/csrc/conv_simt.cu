@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
       if (res) v += to_f<T>(res[m * p.ld_res + n]);
       if (p.relu) v = fmaxf(v, 0.f);
       if (mask && !(to_f<T>(mask[m * p.ld_mask + n]) > 0.f)) v = 0.f;
+      if (p.round_tf32) v = round_tf32_f(v);
       y[m * p.ldy + n] = from_f<T>(v);
     }
   }
@@ -194,17 +195,19 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int nchunk, 
 
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int ks,
-                                   int tflip) {
+                                   int tflip, int rtf32) {
   const int taps = ks * ks;
   const int64_t n = (int64_t)taps * cout * cin;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (!tflip) {  // out[tap][co][ci]
     const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
-    out[i] = from_f<T>(w[((int64_t)co * cin + ci) * taps + tap]);
+    const float v = w[((int64_t)co * cin + ci) * taps + tap];
+    out[i] = from_f<T>(rtf32 ? round_tf32_f(v) : v);
   } else {  // out[tap][ci][co] = w[co][ci][mirror(tap)]
     const int co = (int)(i % cout), ci = (int)((i / cout) % cin), tap = (int)(i / ((int64_t)cin * cout));
-    out[i] = from_f<T>(w[((int64_t)co * cin + ci) * taps + (taps - 1 - tap)]);
+    const float v = w[((int64_t)co * cin + ci) * taps + (taps - 1 - tap)];
+    out[i] = from_f<T>(rtf32 ? round_tf32_f(v) : v);
   }
 }
 
@@ -300,8 +303,8 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
 
 int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype, int tflip, cudaStream_t s) {
   const int64_t n = (int64_t)ks * ks * cout * cin;
-  if (dtype == PUB_BF16) pack_weight_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(w, (bf16*)out, cout, cin, ks, tflip);
-  else pack_weight_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(w, (float*)out, cout, cin, ks, tflip);
+  if (dtype == PUB_BF16) pack_weight_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(w, (bf16*)out, cout, cin, ks, tflip, 0);
+  else pack_weight_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(w, (float*)out, cout, cin, ks, tflip, dtype == PUB_TF32);
   PUB_LAUNCH_CHECK();
   return 0;
 }

@@ -16,6 +16,8 @@
 // tcgen05.commit releases stages and publishes the accumulator.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -101,6 +103,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, kind::tf32: A, B are 32-bit floats whose low 13 mantissa bits are ignored (K = 8 per instruction)
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int ES>
+__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (ES == 2) umma_bf16(d, a, b, idesc, acc);
+  else umma_tf32(d, a, b, idesc, acc);
+}
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // 32 lanes x 32 consecutive f32 columns -> 32 registers per thread (thread t <-> lane base+t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -131,8 +154,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), majors (15,16), N>>3 (17..22),
 // M>>4 (24..28)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// fmt: 1 = BF16, 2 = TF32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -149,20 +173,24 @@ struct TcConvArgs {
   int cout;                    // total output channels
   int stages;
   const float* bias;
-  const bf16* res; int ld_res;
-  const bf16* mask; int ld_mask;
-  bf16* y; int ldy;
+  const void* res; int ld_res;
+  const void* mask; int ld_mask;
+  void* y; int ldy;
   int relu;
 };
 
 // ------------------------------------------------------------------ forward / dgrad kernel
-template <int KC>  // channels per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)
+// ROWB: bytes per smem row (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); ES: operand element size
+// (2 = bf16 / kind::f16, 4 = tf32-rounded f32 / kind::tf32).  Channels per K block = ROWB / ES.
+template <int ROWB_, int ES>
 __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                            const __grid_constant__ CUtensorMap tmA1,
                                                            const __grid_constant__ CUtensorMap tmW, TcConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr uint32_t ROWB = KC * 2;                   // bytes per smem row
-  constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
+  typedef typename std::conditional<ES == 2, bf16, float>::type T;
+  constexpr uint32_t ROWB = ROWB_;                     // bytes per smem row
+  constexpr int KC = ROWB_ / ES;                       // channels per K block
+  constexpr uint32_t LAYOUT = (ROWB_ == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
   constexpr uint32_t SBO = 8 * ROWB;                  // 8-row core-matrix group pitch
   constexpr uint32_t A_BYTES = 128 * ROWB;
   const uint32_t B_BYTES = (uint32_t)a.BN * ROWB;
@@ -221,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer
-      const uint32_t idesc = make_idesc(128, a.BN, 0, 0);
+      const uint32_t idesc = make_idesc(128, a.BN, 0, 0, ES == 2 ? 1u : 2u);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
@@ -229,8 +257,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
         const uint64_t ad = make_desc(sa, 16, SBO, LAYOUT), bd = make_desc(sb, 16, SBO, LAYOUT);
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k)  // +32 B per 16-element K step inside the swizzled row
-          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        for (int k = 0; k < (int)ROWB / 32; ++k)  // one MMA consumes 32 B of K; +32 B inside the swizzled row
+          umma<ES>(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
@@ -259,11 +287,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
           for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
         }
         if (a.res) {
-          const bf16* rp = a.res + pix * a.ld_res + n;
+          const T* rp = (const T*)a.res + pix * a.ld_res + n;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
-            Vec8<bf16>::load(rp + g * 8, f);
+            Vec8<T>::load(rp + g * 8, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
           }
@@ -273,22 +301,22 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (a.mask) {
-          const bf16* mp = a.mask + pix * a.ld_mask + n;
+          const T* mp = (const T*)a.mask + pix * a.ld_mask + n;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
-            Vec8<bf16>::load(mp + g * 8, f);
+            Vec8<T>::load(mp + g * 8, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
           }
         }
-        bf16* yp = a.y + pix * a.ldy + n;
+        T* yp = (T*)a.y + pix * a.ldy + n;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
-          Vec8<bf16>::store(yp + g * 8, f);
+          for (int j = 0; j < 8; ++j) f[j] = ES == 4 ? round_tf32(v[g * 8 + j]) : v[g * 8 + j];
+          Vec8<T>::store(yp + g * 8, f);
         }
       }
     }
@@ -310,14 +338,21 @@ struct TcWgradArgs {
   float* part;            // [split][tap][cout][cin] f32
 };
 
-constexpr int WG_P = 64;                         // pixels (K) per stage
-constexpr uint32_t WG_GROUP_BYTES = WG_P * 64;   // one 32-channel x 64-pixel SWIZZLE_64B box
-constexpr uint32_t WG_A_BYTES = 4 * WG_GROUP_BYTES;
+constexpr int WG_P = 64;  // pixels (K) per stage
 
+// ES = 2: bf16 operands, 32-channel groups are 64 B rows (SWIZZLE_64B), 16 pixels per MMA
+// ES = 4: tf32 operands, 32-channel groups are 128 B rows (SWIZZLE_128B), 8 pixels per MMA
+template <int ES>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                             const __grid_constant__ CUtensorMap tmX1,
                                                             const __grid_constant__ CUtensorMap tmDY,
                                                             TcWgradArgs a) {
+  constexpr uint32_t ROW = 32 * ES;                      // bytes of one 32-channel row
+  constexpr uint32_t WG_GROUP_BYTES = WG_P * ROW;        // one 32-channel x 64-pixel box
+  constexpr uint32_t WG_A_BYTES = 4 * WG_GROUP_BYTES;
+  constexpr uint32_t LAYOUT = ES == 2 ? 4u : 2u;
+  constexpr int KROWS = 32 / ES;                         // pixels per MMA (UMMA_K)
+  constexpr uint32_t KSTEP_BYTES = KROWS * ROW;          // = 1024 for both element sizes
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
@@ -375,10 +410,10 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // A = dy  [K=64 px][M=128 co]  MN-major SWIZZLE_64B: 4 groups of 32 channels, LBO = group pitch,
-      //                               SBO = 8 pixel rows * 64 B
-      // B = x   [K=64 px][N=32 ci]   MN-major SWIZZLE_64B
-      const uint32_t idesc = make_idesc(128, 32, 1, 1);
+      // A = dy  [K=64 px][M=128 co]  MN-major: 4 groups of 32 channels, LBO = group pitch,
+      //                               SBO = 8 pixel rows
+      // B = x   [K=64 px][N=32 ci]   MN-major
+      const uint32_t idesc = make_idesc(128, 32, 1, 1, ES == 2 ? 1u : 2u);
       int stage = 0; uint32_t phase = 0;
       bool first = true;
       for (int t = t_beg; t < t_end; ++t) {
@@ -387,10 +422,10 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + WG_A_BYTES;
         for (int tap = 0; tap < a.taps; ++tap) {
 #pragma unroll
-          for (int k = 0; k < WG_P / 16; ++k) {  // 16 pixel rows * 64 B = 1024 B per K step
-            const uint64_t ad = make_desc(sa + k * 1024, WG_GROUP_BYTES, 512, 4u);
-            const uint64_t bd = make_desc(sb + tap * WG_GROUP_BYTES + k * 1024, WG_GROUP_BYTES, 512, 4u);
-            umma_bf16(tmem_base + (uint32_t)(tap * 32), ad, bd, idesc, (!first || k != 0) ? 1u : 0u);
+          for (int k = 0; k < WG_P / KROWS; ++k) {
+            const uint64_t ad = make_desc(sa + k * KSTEP_BYTES, WG_GROUP_BYTES, 8 * ROW, LAYOUT);
+            const uint64_t bd = make_desc(sb + tap * WG_GROUP_BYTES + k * KSTEP_BYTES, WG_GROUP_BYTES, 8 * ROW, LAYOUT);
+            umma<ES>(tmem_base + (uint32_t)(tap * 32), ad, bd, idesc, (!first || k != 0) ? 1u : 0u);
           }
         }
         first = false;
@@ -456,36 +491,36 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// NHWC bf16 activation view [B][H][W][C] with pixel stride ld; box = (cbox, tw, th, tb)
-int make_act_map(CUtensorMap* tm, const void* ptr, int C, int ld, int B, int H, int W, int cbox, int tw, int th,
+// NHWC activation view [B][H][W][C] (es-byte elements) with pixel stride ld; box = (cbox, tw, th, tb)
+int make_act_map(CUtensorMap* tm, const void* ptr, int es, int C, int ld, int B, int H, int W, int cbox, int tw, int th,
                  int tb, CUtensorMapSwizzle sw) {
   EncodeTiledFn enc = get_encode();
   PUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es};
   cuuint32_t box[4] = {(cuuint32_t)cbox, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  PUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d) -> %d",
-              C, ld, B, H, W, cbox, tw, th, tb, (int)r);
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation es=%d C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d) -> %d",
+              es, C, ld, B, H, W, cbox, tw, th, tb, (int)r);
   return 0;
 }
 
-int make_weight_map(CUtensorMap* tm, const void* ptr, int K, int N, int taps, int kbox, int nbox,
+int make_weight_map(CUtensorMap* tm, const void* ptr, int es, int K, int N, int taps, int kbox, int nbox,
                     CUtensorMapSwizzle sw) {
   EncodeTiledFn enc = get_encode();
   PUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)taps};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * es, (cuuint64_t)N * K * es};
   cuuint32_t box[3] = {(cuuint32_t)kbox, (cuuint32_t)nbox, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  PUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights K=%d N=%d taps=%d box=%d,%d) -> %d", K, N, taps, kbox,
-              nbox, (int)r);
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights es=%d K=%d N=%d taps=%d box=%d,%d) -> %d", es, K, N, taps,
+              kbox, nbox, (int)r);
   return 0;
 }
 
@@ -497,7 +532,7 @@ int pick_bn(int n) {
   return 0;
 }
 
-// a 128-pixel patch (tw x th x tb) that tiles [B][H][W] exactly in y and x
+// a `target`-pixel patch (tw x th x tb) that tiles [B][H][W] exactly in y and x
 bool pick_patch(int H, int W, int target, int& tw, int& th, int& tb) {
   tw = W < 16 ? W : 16;
   if (W % tw) return false;
@@ -508,39 +543,48 @@ bool pick_patch(int H, int W, int target, int& tw, int& th, int& tb) {
   return tw * th * tb == target && tb >= 1;
 }
 
+inline int esize(int dtype) { return dtype == PUB_BF16 ? 2 : 4; }
+
+template <typename K>
+int set_smem_attr(K kernel, int bytes) {
+  PUB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
 }  // namespace
 
 bool conv_tc_supported(const ConvParams& p, int dtype) {
-  if (dtype != PUB_BF16) return false;
+  if (dtype != PUB_BF16 && dtype != PUB_TF32) return false;
+  const int es = esize(dtype), al = 16 / es;
   if (p.ks != 1 && p.ks != 3) return false;
   const int cin = p.c0 + p.c1;
   if (p.c0 % 32 || p.c1 % 32 || cin < 32 || pick_bn(p.cout) == 0) return false;
-  if (p.ld0 % 8 || (p.x1 && p.ld1 % 8) || p.ldy % 8) return false;
+  if (p.ld0 % al || (p.x1 && p.ld1 % al) || p.ldy % al) return false;
   if (!aligned16(p.x0) || !aligned16(p.x1) || !aligned16(p.w) || !aligned16(p.y)) return false;
-  if ((p.res && (p.ld_res % 8 || !aligned16(p.res))) || (p.mask && (p.ld_mask % 8 || !aligned16(p.mask))))
+  if ((p.res && (p.ld_res % al || !aligned16(p.res))) || (p.mask && (p.ld_mask % al || !aligned16(p.mask))))
     return false;
   int tw, th, tb;
-  if (!pick_patch(p.H, p.W, 128, tw, th, tb)) return false;
-  if (tb > 1 && tb > 256) return false;
-  return true;
+  return pick_patch(p.H, p.W, 128, tw, th, tb);
 }
 
-int conv_tc(const ConvParams& p, cudaStream_t s) {
-  PUB_REQUIRE(conv_tc_supported(p, PUB_BF16), "conv_tc: unsupported shape (c0=%d c1=%d cout=%d H=%d W=%d ks=%d)", p.c0,
-              p.c1, p.cout, p.H, p.W, p.ks);
-  const int cin = p.c0 + p.c1;
-  const int KC = (p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32;
-  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
+  PUB_REQUIRE(conv_tc_supported(p, dtype), "conv_tc: unsupported shape (c0=%d c1=%d cout=%d H=%d W=%d ks=%d dtype=%d)",
+              p.c0, p.c1, p.cout, p.H, p.W, p.ks, dtype);
+  const int cin = p.c0 + p.c1, es = esize(dtype);
+  // channels per K block: bf16 -> 64 (128 B rows) when both sources allow it, else 32 (64 B rows); tf32 -> 32 (128 B rows)
+  const int KC = es == 4 ? 32 : ((p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32);
+  const int rowb = KC * es;
+  const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   TcConvArgs a{};
   a.c0 = p.c0; a.c1 = p.c1; a.ks = p.ks; a.taps = p.ks * p.ks;
   a.B = p.B; a.H = p.H; a.W = p.W;
   pick_patch(p.H, p.W, 128, a.TW, a.TH, a.TB);
   a.tiles_x = p.W / a.TW; a.tiles_y = p.H / a.TH;
   a.BN = pick_bn(p.cout); a.cout = p.cout;
-  a.bias = p.bias; a.res = (const bf16*)p.res; a.ld_res = p.ld_res;
-  a.mask = (const bf16*)p.mask; a.ld_mask = p.ld_mask;
-  a.y = (bf16*)p.y; a.ldy = p.ldy; a.relu = p.relu;
-  const size_t stage_bytes = (size_t)(128 + a.BN) * KC * 2;
+  a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res;
+  a.mask = p.mask; a.ld_mask = p.ld_mask;
+  a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
+  const size_t stage_bytes = (size_t)(128 + a.BN) * rowb;
   int stages = (int)(98304 / stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 6) stages = 6;
@@ -548,21 +592,22 @@ int conv_tc(const ConvParams& p, cudaStream_t s) {
   const size_t smem = stages * stage_bytes + 1024;
 
   CUtensorMap tmA0, tmA1, tmW;
-  PUB_TRY(make_act_map(&tmA0, p.x0, p.c0, p.ld0, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
-  if (p.c1) PUB_TRY(make_act_map(&tmA1, p.x1, p.c1, p.ld1, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
+  PUB_TRY(make_act_map(&tmA0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
+  if (p.c1) PUB_TRY(make_act_map(&tmA1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
   else tmA1 = tmA0;
-  PUB_TRY(make_weight_map(&tmW, p.w, cin, p.cout, a.taps, KC, a.BN, sw));
+  PUB_TRY(make_weight_map(&tmW, p.w, es, cin, p.cout, a.taps, KC, a.BN, sw));
 
   dim3 grid(cdiv(p.B, a.TB) * a.tiles_x * a.tiles_y, p.cout / a.BN);
-  if (KC == 64) {
-    static bool attr = false;
-    if (!attr) { PUB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-    conv_tc_kernel<64><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
-  } else {
-    static bool attr = false;
-    if (!attr) { PUB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-    conv_tc_kernel<32><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  static bool attr = false;
+  if (!attr) {
+    PUB_TRY(set_smem_attr(conv_tc_kernel<128, 2>, 200 * 1024));
+    PUB_TRY(set_smem_attr(conv_tc_kernel<64, 2>, 200 * 1024));
+    PUB_TRY(set_smem_attr(conv_tc_kernel<128, 4>, 200 * 1024));
+    attr = true;
   }
+  if (es == 4) conv_tc_kernel<128, 4><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  else if (rowb == 128) conv_tc_kernel<128, 2><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  else conv_tc_kernel<64, 2><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -570,7 +615,7 @@ int conv_tc(const ConvParams& p, cudaStream_t s) {
 // ------------------------------------------------------------------ wgrad host side
 namespace {
 struct WgPlan { int tw, th, tiles_x, tiles_y, tiles_total, nsplit, tiles_per_split, stages; size_t smem; };
-bool wgrad_plan(const WgradParams& p, WgPlan& pl) {
+bool wgrad_plan(const WgradParams& p, int es, WgPlan& pl) {
   int tb;
   if (!pick_patch(p.H, p.W, WG_P, pl.tw, pl.th, tb) || tb != 1) return false;
   pl.tiles_x = p.W / pl.tw; pl.tiles_y = p.H / pl.th;
@@ -584,8 +629,9 @@ bool wgrad_plan(const WgradParams& p, WgPlan& pl) {
   if (want > max_split) want = max_split;
   pl.tiles_per_split = cdiv(pl.tiles_total, want);
   pl.nsplit = cdiv(pl.tiles_total, pl.tiles_per_split);
-  const size_t stage = WG_A_BYTES + (size_t)p.ks * p.ks * WG_GROUP_BYTES;
-  pl.stages = (int)((200 * 1024) / stage);
+  const size_t group = (size_t)WG_P * 32 * es;
+  const size_t stage = (4 + (size_t)p.ks * p.ks) * group;
+  pl.stages = (int)((212 * 1024) / stage);
   if (pl.stages > 6) pl.stages = 6;
   pl.smem = pl.stages * stage + 1024;
   return pl.stages >= 2;
@@ -593,27 +639,29 @@ bool wgrad_plan(const WgradParams& p, WgPlan& pl) {
 }  // namespace
 
 bool wgrad_tc_supported(const WgradParams& p, int dtype) {
-  if (dtype != PUB_BF16) return false;
+  if (dtype != PUB_BF16 && dtype != PUB_TF32) return false;
+  const int es = esize(dtype), al = 16 / es;
   if (p.ks != 1 && p.ks != 3) return false;
   if (p.c0 % 32 || p.c1 % 32 || p.c0 + p.c1 < 32 || p.cout % 32) return false;
-  if (p.ld0 % 8 || (p.x1 && p.ld1 % 8) || p.ld_dy % 8) return false;
+  if (p.ld0 % al || (p.x1 && p.ld1 % al) || p.ld_dy % al) return false;
   if (!aligned16(p.x0) || !aligned16(p.x1) || !aligned16(p.dy)) return false;
   WgPlan pl;
-  return wgrad_plan(p, pl);
+  return wgrad_plan(p, es, pl);
 }
 
-size_t wgrad_tc_workspace(const WgradParams& p) {
+size_t wgrad_tc_workspace(const WgradParams& p, int dtype) {
   WgPlan pl;
-  if (!wgrad_plan(p, pl)) return 0;
+  if (!wgrad_plan(p, esize(dtype), pl)) return 0;
   const int64_t n = (int64_t)p.ks * p.ks * p.cout * (p.c0 + p.c1);
   const int64_t M = (int64_t)p.B * p.H * p.W;
   return align_up((size_t)pl.nsplit * n * sizeof(float), 256) + align_up((size_t)cdiv(M, 1024) * p.cout * 4, 256);
 }
 
-int wgrad_tc(const WgradParams& p, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
+int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
   WgPlan pl;
-  PUB_REQUIRE(wgrad_tc_supported(p, PUB_BF16) && wgrad_plan(p, pl), "wgrad_tc: unsupported shape");
-  PUB_REQUIRE(ws_bytes >= wgrad_tc_workspace(p), "wgrad_tc: workspace too small");
+  const int es = esize(dtype);
+  PUB_REQUIRE(wgrad_tc_supported(p, dtype) && wgrad_plan(p, es, pl), "wgrad_tc: unsupported shape");
+  PUB_REQUIRE(ws_bytes >= wgrad_tc_workspace(p, dtype), "wgrad_tc: workspace too small");
   const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
   TcWgradArgs a{};
   a.c0 = p.c0; a.c1 = p.c1; a.cout = p.cout; a.taps = taps; a.ks = p.ks;
@@ -621,22 +669,28 @@ int wgrad_tc(const WgradParams& p, void* ws, size_t ws_bytes, int accumulate, cu
   a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
   a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages;
   a.part = (float*)ws;
+  const CUtensorMapSwizzle sw = es == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUtensorMap tmX0, tmX1, tmDY;
-  PUB_TRY(make_act_map(&tmX0, p.x0, p.c0, p.ld0, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, CU_TENSOR_MAP_SWIZZLE_64B));
-  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, p.c1, p.ld1, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  PUB_TRY(make_act_map(&tmX0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
+  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
   else tmX1 = tmX0;
-  PUB_TRY(make_act_map(&tmDY, p.dy, p.cout, p.ld_dy, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, CU_TENSOR_MAP_SWIZZLE_64B));
+  PUB_TRY(make_act_map(&tmDY, p.dy, es, p.cout, p.ld_dy, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
   static bool attr = false;
-  if (!attr) { PUB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+  if (!attr) {
+    PUB_TRY(set_smem_attr(wgrad_tc_kernel<2>, 220 * 1024));
+    PUB_TRY(set_smem_attr(wgrad_tc_kernel<4>, 220 * 1024));
+    attr = true;
+  }
   dim3 grid(cin / 32, cdiv(p.cout, 128), pl.nsplit);
-  wgrad_tc_kernel<<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
+  if (es == 2) wgrad_tc_kernel<2><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
+  else wgrad_tc_kernel<4><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
   wgrad_tc_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(a.part, p.dw, pl.nsplit, taps, p.cout, cin, accumulate);
   PUB_LAUNCH_CHECK();
   if (p.dbias) {
     float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * n * sizeof(float), 256));
-    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, PUB_BF16, bpart, p.dbias, accumulate, s));
+    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, p.dbias, accumulate, s));
   }
   return 0;
 }

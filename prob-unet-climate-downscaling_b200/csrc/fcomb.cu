@@ -414,6 +414,12 @@ int pub_fcomb_backward(const pub_fcomb_args* a, const float* dout, void* dfeat, 
   const int gx = bwd_grid_x(a->B, a->H * a->W);
   dim3 grid(gx, a->B);
   const size_t dyn = (size_t)a->M * F * 4 * 2;
+  static bool attr = false;
+  if (!attr) {  // static (tiles + weights, ~45 KB) + dynamic smem exceeds the 48 KB default limit for M > 8
+    PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
   if (!a->feat_nchw && a->dtype == PUB_BF16) fcomb_bwd_kernel<bf16><<<grid, NT, dyn, st>>>(d, dout, dfeat, part);
   else fcomb_bwd_kernel<float><<<grid, NT, dyn, st>>>(d, dout, dfeat, part);
   PUB_LAUNCH_CHECK();

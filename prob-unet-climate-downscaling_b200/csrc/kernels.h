@@ -14,6 +14,7 @@ struct ConvParams {
   const void* mask; int ld_mask;
   void* y; int ldy;
   int B, H, W, cout, ks, relu;
+  int round_tf32;  // SIMT path only: round the stored output to tf32 (PUB_TF32 tensors feed kind::tf32 MMAs)
 };
 
 struct WgradParams {
@@ -35,10 +36,10 @@ int nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, in
 
 // ---- conv_tc.cu (tcgen05 / TMEM / TMA)
 bool conv_tc_supported(const ConvParams& p, int dtype);
-int conv_tc(const ConvParams& p, cudaStream_t s);
+int conv_tc(const ConvParams& p, int dtype, cudaStream_t s);
 bool wgrad_tc_supported(const WgradParams& p, int dtype);
-size_t wgrad_tc_workspace(const WgradParams& p);
-int wgrad_tc(const WgradParams& p, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+size_t wgrad_tc_workspace(const WgradParams& p, int dtype);
+int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
 
 // dispatchers (api.cu)
 int conv_forward(const ConvParams& p, int dtype, int backend, cudaStream_t s);

@@ -71,7 +71,7 @@ class AxisAlignedConvGaussian(nn.Module):
         self._engine = None
 
     def engine(self):
-        dt = _native.resolve_dtype(self.compute_dtype)
+        dt = _native.resolve_encoder_dtype(self.compute_dtype)
         if self._engine is None or self._engine.dtype != dt:
             self._engine = _native.EncoderEngine(self, dt)
         return self._engine

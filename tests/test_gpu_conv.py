@@ -54,30 +54,38 @@ CASES = [
 ]
 
 
+def to_tf32(x):
+    """round-to-nearest onto the tf32 grid (10-bit mantissa), what PUB_TF32 tensors hold"""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16"])
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16", "tc_tf32"])
 def test_conv_forward(case, mode):
     N = _setup()
     B, H, W, c0, c1, cout, ks = case
-    dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
-    backend = N.BACKEND_TCGEN05 if mode == "tc_bf16" else N.BACKEND_SIMT
-    if mode == "tc_bf16" and (c0 % 32 or c1 % 32):
+    dt = torch.bfloat16 if mode.endswith("bf16") else torch.float32
+    backend = N.BACKEND_TCGEN05 if mode.startswith("tc") else N.BACKEND_SIMT
+    ndt = {"simt_f32": N.F32, "simt_bf16": N.BF16, "tc_bf16": N.BF16, "tc_tf32": N.TF32}[mode]
+    cast = to_tf32 if mode == "tc_tf32" else (lambda t: t.to(dt))
+    if mode.startswith("tc") and (c0 % 32 or c1 % 32):
         pytest.skip("tcgen05 path needs Cin % 32 == 0 (first layers run on the SIMT kernel)")
     g = torch.Generator(device="cuda").manual_seed(1)
     # inputs are channel slices of wider buffers -> exercises the pixel-stride (ld) handling
-    buf0 = torch.randn(B, H, W, c0 + 32, device="cuda", generator=g).to(dt)
+    buf0 = cast(torch.randn(B, H, W, c0 + 32, device="cuda", generator=g))
     x0 = buf0[..., :c0]
-    x1 = torch.randn(B, H, W, c1, device="cuda", generator=g).to(dt) if c1 else None
+    x1 = cast(torch.randn(B, H, W, c1, device="cuda", generator=g)) if c1 else None
     w = torch.randn(cout, c0 + c1, ks, ks, device="cuda", generator=g) / ((c0 + c1) * ks * ks) ** 0.5
     b = torch.randn(cout, device="cuda", generator=g) * 0.1
-    res = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
-    mask = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
-    wp = N.pack_conv_weight(w, N.BF16 if dt == torch.bfloat16 else N.F32)
+    res = cast(torch.randn(B, H, W, cout, device="cuda", generator=g))
+    mask = cast(torch.randn(B, H, W, cout, device="cuda", generator=g))
+    wp = N.pack_conv_weight(w, ndt)
     xin = x0 if x1 is None else torch.cat([x0, x1], dim=3)
     wq = wp.float().permute(1, 2, 0).reshape(cout, c0 + c1, ks, ks)   # the (rounded) weights the kernel sees
-    tol = 1e-4 if dt == torch.float32 else 1e-2
+    tol = {"simt_f32": 1e-4, "simt_bf16": 1e-2, "tc_bf16": 1e-2, "tc_tf32": 1e-3}[mode]   # tf32: output rounded to 10 bits
     for kw in (dict(), dict(res=res), dict(relu=True), dict(res=res, mask=mask)):
-        y = N.conv2d_nhwc(x0, wp, b, x1=x1, ksize=ks, backend=backend, **kw)
+        y = N.conv2d_nhwc(x0, wp, b, x1=x1, ksize=ks, backend=backend, dtype=ndt, **kw)
         ref = _ref_conv(xin, wq, b, **kw)
         torch.cuda.synchronize()
         e = rel_err(y.float(), ref)
@@ -85,19 +93,21 @@ def test_conv_forward(case, mode):
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] * c[1] * c[2] <= 4096 * 4])
-@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16"])
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16", "tc_tf32"])
 def test_conv_wgrad(case, mode):
     N = _setup()
     B, H, W, c0, c1, cout, ks = case
-    dt = torch.float32 if mode == "simt_f32" else torch.bfloat16
-    backend = N.BACKEND_TCGEN05 if mode == "tc_bf16" else N.BACKEND_SIMT
-    if mode == "tc_bf16" and (c0 % 32 or c1 % 32 or (H * W) % 64):
+    dt = torch.bfloat16 if mode.endswith("bf16") else torch.float32
+    backend = N.BACKEND_TCGEN05 if mode.startswith("tc") else N.BACKEND_SIMT
+    ndt = {"simt_f32": N.F32, "simt_bf16": N.BF16, "tc_bf16": N.BF16, "tc_tf32": N.TF32}[mode]
+    cast = to_tf32 if mode == "tc_tf32" else (lambda t: t.to(dt))
+    if mode.startswith("tc") and (c0 % 32 or c1 % 32 or (H * W) % 64):
         pytest.skip("tcgen05 wgrad needs Cin % 32 == 0 and 64-pixel K tiles")
     g = torch.Generator(device="cuda").manual_seed(2)
-    x0 = torch.randn(B, H, W, c0, device="cuda", generator=g).to(dt)
-    x1 = torch.randn(B, H, W, c1, device="cuda", generator=g).to(dt) if c1 else None
-    dy = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
-    dw, db = N.conv2d_wgrad_nhwc(x0, dy, ks, x1=x1, backend=backend)
+    x0 = cast(torch.randn(B, H, W, c0, device="cuda", generator=g))
+    x1 = cast(torch.randn(B, H, W, c1, device="cuda", generator=g)) if c1 else None
+    dy = cast(torch.randn(B, H, W, cout, device="cuda", generator=g))
+    dw, db = N.conv2d_wgrad_nhwc(x0, dy, ks, x1=x1, backend=backend, dtype=ndt)
     xin = (x0 if x1 is None else torch.cat([x0, x1], dim=3)).float().permute(0, 3, 1, 2)
     w = torch.zeros(cout, c0 + c1, ks, ks, device="cuda", requires_grad=True)
     bb = torch.zeros(cout, device="cuda", requires_grad=True)
