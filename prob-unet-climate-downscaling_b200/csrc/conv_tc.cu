@@ -340,8 +340,9 @@ struct TcWgradArgs {
 
 constexpr int WG_P = 64;  // pixels (K) per stage
 
-// ES = 2: bf16 operands, 32-channel groups are 64 B rows (SWIZZLE_64B), 16 pixels per MMA
-// ES = 4: tf32 operands, 32-channel groups are 128 B rows (SWIZZLE_128B), 8 pixels per MMA
+// ES = 2: bf16 operands, 32-channel groups are 64 B rows (SWIZZLE_64B, 8-row swizzle atoms), 16 pixels per MMA
+// ES = 4: tf32 operands, 32-channel groups are 128 B rows; MN-major tf32 only exists with the
+//         SWIZZLE_128B_BASE32B layout (32-byte chunks XOR row%4, 4-row atoms; TMA mode 128B_ATOM_32B), 8 pixels per MMA
 template <int ES>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                             const __grid_constant__ CUtensorMap tmX1,
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   constexpr uint32_t ROW = 32 * ES;                      // bytes of one 32-channel row
   constexpr uint32_t WG_GROUP_BYTES = WG_P * ROW;        // one 32-channel x 64-pixel box
   constexpr uint32_t WG_A_BYTES = 4 * WG_GROUP_BYTES;
-  constexpr uint32_t LAYOUT = ES == 2 ? 4u : 2u;
+  constexpr uint32_t LAYOUT = ES == 2 ? 4u : 1u;         // SWIZZLE_64B : SWIZZLE_128B_BASE32B
+  constexpr uint32_t SBO_WG = ES == 2 ? 8 * ROW : 4 * ROW;  // pitch between swizzle atoms along K (8 rows / 4 rows)
   constexpr int KROWS = 32 / ES;                         // pixels per MMA (UMMA_K)
   constexpr uint32_t KSTEP_BYTES = KROWS * ROW;          // = 1024 for both element sizes
   extern __shared__ uint8_t smem_raw[];
@@ -423,8 +425,8 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
         for (int tap = 0; tap < a.taps; ++tap) {
 #pragma unroll
           for (int k = 0; k < WG_P / KROWS; ++k) {
-            const uint64_t ad = make_desc(sa + k * KSTEP_BYTES, WG_GROUP_BYTES, 8 * ROW, LAYOUT);
-            const uint64_t bd = make_desc(sb + tap * WG_GROUP_BYTES + k * KSTEP_BYTES, WG_GROUP_BYTES, 8 * ROW, LAYOUT);
+            const uint64_t ad = make_desc(sa + k * KSTEP_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
+            const uint64_t bd = make_desc(sb + tap * WG_GROUP_BYTES + k * KSTEP_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
             umma<ES>(tmem_base + (uint32_t)(tap * 32), ad, bd, idesc, (!first || k != 0) ? 1u : 0u);
           }
         }
@@ -669,7 +671,7 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
   a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages;
   a.part = (float*)ws;
-  const CUtensorMapSwizzle sw = es == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw = es == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX0, tmX1, tmDY;
   PUB_TRY(make_act_map(&tmX0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
   if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
