@@ -173,7 +173,95 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   dw[o] = accumulate ? dw[o] + s : s;
 }
 
-// column sums over pixels: partial[chunk][C]
+// Weight gradient of the Cin <= 8 first layers (3 / 6 input variables): lane = output channel, the 9 x Cin
+// accumulators live in registers, x values are warp-uniform broadcast loads.  part[cta][tap][co][ci].
+template <typename T, int CMAX>
+__global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float* __restrict__ part, int pix_per_cta) {
+  __shared__ float red[9 * CMAX][32];
+  const T* x0 = (const T*)p.x0;
+  const T* dy = (const T*)p.dy;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = blockIdx.y * 32 + lane;
+  const int cin = p.c0, taps = p.ks * p.ks, half = p.ks / 2;
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
+  float acc[9][CMAX];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[t][c] = 0.f;
+  for (int64_t m = pbeg + warp; m < pend; m += 8) {
+    const int x = (int)(m % p.W), y = (int)((m / p.W) % p.H), b = (int)(m / ((int64_t)p.W * p.H));
+    const float g = co < p.cout ? to_f<T>(dy[m * p.ld_dy + co]) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t < taps) {
+        const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+          const T* xp = x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < cin) acc[t][c] = fmaf(g, to_f<T>(xp[c]), acc[t][c]);
+        }
+      }
+    }
+  }
+  // sum the 8 warps in a fixed order
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) red[t * CMAX + c][lane] = (w == 0 ? 0.f : red[t * CMAX + c][lane]) + acc[t][c];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < taps * 32 * cin; i += 256) {
+    const int ci = i % cin, l = (i / cin) % 32, t = i / (cin * 32);
+    const int c2 = blockIdx.y * 32 + l;
+    if (c2 < p.cout) part[(((int64_t)blockIdx.x * taps + t) * p.cout + c2) * cin + ci] = red[t * CMAX + ci][l];
+  }
+}
+
+// column sums over pixels: partial[chunk][C]  (vectorised: 8 channels per thread, several rows in flight)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int ld, int C, int64_t M,
+                                                         int rows_per_chunk, float* __restrict__ part) {
+  extern __shared__ float sm[];  // [RY][V][8]
+  const int V = C / 8, RY = 256 / V;
+  const int v = threadIdx.x % V, ry = threadIdx.x / V;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (ry < RY) {
+    int64_t r = r0 + ry;
+    for (; r + 3 * (int64_t)RY < r1; r += 4 * (int64_t)RY) {
+      float f0[8], f1[8], f2[8], f3[8];
+      Vec8<T>::load(x + r * ld + v * 8, f0);
+      Vec8<T>::load(x + (r + RY) * ld + v * 8, f1);
+      Vec8<T>::load(x + (r + 2 * (int64_t)RY) * ld + v * 8, f2);
+      Vec8<T>::load(x + (r + 3 * (int64_t)RY) * ld + v * 8, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < r1; r += RY) {
+      float f0[8];
+      Vec8<T>::load(x + r * ld + v * 8, f0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += f0[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[(ry * V + v) * 8 + j] = a[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V * 8; i += 256) {
+    float s = 0.f;
+    for (int q = 0; q < RY; ++q) s += sm[q * V * 8 + i];
+    part[(int64_t)blockIdx.x * C + i] = s;
+  }
+}
+
 template <typename T>
 __global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int C, int64_t M, int rows_per_chunk,
                                       float* __restrict__ part) {
@@ -245,6 +333,16 @@ int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
   return 0;
 }
 
+static bool smallc_ok(const WgradParams& p) { return p.c1 == 0 && p.c0 <= 8 && (p.ks == 1 || p.ks == 3); }
+static void smallc_plan(const WgradParams& p, int& nctas, int& ppc) {
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  int want = 4 * num_sms() / cdiv(p.cout, 32);
+  if (want < 1) want = 1;
+  ppc = (int)((M + want - 1) / want);
+  if (ppc < 256) ppc = 256;
+  nctas = cdiv(M, ppc);
+}
+
 static void wgrad_simt_plan(const WgradParams& p, int& nsplit, int& pps) {
   const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
   const int64_t M = (int64_t)p.B * p.H * p.W;
@@ -260,6 +358,11 @@ static void wgrad_simt_plan(const WgradParams& p, int& nsplit, int& pps) {
 size_t wgrad_simt_workspace(const WgradParams& p) {
   int nsplit, pps;
   wgrad_simt_plan(p, nsplit, pps);
+  if (smallc_ok(p)) {
+    int nctas, ppc;
+    smallc_plan(p, nctas, ppc);
+    if (nctas > nsplit) nsplit = nctas;
+  }
   const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const size_t a = (size_t)nsplit * taps * p.cout * cin * sizeof(float);
@@ -271,9 +374,15 @@ int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, floa
            cudaStream_t s) {
   const int rows = 1024;
   const int nchunk = cdiv(M, rows);
-  dim3 grid(nchunk, cdiv(C, 64));
-  if (dtype == PUB_BF16) colsum_partial_kernel<bf16><<<grid, 64, 0, s>>>((const bf16*)x, ld, C, M, rows, part);
-  else colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)x, ld, C, M, rows, part);
+  if (C % 8 == 0 && ld % 8 == 0 && C <= 2048 && (((uintptr_t)x) & 31) == 0) {
+    const size_t smem = (size_t)(256 / (C / 8)) * (C / 8) * 8 * sizeof(float);
+    if (dtype == PUB_BF16) colsum_vec_kernel<bf16><<<nchunk, 256, smem, s>>>((const bf16*)x, ld, C, M, rows, part);
+    else colsum_vec_kernel<float><<<nchunk, 256, smem, s>>>((const float*)x, ld, C, M, rows, part);
+  } else {
+    dim3 grid(nchunk, cdiv(C, 64));
+    if (dtype == PUB_BF16) colsum_partial_kernel<bf16><<<grid, 64, 0, s>>>((const bf16*)x, ld, C, M, rows, part);
+    else colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)x, ld, C, M, rows, part);
+  }
   PUB_LAUNCH_CHECK();
   colsum_final_kernel<<<cdiv(C, 128), 128, 0, s>>>(part, nchunk, C, out, accumulate);
   PUB_LAUNCH_CHECK();
@@ -287,9 +396,18 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
   PUB_REQUIRE(ws_bytes >= wgrad_simt_workspace(p), "wgrad workspace too small (%zu < %zu)", ws_bytes,
               wgrad_simt_workspace(p));
   float* part = (float*)ws;
-  dim3 grid(cdiv(cin, BN), cdiv(p.cout, BM), taps * nsplit);
-  if (dtype == PUB_BF16) wgrad_simt_kernel<bf16><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
-  else wgrad_simt_kernel<float><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
+  if (smallc_ok(p)) {
+    int nctas, ppc;
+    smallc_plan(p, nctas, ppc);
+    dim3 grid(nctas, cdiv(p.cout, 32));
+    if (dtype == PUB_BF16) wgrad_smallc_kernel<bf16, 8><<<grid, 256, 0, s>>>(p, part, ppc);
+    else wgrad_smallc_kernel<float, 8><<<grid, 256, 0, s>>>(p, part, ppc);
+    nsplit = nctas;
+  } else {
+    dim3 grid(cdiv(cin, BN), cdiv(p.cout, BM), taps * nsplit);
+    if (dtype == PUB_BF16) wgrad_simt_kernel<bf16><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
+    else wgrad_simt_kernel<float><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
+  }
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
   wgrad_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part, p.dw, nsplit, taps, p.cout, cin, accumulate);

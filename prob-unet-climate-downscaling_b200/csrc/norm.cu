@@ -230,18 +230,21 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
   }
 }
 
-// backward finalize 2: per channel parameter gradients (sum over batch and chunks, fixed order)
+// backward finalize 2: per channel parameter gradients; one warp per channel, lanes stride over the
+// (batch, chunk) partials, fixed shuffle tree -> deterministic
 __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ dfilm) {
   const int C = p.c0 + p.c1;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < p.B; ++b)
-    for (int k = 0; k < nchunk; ++k) {
-      const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
-      s1 += (double)v.x; s2 += (double)v.y;
-    }
+  const int n = p.B * nchunk;
+  for (int i = lane; i < n; i += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((int64_t)i * C + c) * 2);
+    s1 += (double)v.x; s2 += (double)v.y;
+  }
+  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+  if (lane != 0) return;
   const float sc = p.film ? 1.f + p.film[c] : 1.f;
   dgamma[c] = (float)(s2 * sc);
   dbeta[c] = (float)(s1 * sc);
@@ -359,7 +362,7 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   PUB_LAUNCH_CHECK();
   gn_bwd_group_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc, bcoef);
   PUB_LAUNCH_CHECK();
-  gn_bwd_param_kernel<<<cdiv(C, 64), 64, 0, s>>>(p, p.partial, nc, dgamma, dbeta, dfilm);
+  gn_bwd_param_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(p, p.partial, nc, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)p.B * p.H * p.W * V;
   if (dx) {
