@@ -71,6 +71,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Samples before this point (warm-up) are ignored."""
+        try:
+            self.skip = sum(1 for _ in open(self.path))
+        except Exception:
+            self.skip = 0
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -82,7 +89,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        for li, line in enumerate(open(self.path)):
+            if li < getattr(self, "skip", 0):
+                continue
             f = [c.strip() for c in line.split(",")]
             if len(f) < 7:
                 continue
@@ -298,21 +307,25 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi is started BEFORE the warm-up: its NVML start-up (~1 s) briefly serialises with the CUDA driver
+    # and must not fall into the timed region
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device(x, y)
     # ---- device-resident timing
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark()
     l0 = N.lib().pub_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
         loss = step_device(x, y)
-    e1.record()
+        evs[i + 1].record()
     barrier()
     launches = (N.lib().pub_launch_count() - l0)
     clocks = sampler.stop()
-    t_dev = e0.elapsed_time(e1) * 1e-3
+    t_dev = evs[0].elapsed_time(evs[-1]) * 1e-3
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H of the loss
     barrier()
     w0 = time.perf_counter()
@@ -331,7 +344,8 @@ def run_b200(args):
 
     line = {
         "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+        "ms_per_step_each": [round(v, 2) for v in per_step], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),

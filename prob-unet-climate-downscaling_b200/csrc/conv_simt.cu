@@ -160,15 +160,21 @@ __global__ void __launch_bounds__(NT) wgrad_simt_kernel(WgradParams p, float* __
   }
 }
 
-// sum the split partials in a fixed order -> OIHW f32 gradient (deterministic split-K)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int taps,
-                                    int cout, int cin, int accumulate) {
+// sum the split partials in a fixed order -> OIHW f32 gradient (deterministic split-K).
+// LANES = 1: one thread per element; LANES = 32: one warp per element (many splits, few elements)
+template <int LANES>
+__global__ void wgrad_reduce_kernel_t(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int taps,
+                                      int cout, int cin, int accumulate) {
   const int64_t n = (int64_t)taps * cout * cin;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = gid / LANES;
+  const int lane = (int)(gid % LANES);
   if (i >= n) return;
-  const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
   float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * n + i];
+  for (int k = lane; k < nsplit; k += LANES) s += part[(int64_t)k * n + i];
+  if (LANES == 32) s = warp_sum(s);
+  if (lane != 0) return;
+  const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
   const int64_t o = ((int64_t)co * cin + ci) * taps + tap;  // OIHW with (ky,kx) == tap
   dw[o] = accumulate ? dw[o] + s : s;
 }
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
   const int cin = p.c0, taps = p.ks * p.ks, half = p.ks / 2;
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
+  const bool vec = CMAX == 8 && p.ld0 % 8 == 0 && (((uintptr_t)p.x0) & 31) == 0;
   float acc[9][CMAX];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
@@ -199,9 +206,17 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
         const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
         if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
           const T* xp = x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0;
+          if (vec) {  // the input buffer is padded to 8 channels: one 16/32-byte warp-uniform load per tap
+            float xv[8];
+            Vec8<T>::load(xp, xv);
 #pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < cin) acc[t][c] = fmaf(g, to_f<T>(xp[c]), acc[t][c]);
+            for (int c = 0; c < CMAX; ++c)
+              if (c < cin) acc[t][c] = fmaf(g, xv[c], acc[t][c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+              if (c < cin) acc[t][c] = fmaf(g, to_f<T>(xp[c]), acc[t][c]);
+          }
         }
       }
     }
@@ -274,11 +289,13 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int C, in
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nchunk, int C, float* __restrict__ out,
                                     int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel, lanes stride over the chunk partials, fixed shuffle tree
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0;
-  for (int k = 0; k < nchunk; ++k) s += (double)part[(int64_t)k * C + c];
-  out[c] = accumulate ? out[c] + (float)s : (float)s;
+  for (int k = lane; k < nchunk; k += 32) s += (double)part[(int64_t)k * C + c];
+  s = warp_sum_d(s);
+  if (lane == 0) out[c] = accumulate ? out[c] + (float)s : (float)s;
 }
 
 template <typename T>
@@ -384,7 +401,17 @@ int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, floa
     else colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)x, ld, C, M, rows, part);
   }
   PUB_LAUNCH_CHECK();
-  colsum_final_kernel<<<cdiv(C, 128), 128, 0, s>>>(part, nchunk, C, out, accumulate);
+  colsum_final_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(part, nchunk, C, out, accumulate);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int wgrad_reduce(const float* part, float* dw, int nsplit, int taps, int cout, int cin, int accumulate, cudaStream_t s) {
+  const int64_t n = (int64_t)taps * cout * cin;
+  if (nsplit >= 16 && n * 32 <= (int64_t)1 << 26)
+    wgrad_reduce_kernel_t<32><<<cdiv(n * 32, 256), 256, 0, s>>>(part, dw, nsplit, taps, cout, cin, accumulate);
+  else
+    wgrad_reduce_kernel_t<1><<<cdiv(n, 256), 256, 0, s>>>(part, dw, nsplit, taps, cout, cin, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -410,8 +437,7 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
   }
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
-  wgrad_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part, p.dw, nsplit, taps, p.cout, cin, accumulate);
-  PUB_LAUNCH_CHECK();
+  PUB_TRY(wgrad_reduce(part, p.dw, nsplit, taps, p.cout, cin, accumulate, s));
   if (p.dbias) {
     float* bpart = (float*)((char*)ws + align_up((size_t)nsplit * n * sizeof(float), 256));
     PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, p.dbias, accumulate, s));

@@ -462,18 +462,6 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, ncols);
 }
 
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int taps,
-                                       int cout, int cin, int accumulate) {
-  const int64_t n = (int64_t)taps * cout * cin;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
-  float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += part[(int64_t)k * n + i];
-  const int64_t o = ((int64_t)co * cin + ci) * taps + tap;
-  dw[o] = accumulate ? dw[o] + s : s;
-}
-
 // ------------------------------------------------------------------ host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -688,8 +676,7 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   else wgrad_tc_kernel<4><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
-  wgrad_tc_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(a.part, p.dw, pl.nsplit, taps, p.cout, cin, accumulate);
-  PUB_LAUNCH_CHECK();
+  PUB_TRY(wgrad_reduce(a.part, p.dw, pl.nsplit, taps, p.cout, cin, accumulate, s));
   if (p.dbias) {
     float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * n * sizeof(float), 256));
     PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, p.dbias, accumulate, s));

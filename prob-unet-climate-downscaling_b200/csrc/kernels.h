@@ -28,6 +28,7 @@ struct WgradParams {
 int conv_simt(const ConvParams& p, int dtype, cudaStream_t s);
 size_t wgrad_simt_workspace(const WgradParams& p);
 int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
+int wgrad_reduce(const float* part, float* dw, int nsplit, int taps, int cout, int cin, int accumulate, cudaStream_t s);
 int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, float* out, int accumulate, cudaStream_t s);
 int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype, int tflip, cudaStream_t s);
 int nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, int ldy, int B, int H, int W, int dtype,

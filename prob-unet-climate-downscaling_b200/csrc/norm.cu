@@ -15,7 +15,12 @@ namespace pub {
 namespace {
 
 constexpr int GN_NT = 256;
-constexpr int GN_ROWS = 256;  // pixels per statistics chunk
+constexpr int GN_ROWS = 256;  // pixels per chunk (one CTA)
+
+// Every heavy kernel uses the same decomposition: grid = (pixel chunks, batch); inside a CTA thread t owns the
+// 8-channel vector v = t % V for the rows pr, pr + ppi, ... of the chunk (ppi = 256 / V).  The per-channel
+// constants of that vector (affine a/b, backward c1/c2/c3) are loaded ONCE into registers, so the inner loop is
+// 16/32-byte loads + ~10 FLOP per element -- the only way these passes get near the HBM roofline.
 
 template <typename T>
 __device__ __forceinline__ void load_vec(const GnParams& p, int64_t pix, int v, float (&f)[8]) {
@@ -24,24 +29,70 @@ __device__ __forceinline__ void load_vec(const GnParams& p, int64_t pix, int v, 
   else Vec8<T>::load((const T*)p.x1 + pix * p.ld1 + (c - p.c0), f);
 }
 
-// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0)
-__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint64_t subseq, int64_t e, float p, bool (&keep)[8]) {
-  const uint4 r0 = Philox::gen(seed, subseq, (uint64_t)(e >> 2));
-  const uint4 r1 = Philox::gen(seed, subseq, (uint64_t)(e >> 2) + 1);
-  keep[0] = Philox::u01(r0.x) >= p; keep[1] = Philox::u01(r0.y) >= p;
-  keep[2] = Philox::u01(r0.z) >= p; keep[3] = Philox::u01(r0.w) >= p;
-  keep[4] = Philox::u01(r1.x) >= p; keep[5] = Philox::u01(r1.y) >= p;
-  keep[6] = Philox::u01(r1.z) >= p; keep[7] = Philox::u01(r1.w) >= p;
+// coef[b][c][2] -> a[8], bb[8] for channels v*8 .. v*8+7
+__device__ __forceinline__ void load_affine(const float* coef, int b, int C, int v, float (&a)[8], float (&bb)[8]) {
+  const float4* q = reinterpret_cast<const float4*>(coef + ((int64_t)b * C + v * 8) * 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = q[i];
+    a[2 * i] = t.x; bb[2 * i] = t.y; a[2 * i + 1] = t.z; bb[2 * i + 1] = t.w;
+  }
+}
+
+// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0): ONE Philox call,
+// 16 random bits per element, keep <=> u16 >= round(p * 65536)
+__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint64_t subseq, int64_t e, uint32_t thresh, bool (&keep)[8]) {
+  const uint4 r = Philox::gen(seed, subseq, (uint64_t)(e >> 3));
+  keep[0] = (r.x & 0xFFFFu) >= thresh; keep[1] = (r.x >> 16) >= thresh;
+  keep[2] = (r.y & 0xFFFFu) >= thresh; keep[3] = (r.y >> 16) >= thresh;
+  keep[4] = (r.z & 0xFFFFu) >= thresh; keep[5] = (r.z >> 16) >= thresh;
+  keep[6] = (r.w & 0xFFFFu) >= thresh; keep[7] = (r.w >> 16) >= thresh;
+}
+__device__ __forceinline__ uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
+
+// gradient wrt the activated output at INPUT resolution, rebuilt from dy (output resolution) + dropout
+template <typename T>
+__device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__ dy, int b, int r, int64_t pix, int C,
+                                        int v, uint32_t thresh, float inv_keep, float (&g)[8]) {
+  if (p.resample == 0) {
+    Vec8<T>::load(dy + pix * C + v * 8, g);
+  } else {
+    const int yy = r / p.W, xx = r % p.W;
+    if (p.resample == 1) {  // forward was a 2x2 mean
+      const int64_t q = ((int64_t)b * (p.H / 2) + yy / 2) * (p.W / 2) + xx / 2;
+      Vec8<T>::load(dy + q * C + v * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+    } else {  // forward was a nearest 2x upsample
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
+        float h[8];
+        Vec8<T>::load(dy + q * C + v * 8, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += h[j];
+      }
+    }
+  }
+  if (p.p_drop > 0.f) {
+    bool keep[8];
+    dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------- per-channel two-value partial sums
-// MODE 0: (x, x^2)            -- forward statistics
-// MODE 1: (du, du * xhat)     -- backward; du = g_y * silu'(a x + b) with g_y rebuilt from dy
+// MODE 0: (x, x^2)          -- forward statistics
+// MODE 1: (du, du * x)      -- backward; du = g_y * silu'(a x + b).  (sum du*xhat is formed in the finalize
+//                              kernels as rstd * (sum du*x - mean * sum du).)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* __restrict__ dy, float* __restrict__ part) {
   extern __shared__ float sm[];  // [ppi][V][16]
   const int C = p.c0 + p.c1, V = C / 8;
-  const int ppi = GN_NT / V;  // pixels per iteration
+  const int ppi = GN_NT / V;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int HW = p.H * p.W;
   const int r0 = chunk * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
@@ -51,51 +102,25 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (pr < ppi) {
-    const int cpg = C / p.groups;
+    float a[8], bb[8];
+    if (MODE == 1) load_affine(p.coef, b, C, v, a, bb);
+    const uint32_t thresh = drop_thresh(p.p_drop);
+    const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     for (int r = r0 + pr; r < r1; r += ppi) {
       const int64_t pix = (int64_t)b * HW + r;
       float x[8];
       load_vec<T>(p, pix, v, x);
       if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] += x[j] * x[j]; }
+        for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
       } else {
-        // rebuild g_y (gradient wrt the activated output at input resolution)
         float g[8];
-        const int yy = r / p.W, xx = r % p.W;
-        if (p.resample == 0) {
-          Vec8<T>::load(dy + pix * C + v * 8, g);
-        } else if (p.resample == 1) {  // forward was 2x2 mean
-          const int64_t q = ((int64_t)b * (p.H / 2) + yy / 2) * (p.W / 2) + xx / 2;
-          Vec8<T>::load(dy + q * C + v * 8, g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
-        } else {  // forward was nearest 2x upsample
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = 0.f;
-          for (int d = 0; d < 4; ++d) {
-            const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
-            float h[8];
-            Vec8<T>::load(dy + q * C + v * 8, h);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] += h[j];
-          }
-        }
-        if (p.p_drop > 0.f) {
-          bool keep[8];
-          dropout_keep8(p.seed, p.subseq, pix * C + v * 8, p.p_drop, keep);
-          const float inv = 1.f / (1.f - p.p_drop);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv : 0.f;
-        }
+        load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = v * 8 + j;
-          const float2 ab = *reinterpret_cast<const float2*>(p.coef + ((int64_t)b * C + c) * 2);
-          const float2 st = *reinterpret_cast<const float2*>(p.stats + ((int64_t)b * p.groups + c / cpg) * 2);
-          const float du = g[j] * silu_grad_f(ab.x * x[j] + ab.y);
+          const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
           s1[j] += du;
-          s2[j] += du * (x[j] - st.x) * st.y;
+          s2[j] = fmaf(du, x[j], s2[j]);
         }
       }
     }
@@ -103,8 +128,7 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
     for (int j = 0; j < 8; ++j) { sm[(pr * V + v) * 16 + j] = s1[j]; sm[(pr * V + v) * 16 + 8 + j] = s2[j]; }
   }
   __syncthreads();
-  // thread (v, j2) sums over pr in fixed order
-  for (int i = t; i < V * 16; i += GN_NT) {
+  for (int i = t; i < V * 16; i += GN_NT) {  // fixed-order sum over the row slots
     float s = 0.f;
     for (int q = 0; q < ppi; ++q) s += sm[q * V * 16 + i];
     const int vv = i / 16, jj = i % 16;
@@ -142,33 +166,35 @@ __global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, i
   }
 }
 
-// y = resample(dropout(silu(a x + b)))
+// y = resample(dropout(silu(a x + b))); the chunk index runs over INPUT pixels (none / up) or OUTPUT pixels (down)
 template <typename T>
 __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restrict__ y) {
-  const int C = p.c0 + p.c1, V = C / 8;
+  const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
+  const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
+  if (pr >= ppi) return;
+  float a[8], bb[8];
+  load_affine(p.coef, b, C, v, a, bb);
   const int HW = p.H * p.W;
-  const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   if (p.resample != 1) {
-    const int64_t total = (int64_t)p.B * HW * V;
-    for (int64_t i = (int64_t)blockIdx.x * GN_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * GN_NT) {
-      const int v = (int)(i % V);
-      const int64_t pix = i / V;
-      const int b = (int)(pix / HW);
+    const uint32_t thresh = drop_thresh(p.p_drop);
+    const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
+    const int r0 = blockIdx.x * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+    for (int r = r0 + pr; r < r1; r += ppi) {
+      const int64_t pix = (int64_t)b * HW + r;
       float x[8], o[8];
       load_vec<T>(p, pix, v, x);
-      const float* cf = p.coef + ((int64_t)b * C + v * 8) * 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = silu_f(cf[2 * j] * x[j] + cf[2 * j + 1]);
+      for (int j = 0; j < 8; ++j) o[j] = silu_f(fmaf(a[j], x[j], bb[j]));
       if (p.p_drop > 0.f) {
         bool keep[8];
-        dropout_keep8(p.seed, p.subseq, pix * C + v * 8, p.p_drop, keep);
+        dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
       }
       if (p.resample == 0) {
         Vec8<T>::store(y + pix * C + v * 8, o);
       } else {  // nearest 2x upsample: write the 2x2 children
-        const int r = (int)(pix % HW), yy = r / p.W, xx = r % p.W;
+        const int yy = r / p.W, xx = r % p.W;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
           const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
@@ -177,13 +203,10 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
       }
     }
   } else {  // 2x2 mean of the activated values
-    const int Ho = p.H / 2, Wo = p.W / 2;
-    const int64_t total = (int64_t)p.B * Ho * Wo * V;
-    for (int64_t i = (int64_t)blockIdx.x * GN_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * GN_NT) {
-      const int v = (int)(i % V);
-      const int64_t q = i / V;
-      const int xo = (int)(q % Wo), yo = (int)((q / Wo) % Ho), b = (int)(q / ((int64_t)Wo * Ho));
-      const float* cf = p.coef + ((int64_t)b * C + v * 8) * 2;
+    const int Ho = p.H / 2, Wo = p.W / 2, HWo = Ho * Wo;
+    const int r0 = blockIdx.x * GN_ROWS, r1 = min(HWo, r0 + GN_ROWS);
+    for (int r = r0 + pr; r < r1; r += ppi) {
+      const int yo = r / Wo, xo = r % Wo;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
@@ -193,40 +216,42 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
         float x[8];
         load_vec<T>(p, pix, v, x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += silu_f(cf[2 * j] * x[j] + cf[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) o[j] += silu_f(fmaf(a[j], x[j], bb[j]));
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
-      Vec8<T>::store(y + q * C + v * 8, o);
+      Vec8<T>::store(y + ((int64_t)b * HWo + r) * C + v * 8, o);
     }
   }
 }
 
 // backward finalize 1: per (b, g) -> bcoef[b][c] = (c1, c2, c3):  dx = c1*du + c2*x + c3
+// partials hold P1 = sum du, P2 = sum du*x;  sum du*xhat = rstd * (P2 - mean * P1)
 __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef) {
   const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= p.B * p.groups) return;
   const int b = wid / p.groups, g = wid % p.groups;
-  double m1 = 0.0, m2 = 0.0;
+  double q1 = 0.0, q2 = 0.0;
   for (int i = lane; i < nchunk * cpg; i += 32) {
     const int k = i / cpg, c = g * cpg + i % cpg;
     const float sc = p.film ? 1.f + p.film[c] : 1.f;
     const double gp = (double)p.gamma[c] * sc;
     const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
-    m1 += gp * (double)v.x; m2 += gp * (double)v.y;
+    q1 += gp * (double)v.x; q2 += gp * (double)v.y;
   }
-  m1 = warp_sum_d(m1); m2 = warp_sum_d(m2);
-  const double n = (double)cpg * p.H * p.W;
-  m1 /= n; m2 /= n;
+  q1 = warp_sum_d(q1); q2 = warp_sum_d(q2);
   const float mean = p.stats[((int64_t)b * p.groups + g) * 2], rstd = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
+  const double n = (double)cpg * p.H * p.W;
+  const double m1 = q1 / n;
+  const double m2 = (double)rstd * (q2 - (double)mean * q1) / n;
   const float c2 = (float)(-(double)rstd * rstd * m2);
   const float c3 = (float)(-(double)rstd * m1 + (double)rstd * rstd * m2 * mean);
   for (int i = lane; i < cpg; i += 32) {
     const int c = g * cpg + i;
     const float sc = p.film ? 1.f + p.film[c] : 1.f;
-    float* o = bcoef + ((int64_t)b * C + c) * 3;
-    o[0] = rstd * p.gamma[c] * sc; o[1] = c2; o[2] = c3;
+    float* o = bcoef + ((int64_t)b * C + c) * 4;
+    o[0] = rstd * p.gamma[c] * sc; o[1] = c2; o[2] = c3; o[3] = 0.f;
   }
 }
 
@@ -234,14 +259,17 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
 // (batch, chunk) partials, fixed shuffle tree -> deterministic
 __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ dfilm) {
-  const int C = p.c0 + p.c1;
+  const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
   const int n = p.B * nchunk;
   for (int i = lane; i < n; i += 32) {
+    const int b = i / nchunk;
+    const float2 st = *reinterpret_cast<const float2*>(p.stats + ((int64_t)b * p.groups + c / cpg) * 2);
     const float2 v = *reinterpret_cast<const float2*>(part + ((int64_t)i * C + c) * 2);
-    s1 += (double)v.x; s2 += (double)v.y;
+    s1 += (double)v.x;
+    s2 += (double)st.y * ((double)v.y - (double)st.x * (double)v.x);
   }
   s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
   if (lane != 0) return;
@@ -258,48 +286,29 @@ template <typename T>
 __global__ void __launch_bounds__(GN_NT) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
                                                              const float* __restrict__ bcoef, T* __restrict__ dx,
                                                              const T* __restrict__ addend, int ld_add) {
-  const int C = p.c0 + p.c1, V = C / 8;
-  const int HW = p.H * p.W;
-  const int64_t total = (int64_t)p.B * HW * V;
+  const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
+  const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
+  if (pr >= ppi) return;
+  float a[8], bb[8], c1[8], c2[8], c3[8];
+  load_affine(p.coef, b, C, v, a, bb);
+  {
+    const float4* q = reinterpret_cast<const float4*>(bcoef + ((int64_t)b * C + v * 8) * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 u = q[j]; c1[j] = u.x; c2[j] = u.y; c3[j] = u.z; }
+  }
+  const uint32_t thresh = drop_thresh(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-  for (int64_t i = (int64_t)blockIdx.x * GN_NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * GN_NT) {
-    const int v = (int)(i % V);
-    const int64_t pix = i / V;
-    const int b = (int)(pix / HW), r = (int)(pix % HW), yy = r / p.W, xx = r % p.W;
-    float x[8], g[8];
+  const int HW = p.H * p.W;
+  const int r0 = blockIdx.x * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+  for (int r = r0 + pr; r < r1; r += ppi) {
+    const int64_t pix = (int64_t)b * HW + r;
+    float x[8], g[8], o[8];
     load_vec<T>(p, pix, v, x);
-    if (p.resample == 0) {
-      Vec8<T>::load(dy + pix * C + v * 8, g);
-    } else if (p.resample == 1) {
-      const int64_t q = ((int64_t)b * (p.H / 2) + yy / 2) * (p.W / 2) + xx / 2;
-      Vec8<T>::load(dy + q * C + v * 8, g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
-        float h[8];
-        Vec8<T>::load(dy + q * C + v * 8, h);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += h[j];
-      }
-    }
-    if (p.p_drop > 0.f) {
-      bool keep[8];
-      dropout_keep8(p.seed, p.subseq, pix * C + v * 8, p.p_drop, keep);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
-    }
-    const float* cf = p.coef + ((int64_t)b * C + v * 8) * 2;
-    const float* bc = bcoef + ((int64_t)b * C + v * 8) * 3;
-    float o[8];
+    load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float du = g[j] * silu_grad_f(cf[2 * j] * x[j] + cf[2 * j + 1]);
-      o[j] = bc[3 * j] * du + bc[3 * j + 1] * x[j] + bc[3 * j + 2];
+      const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
+      o[j] = fmaf(c1[j], du, fmaf(c2[j], x[j], c3[j]));
     }
     if (addend) {
       float ad[8];
@@ -330,7 +339,7 @@ inline int grid_for(int64_t n) {
 }  // namespace
 
 size_t gn_partial_floats(int B, int C, int H, int W) {
-  return (size_t)B * cdiv((int64_t)H * W, GN_ROWS) * C * 2 + (size_t)B * C * 3;
+  return (size_t)B * cdiv((int64_t)H * W, GN_ROWS) * C * 2 + (size_t)B * C * 4 + 64;
 }
 
 int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
@@ -343,9 +352,9 @@ int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
   PUB_LAUNCH_CHECK();
   gn_finalize_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc);
   PUB_LAUNCH_CHECK();
-  const int64_t n = (int64_t)p.B * p.H * p.W * V / (p.resample == 1 ? 4 : 1);
-  if (dtype == PUB_BF16) gn_apply_kernel<bf16><<<grid_for(n), GN_NT, 0, s>>>(p, (bf16*)y);
-  else gn_apply_kernel<float><<<grid_for(n), GN_NT, 0, s>>>(p, (float*)y);
+  dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), GN_ROWS), p.B);
+  if (dtype == PUB_BF16) gn_apply_kernel<bf16><<<agrid, GN_NT, 0, s>>>(p, (bf16*)y);
+  else gn_apply_kernel<float><<<agrid, GN_NT, 0, s>>>(p, (float*)y);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -355,7 +364,7 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   PUB_TRY(check(p));
   const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
   const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
-  float* bcoef = p.partial + (size_t)p.B * nc * C * 2;
+  float* bcoef = p.partial + align_up((size_t)p.B * nc * C * 2, 4);  // 16-byte aligned rows of 4 floats
   dim3 grid(nc, p.B);
   if (dtype == PUB_BF16) gn_partial_kernel<bf16, 1><<<grid, GN_NT, smem, s>>>(p, (const bf16*)dy, p.partial);
   else gn_partial_kernel<float, 1><<<grid, GN_NT, smem, s>>>(p, (const float*)dy, p.partial);
@@ -364,12 +373,11 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   PUB_LAUNCH_CHECK();
   gn_bwd_param_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(p, p.partial, nc, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
-  const int64_t n = (int64_t)p.B * p.H * p.W * V;
   if (dx) {
     if (dtype == PUB_BF16)
-      gn_bwd_apply_kernel<bf16><<<grid_for(n), GN_NT, 0, s>>>(p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
+      gn_bwd_apply_kernel<bf16><<<grid, GN_NT, 0, s>>>(p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
     else
-      gn_bwd_apply_kernel<float><<<grid_for(n), GN_NT, 0, s>>>(p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
+      gn_bwd_apply_kernel<float><<<grid, GN_NT, 0, s>>>(p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
     PUB_LAUNCH_CHECK();
   }
   return 0;
