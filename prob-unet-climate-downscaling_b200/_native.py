@@ -257,6 +257,31 @@ def manual_seed(seed):
     _Rng.seed, _Rng.offset = int(seed) & 0x7FFFFFFFFFFFFFFF, 0
 
 
+class _WorkspacePool:
+    """Engine workspaces are multi-GB; allocating a fresh one per forward makes the caching allocator split and
+    re-malloc huge blocks (measured: sporadic ~1 s stalls).  Buffers are checked out for forward..backward and
+    returned afterwards, so a steady-state training step allocates nothing."""
+
+    def __init__(self):
+        self.free = {}
+
+    def take(self, nbytes, device):
+        lst = self.free.get((nbytes, device))
+        if lst:
+            return lst.pop()
+        return torch.empty(nbytes, device=device, dtype=torch.uint8)
+
+    def give(self, ws):
+        if ws is not None:
+            self.free.setdefault((ws.numel(), ws.device), []).append(ws)
+
+    def clear(self):
+        self.free.clear()
+
+
+workspaces = _WorkspacePool()
+
+
 # gradient-ready callback (set by parallel.GradSynchronizer): called with each engine's flat
 # gradient buffer right after its backward kernels have been enqueued
 grad_ready_callback = None
@@ -290,7 +315,7 @@ class _UNetFn(torch.autograd.Function):
         nbytes = L.pub_unet_workspace_bytes(eng.handle, B, H, W)
         if nbytes == 0:
             raise NativeError("pub_unet_workspace_bytes: " + L.pub_last_error().decode())
-        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        ws = workspaces.take(nbytes, x.device)
         real = params[:len(params) - nzero]
         if nhwc_out:
             out = torch.empty(B, H, W, eng.out_ch, device=x.device, dtype=_TORCH_DT[eng.dtype])
@@ -299,10 +324,15 @@ class _UNetFn(torch.autograd.Function):
         xc = x.contiguous()
         check(L.pub_unet_forward(eng.handle, B, H, W, ptr(xc), _ptr_table(real), ptr(out), int(not nhwc_out), ptr(ws),
                                  C.c_size_t(nbytes), C.c_uint64(seed), int(training), _backend, stream()), "pub_unet_forward")
-        ctx.eng, ctx.ws, ctx.nbytes, ctx.shape = eng, ws, nbytes, (B, H, W)
+        ctx.eng, ctx.nbytes, ctx.shape = eng, nbytes, (B, H, W)
         ctx.training, ctx.nhwc_out, ctx.seed, ctx.nzero = training, nhwc_out, seed, nzero
         ctx.x_req = ctx.needs_input_grad[1]
-        ctx.save_for_backward(*params)
+        if any(ctx.needs_input_grad):
+            ctx.ws = ws                                  # held until backward
+            ctx.save_for_backward(*params)
+        else:
+            ctx.ws = None
+            workspaces.give(ws)                          # inference: nothing to keep
         return out
 
     @staticmethod
@@ -320,6 +350,7 @@ class _UNetFn(torch.autograd.Function):
         check(lib().pub_unet_backward(eng.handle, B, H, W, ptr(dout), int(not ctx.nhwc_out), _ptr_table(real),
                                       _ptr_table(gviews[:len(real)]), ptr(dx), ptr(ctx.ws), C.c_size_t(ctx.nbytes),
                                       C.c_uint64(ctx.seed), int(ctx.training), _backend, stream()), "pub_unet_backward")
+        workspaces.give(ctx.ws)
         ctx.ws = None
         _notify(flat)
         return (None, dx, None, None, None, None) + tuple(gviews)
@@ -413,7 +444,7 @@ class _EncoderFn(torch.autograd.Function):
         nbytes = L.pub_encoder_workspace_bytes(eng.handle, B, H, W)
         if nbytes == 0:
             raise NativeError("pub_encoder_workspace_bytes: " + L.pub_last_error().decode())
-        ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+        ws = workspaces.take(nbytes, x.device)
         mu = torch.empty(B, eng.latent, device=x.device, dtype=torch.float32)
         sigma = torch.empty_like(mu)
         xc = x.contiguous()
@@ -421,8 +452,13 @@ class _EncoderFn(torch.autograd.Function):
         check(L.pub_encoder_forward(eng.handle, B, H, W, ptr(xc), cx, ptr(tc), tc.shape[1] if tc is not None else 0,
                                     _ptr_table(params), ptr(mu), ptr(sigma), ptr(ws), C.c_size_t(nbytes), _backend,
                                     stream()), "pub_encoder_forward")
-        ctx.eng, ctx.ws, ctx.nbytes, ctx.shape = eng, ws, nbytes, (B, H, W)
-        ctx.save_for_backward(*params)
+        ctx.eng, ctx.nbytes, ctx.shape = eng, nbytes, (B, H, W)
+        if any(ctx.needs_input_grad):
+            ctx.ws = ws
+            ctx.save_for_backward(*params)
+        else:
+            ctx.ws = None
+            workspaces.give(ws)
         return mu, sigma
 
     @staticmethod
@@ -435,6 +471,7 @@ class _EncoderFn(torch.autograd.Function):
         check(lib().pub_encoder_backward(eng.handle, B, H, W, ptr(dmu), ptr(dsigma), _ptr_table(params),
                                          _ptr_table(gviews), ptr(ctx.ws), C.c_size_t(ctx.nbytes), _backend, stream()),
               "pub_encoder_backward")
+        workspaces.give(ctx.ws)
         ctx.ws = None
         _notify(flat)
         return (None, None, None) + tuple(gviews)

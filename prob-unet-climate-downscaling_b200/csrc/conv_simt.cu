@@ -94,6 +94,57 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
   }
 }
 
+// Forward conv of the Cin <= 8 first layers (3 / 6 climate variables): lane = output channel (its 9 x Cin
+// weights live in registers), each warp walks a contiguous pixel range; the padded 8-channel pixel is one
+// warp-uniform 16/32-byte load per tap.  Replaces the 16-wide K chunks of the generic kernel (Cin = 3 wastes 13/16).
+template <typename T>
+__global__ void __launch_bounds__(256) conv_smallc_kernel(ConvParams p, int pix_per_cta) {
+  const T* x0 = (const T*)p.x0;
+  const T* w = (const T*)p.w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = blockIdx.y * 32 + lane;
+  const int cin = p.c0, taps = p.ks * p.ks, half = p.ks / 2;
+  const bool cov = co < p.cout;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wr[t][c] = (cov && t < taps && c < cin) ? to_f<T>(w[((int64_t)t * p.cout + co) * cin + c]) : 0.f;
+  const float bias = (cov && p.bias) ? p.bias[co] : 0.f;
+  const int64_t M = (int64_t)p.B * p.H * p.W;
+  const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
+  const int64_t per_warp = (pend - pbeg + 7) / 8;
+  const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
+  int x = (int)(wbeg % p.W), y = (int)((wbeg / p.W) % p.H), b = (int)(wbeg / ((int64_t)p.W * p.H));
+  T* yo = (T*)p.y;
+  const T* res = (const T*)p.res;
+  const T* mask = (const T*)p.mask;
+#pragma unroll 2
+  for (int64_t m = wbeg; m < wend; ++m) {
+    float acc = bias;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t < taps) {
+        const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+          float xv[8];
+          Vec8<T>::load(x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0, xv);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc = fmaf(wr[t][c], xv[c], acc);   // wr == 0 for the padding channels
+        }
+      }
+    }
+    if (cov) {
+      if (res) acc += to_f<T>(res[m * p.ld_res + co]);
+      if (p.relu) acc = fmaxf(acc, 0.f);
+      if (mask && !(to_f<T>(mask[m * p.ld_mask + co]) > 0.f)) acc = 0.f;
+      if (p.round_tf32) acc = round_tf32_f(acc);
+      yo[m * p.ldy + co] = from_f<T>(acc);
+    }
+    if (++x == p.W) { x = 0; if (++y == p.H) { y = 0; ++b; } }
+  }
+}
+
 // dW[tap][co][ci] partial over a pixel range:  sum_p dy[p][co] * x[p + tap][ci]
 template <typename T>
 __global__ void __launch_bounds__(NT) wgrad_simt_kernel(WgradParams p, float* __restrict__ part, int nsplit,
@@ -160,20 +211,24 @@ __global__ void __launch_bounds__(NT) wgrad_simt_kernel(WgradParams p, float* __
   }
 }
 
-// sum the split partials in a fixed order -> OIHW f32 gradient (deterministic split-K).
-// LANES = 1: one thread per element; LANES = 32: one warp per element (many splits, few elements)
-template <int LANES>
-__global__ void wgrad_reduce_kernel_t(const float* __restrict__ part, float* __restrict__ dw, int nsplit, int taps,
-                                      int cout, int cin, int accumulate) {
+// sum the split partials in a fixed order -> OIHW f32 gradient (deterministic split-K).  One thread per
+// element (coalesced across elements); the loads of consecutive splits are independent, so the unrolled loop
+// keeps 8 of them in flight while the additions stay in split order.
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
+                                                           int nsplit, int taps, int cout, int cin, int accumulate) {
   const int64_t n = (int64_t)taps * cout * cin;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = gid / LANES;
-  const int lane = (int)(gid % LANES);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
-  for (int k = lane; k < nsplit; k += LANES) s += part[(int64_t)k * n + i];
-  if (LANES == 32) s = warp_sum(s);
-  if (lane != 0) return;
+  int k = 0;
+  for (; k + 8 <= nsplit; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(part + (int64_t)(k + j) * n + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; k < nsplit; ++k) s += __ldg(part + (int64_t)k * n + i);
   const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
   const int64_t o = ((int64_t)co * cin + ci) * taps + tap;  // OIHW with (ky,kx) == tap
   dw[o] = accumulate ? dw[o] + s : s;
@@ -197,8 +252,12 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) acc[t][c] = 0.f;
-  for (int64_t m = pbeg + warp; m < pend; m += 8) {
-    const int x = (int)(m % p.W), y = (int)((m / p.W) % p.H), b = (int)(m / ((int64_t)p.W * p.H));
+  // each warp owns a contiguous pixel range; (b, y, x) advance incrementally (no divisions in the loop)
+  const int64_t per_warp = (pend - pbeg + 7) / 8;
+  const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
+  int x = (int)(wbeg % p.W), y = (int)((wbeg / p.W) % p.H), b = (int)(wbeg / ((int64_t)p.W * p.H));
+#pragma unroll 2
+  for (int64_t m = wbeg; m < wend; ++m) {
     const float g = co < p.cout ? to_f<T>(dy[m * p.ld_dy + co]) : 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -220,6 +279,7 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
         }
       }
     }
+    if (++x == p.W) { x = 0; if (++y == p.H) { y = 0; ++b; } }
   }
   // sum the 8 warps in a fixed order
   for (int w = 0; w < 8; ++w) {
@@ -343,6 +403,18 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ld, int C, floa
 
 int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
   const int64_t M = (int64_t)p.B * p.H * p.W;
+  // Cin <= 8 with an 8-channel padded, 32-byte aligned input buffer (how the engines stage the network input)
+  if (p.c1 == 0 && p.c0 <= 8 && p.ld0 % 8 == 0 && (((uintptr_t)p.x0) & 31) == 0 && (p.ks == 1 || p.ks == 3)) {
+    int want = 4 * num_sms() / cdiv(p.cout, 32);
+    if (want < 1) want = 1;
+    int ppc = (int)((M + want - 1) / want);
+    if (ppc < 256) ppc = 256;
+    dim3 grid(cdiv(M, ppc), cdiv(p.cout, 32));
+    if (dtype == PUB_BF16) conv_smallc_kernel<bf16><<<grid, 256, 0, s>>>(p, ppc);
+    else conv_smallc_kernel<float><<<grid, 256, 0, s>>>(p, ppc);
+    PUB_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(cdiv(M, BM), cdiv(p.cout, BN));
   if (dtype == PUB_BF16) conv_simt_kernel<bf16><<<grid, NT, 0, s>>>(p);
   else conv_simt_kernel<float><<<grid, NT, 0, s>>>(p);
@@ -408,10 +480,7 @@ int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, floa
 
 int wgrad_reduce(const float* part, float* dw, int nsplit, int taps, int cout, int cin, int accumulate, cudaStream_t s) {
   const int64_t n = (int64_t)taps * cout * cin;
-  if (nsplit >= 16 && n * 32 <= (int64_t)1 << 26)
-    wgrad_reduce_kernel_t<32><<<cdiv(n * 32, 256), 256, 0, s>>>(part, dw, nsplit, taps, cout, cin, accumulate);
-  else
-    wgrad_reduce_kernel_t<1><<<cdiv(n, 256), 256, 0, s>>>(part, dw, nsplit, taps, cout, cin, accumulate);
+  wgrad_reduce_kernel<<<cdiv(n, 128), 128, 0, s>>>(part, dw, nsplit, taps, cout, cin, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
 }

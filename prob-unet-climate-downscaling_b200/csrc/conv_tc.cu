@@ -169,9 +169,11 @@ struct TcConvArgs {
   int B, H, W;
   int TW, TH, TB;              // 128-pixel patch
   int tiles_x, tiles_y;        // patches per image row / column
+  int m_tiles;                 // total number of 128-pixel patches
   int BN;                      // output channels per CTA (multiple of 32, <= 256)
   int cout;                    // total output channels
   int stages;
+  int resident;                // 1: the CTA's whole weight slab [taps*Cin/KC][BN] stays in smem for all its tiles
   const float* bias;
   const void* res; int ld_res;
   const void* mask; int ld_mask;
@@ -179,45 +181,54 @@ struct TcConvArgs {
   int relu;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ------------------------------------------------------------------ forward / dgrad kernel
 // ROWB: bytes per smem row (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); ES: operand element size
 // (2 = bf16 / kind::f16, 4 = tf32-rounded f32 / kind::tf32).  Channels per K block = ROWB / ES.
+//
+// PERSISTENT: grid.x CTAs stride over the 128-pixel patches of one N tile (blockIdx.y).  The accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of patch i overlaps the MMAs of patch i+1, and the
+// per-CTA set-up (TMEM alloc, barrier init, descriptor prefetch) is paid once.  When the weight slab of the
+// N tile fits (<= 80 KB) it is loaded once and stays resident; the ring then carries activation tiles only.
 template <int ROWB_, int ES>
 __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                            const __grid_constant__ CUtensorMap tmA1,
                                                            const __grid_constant__ CUtensorMap tmW, TcConvArgs a) {
-  extern __shared__ uint8_t smem_raw[];
   typedef typename std::conditional<ES == 2, bf16, float>::type T;
-  constexpr uint32_t ROWB = ROWB_;                     // bytes per smem row
-  constexpr int KC = ROWB_ / ES;                       // channels per K block
-  constexpr uint32_t LAYOUT = (ROWB_ == 128) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
-  constexpr uint32_t SBO = 8 * ROWB;                  // 8-row core-matrix group pitch
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t ROWB = ROWB_;
+  constexpr int KC = ROWB_ / ES;                          // channels per K block
+  constexpr uint32_t LAYOUT = (ROWB_ == 128) ? 2u : 4u;   // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t SBO = 8 * ROWB;                      // 8-row core-matrix group pitch
   constexpr uint32_t A_BYTES = 128 * ROWB;
   const uint32_t B_BYTES = (uint32_t)a.BN * ROWB;
-  const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
-  __shared__ uint32_t tmem_slot;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]),
-                 accbar = smem_u32(&bars[2 * MAX_STAGES]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblk0 = a.c0 / KC, cblk = (a.c0 + a.c1) / KC;
   const int num_kb = a.taps * cblk;
-  uint32_t ncols = 32;
-  while ((int)ncols < a.BN) ncols <<= 1;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wres = base;                                            // resident weights (if any)
+  const uint32_t ring = base + (a.resident ? (uint32_t)num_kb * B_BYTES : 0u);
+  const uint32_t STAGE_BYTES = A_BYTES + (a.resident ? 0u : B_BYTES);
 
-  // patch coordinates
-  int t = blockIdx.x;
-  const int tx = t % a.tiles_x; t /= a.tiles_x;
-  const int ty = t % a.tiles_y; t /= a.tiles_y;
-  const int b0 = t * a.TB, y0 = ty * a.TH, x0 = tx * a.TW;
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
+  const uint32_t accfull0 = smem_u32(&bars[2 * MAX_STAGES]), accempty0 = smem_u32(&bars[2 * MAX_STAGES + 2]);
+  const uint32_t wbar = smem_u32(&bars[2 * MAX_STAGES + 4]);
+
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * a.BN) ncols <<= 1;
   const int n0 = blockIdx.y * a.BN;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    mbar_init(accbar, 1);
+    mbar_init(accfull0, 1); mbar_init(accfull0 + 8, 1);
+    mbar_init(accempty0, 4); mbar_init(accempty0 + 8, 4);
+    mbar_init(wbar, 1);
     fence_barrier_init();
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmW);
@@ -233,90 +244,125 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
     if (lane == 0) {
       // ---------------- TMA producer
       const int half = a.ks / 2;
+      if (a.resident) {
+        mbar_expect_tx(wbar, (uint32_t)num_kb * B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_3d(wres + kb * B_BYTES, &tmW, wbar, (kb % cblk) * KC, n0, kb / cblk);
+      }
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / cblk, cb = kb % cblk;
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
-        const int dy = tap / a.ks - half, dx = tap % a.ks - half;
-        if (cb < cblk0) tma_load_4d(sa, &tmA0, full0 + 8 * stage, cb * KC, x0 + dx, y0 + dy, b0);
-        else tma_load_4d(sa, &tmA1, full0 + 8 * stage, (cb - cblk0) * KC, x0 + dx, y0 + dy, b0);
-        tma_load_3d(sb, &tmW, full0 + 8 * stage, cb * KC, n0, tap);
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % a.tiles_x; t /= a.tiles_x;
+        const int ty = t % a.tiles_y; t /= a.tiles_y;
+        const int b0 = t * a.TB, y0 = ty * a.TH, x0 = tx * a.TW;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cblk, cb = kb % cblk;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = ring + stage * STAGE_BYTES;
+          mbar_expect_tx(full0 + 8 * stage, STAGE_BYTES);
+          const int dy = tap / a.ks - half, dx = tap % a.ks - half;
+          if (cb < cblk0) tma_load_4d(sa, &tmA0, full0 + 8 * stage, cb * KC, x0 + dx, y0 + dy, b0);
+          else tma_load_4d(sa, &tmA1, full0 + 8 * stage, (cb - cblk0) * KC, x0 + dx, y0 + dy, b0);
+          if (!a.resident) tma_load_3d(sa + A_BYTES, &tmW, full0 + 8 * stage, cb * KC, n0, tap);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---------------- MMA issuer
+      // ---------------- MMA issuer: descriptors are base + byte offset >> 4 (one add per operand)
       const uint32_t idesc = make_idesc(128, a.BN, 0, 0, ES == 2 ? 1u : 2u);
+      const uint64_t adesc0 = make_desc(ring, 16, SBO, LAYOUT);
+      const uint64_t bdesc0 = make_desc(a.resident ? wres : ring + A_BYTES, 16, SBO, LAYOUT);
+      const uint32_t bstep = a.resident ? (B_BYTES >> 4) : 0u;
+      const uint32_t sstep = STAGE_BYTES >> 4;
+      if (a.resident) mbar_wait(wbar, 0);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full0 + 8 * stage, phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(accempty0 + 8 * buf, (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        const uint64_t ad = make_desc(sa, 16, SBO, LAYOUT), bd = make_desc(sb, 16, SBO, LAYOUT);
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * a.BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t ad = adesc0 + (uint64_t)(stage * sstep);
+          const uint64_t bd = bdesc0 + (uint64_t)(a.resident ? kb * bstep : stage * sstep);
 #pragma unroll
-        for (int k = 0; k < (int)ROWB / 32; ++k)  // one MMA consumes 32 B of K; +32 B inside the swizzled row
-          umma<ES>(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-        umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < (int)ROWB / 32; ++k)  // one MMA consumes 32 B of K; +32 B inside the swizzled row
+            umma<ES>(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accfull0 + 8 * buf);  // accumulator of this patch complete
       }
-      umma_commit(accbar);  // accumulator complete
     }
   } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int xl = row % a.TW, yl = (row / a.TW) % a.TH, bl = row / (a.TW * a.TH);
-    const int bb = b0 + bl, yy = y0 + yl, xx = x0 + xl;
-    const bool valid = bb < a.B && yy < a.H && xx < a.W;
-    const int64_t pix = ((int64_t)bb * a.H + yy) * a.W + xx;
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    for (int cb = 0; cb < a.BN; cb += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r);
-      if (valid) {
-        const int n = n0 + cb;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (a.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int tx = t % a.tiles_x; t /= a.tiles_x;
+      const int ty = t % a.tiles_y; t /= a.tiles_y;
+      const int bb = t * a.TB + bl, yy = ty * a.TH + yl, xx = tx * a.TW + xl;
+      const bool valid = bb < a.B && yy < a.H && xx < a.W;
+      const int64_t pix = ((int64_t)bb * a.H + yy) * a.W + xx;
+      const int buf = it & 1;
+      mbar_wait(accfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      for (int cb = 0; cb < a.BN; cb += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.BN + cb), r);
+        if (cb + 32 >= a.BN) {  // last chunk read: hand the TMEM buffer back to the MMA warp before storing
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
         }
-        if (a.res) {
-          const T* rp = (const T*)a.res + pix * a.ld_res + n;
+        if (valid) {
+          const int n = n0 + cb;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
+          }
+          if (a.res) {
+            const T* rp = (const T*)a.res + pix * a.ld_res + n;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              Vec8<T>::load(rp + g * 8, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (a.mask) {
+            const T* mp = (const T*)a.mask + pix * a.ld_mask + n;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              Vec8<T>::load(mp + g * 8, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
+            }
+          }
+          T* yp = (T*)a.y + pix * a.ldy + n;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
-            Vec8<T>::load(rp + g * 8, f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+            for (int j = 0; j < 8; ++j) f[j] = ES == 4 ? round_tf32(v[g * 8 + j]) : v[g * 8 + j];
+            Vec8<T>::store(yp + g * 8, f);
           }
-        }
-        if (a.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (a.mask) {
-          const T* mp = (const T*)a.mask + pix * a.ld_mask + n;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
-            Vec8<T>::load(mp + g * 8, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
-          }
-        }
-        T* yp = (T*)a.y + pix * a.ldy + n;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = ES == 4 ? round_tf32(v[g * 8 + j]) : v[g * 8 + j];
-          Vec8<T>::store(yp + g * 8, f);
         }
       }
     }
@@ -412,23 +458,28 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // A = dy  [K=64 px][M=128 co]  MN-major: 4 groups of 32 channels, LBO = group pitch,
-      //                               SBO = 8 pixel rows
-      // B = x   [K=64 px][N=32 ci]   MN-major
-      const uint32_t idesc = make_idesc(128, 32, 1, 1, ES == 2 ? 1u : 2u);
+      // A = dy  [K=64 px][M=128 co]  MN-major: 4 groups of 32 channels, LBO = group pitch
+      // B = x   [K=64 px][N = taps x 32 ci]  MN-major: the tap tiles lie WG_GROUP_BYTES apart in smem, which is
+      //         exactly the LBO stride between 32-element N groups -> all taps of a K step are ONE wide-N MMA
+      //         (two for 3x3: N = 160 + 128), landing side by side in TMEM.
+      const int n1 = a.taps > 5 ? 5 : a.taps, n2 = a.taps - n1;  // taps per MMA
+      const uint32_t idesc1 = make_idesc(128, n1 * 32, 1, 1, ES == 2 ? 1u : 2u);
+      const uint32_t idesc2 = n2 ? make_idesc(128, n2 * 32, 1, 1, ES == 2 ? 1u : 2u) : 0u;
+      const uint64_t adesc0 = make_desc(base, WG_GROUP_BYTES, SBO_WG, LAYOUT);
+      const uint64_t bdesc0 = make_desc(base + WG_A_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
+      const uint32_t sstep = STAGE_BYTES >> 4;
       int stage = 0; uint32_t phase = 0;
       bool first = true;
       for (int t = t_beg; t < t_end; ++t) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + WG_A_BYTES;
-        for (int tap = 0; tap < a.taps; ++tap) {
+        const uint64_t ad = adesc0 + (uint64_t)(stage * sstep), bd = bdesc0 + (uint64_t)(stage * sstep);
 #pragma unroll
-          for (int k = 0; k < WG_P / KROWS; ++k) {
-            const uint64_t ad = make_desc(sa + k * KSTEP_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
-            const uint64_t bd = make_desc(sb + tap * WG_GROUP_BYTES + k * KSTEP_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
-            umma<ES>(tmem_base + (uint32_t)(tap * 32), ad, bd, idesc, (!first || k != 0) ? 1u : 0u);
-          }
+        for (int k = 0; k < WG_P / KROWS; ++k) {
+          const uint32_t acc = (!first || k != 0) ? 1u : 0u;
+          const uint64_t ko = (uint64_t)(k * (KSTEP_BYTES >> 4));
+          umma<ES>(tmem_base, ad + ko, bd + ko, idesc1, acc);
+          if (n2) umma<ES>(tmem_base + (uint32_t)(n1 * 32), ad + ko, bd + ko + (uint64_t)((n1 * WG_GROUP_BYTES) >> 4), idesc2, acc);
         }
         first = false;
         umma_commit(empty0 + 8 * stage);
@@ -574,12 +625,26 @@ int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
   a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res;
   a.mask = p.mask; a.ld_mask = p.ld_mask;
   a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
-  const size_t stage_bytes = (size_t)(128 + a.BN) * rowb;
-  int stages = (int)(98304 / stage_bytes);
+  a.m_tiles = cdiv(p.B, a.TB) * a.tiles_x * a.tiles_y;
+  const int n_tiles = p.cout / a.BN;
+  const int num_kb = a.taps * (cin / KC);
+  const size_t a_bytes = (size_t)128 * rowb, b_bytes = (size_t)a.BN * rowb;
+  const size_t wres_bytes = (size_t)num_kb * b_bytes;
+  a.resident = wres_bytes <= 80 * 1024;
+  // TMEM: 2 x BN columns (double-buffered accumulator).  <= 256 columns -> two CTAs per SM (more epilogue warps in
+  // flight for the HBM-bound small-C layers), so keep each CTA under ~110 KB of smem there.
+  const bool two_per_sm = 2 * a.BN <= 256;
+  const size_t budget = (two_per_sm ? 110 : 200) * 1024 - 1024;
+  if (a.resident && wres_bytes + 2 * a_bytes > budget) a.resident = 0;
+  const size_t stage_bytes = a_bytes + (a.resident ? 0 : b_bytes);
+  int stages = (int)((budget - (a.resident ? wres_bytes : 0)) / stage_bytes);
   if (stages < 2) stages = 2;
-  if (stages > 6) stages = 6;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   a.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024;
+  const size_t smem = 1024 + (a.resident ? wres_bytes : 0) + stages * stage_bytes;
+  int gx = (two_per_sm ? 2 : 1) * num_sms() / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > a.m_tiles) gx = a.m_tiles;
 
   CUtensorMap tmA0, tmA1, tmW;
   PUB_TRY(make_act_map(&tmA0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, KC, a.TW, a.TH, a.TB, sw));
@@ -587,12 +652,12 @@ int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
   else tmA1 = tmA0;
   PUB_TRY(make_weight_map(&tmW, p.w, es, cin, p.cout, a.taps, KC, a.BN, sw));
 
-  dim3 grid(cdiv(p.B, a.TB) * a.tiles_x * a.tiles_y, p.cout / a.BN);
+  dim3 grid(gx, n_tiles);
   static bool attr = false;
   if (!attr) {
-    PUB_TRY(set_smem_attr(conv_tc_kernel<128, 2>, 200 * 1024));
-    PUB_TRY(set_smem_attr(conv_tc_kernel<64, 2>, 200 * 1024));
-    PUB_TRY(set_smem_attr(conv_tc_kernel<128, 4>, 200 * 1024));
+    PUB_TRY(set_smem_attr(conv_tc_kernel<128, 2>, 201 * 1024));
+    PUB_TRY(set_smem_attr(conv_tc_kernel<64, 2>, 201 * 1024));
+    PUB_TRY(set_smem_attr(conv_tc_kernel<128, 4>, 201 * 1024));
     attr = true;
   }
   if (es == 4) conv_tc_kernel<128, 4><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);

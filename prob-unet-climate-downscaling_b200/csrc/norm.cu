@@ -15,7 +15,8 @@ namespace pub {
 namespace {
 
 constexpr int GN_NT = 256;
-constexpr int GN_ROWS = 256;  // pixels per chunk (one CTA)
+// pixels per chunk (one CTA): small feature maps get small chunks so that the low-resolution layers still fill the GPU
+__host__ __device__ inline int gn_rows(int HW) { return HW >= 16384 ? 256 : (HW >= 1024 ? 128 : 64); }
 
 // Every heavy kernel uses the same decomposition: grid = (pixel chunks, batch); inside a CTA thread t owns the
 // 8-channel vector v = t % V for the rows pr, pr + ppi, ... of the chunk (ppi = 256 / V).  The per-channel
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
   const int ppi = GN_NT / V;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int HW = p.H * p.W;
-  const int r0 = chunk * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+  const int rows = gn_rows(HW);
+  const int r0 = chunk * rows, r1 = min(HW, r0 + rows);
   const int t = threadIdx.x;
   const int v = t % V, pr = t / V;
   float s1[8], s2[8];
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
   if (p.resample != 1) {
     const uint32_t thresh = drop_thresh(p.p_drop);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int r0 = blockIdx.x * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+    const int rows = gn_rows(HW);
+    const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
     for (int r = r0 + pr; r < r1; r += ppi) {
       const int64_t pix = (int64_t)b * HW + r;
       float x[8], o[8];
@@ -204,7 +207,8 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
     }
   } else {  // 2x2 mean of the activated values
     const int Ho = p.H / 2, Wo = p.W / 2, HWo = Ho * Wo;
-    const int r0 = blockIdx.x * GN_ROWS, r1 = min(HWo, r0 + GN_ROWS);
+    const int rows = gn_rows(HW);
+    const int r0 = blockIdx.x * rows, r1 = min(HWo, r0 + rows);
     for (int r = r0 + pr; r < r1; r += ppi) {
       const int yo = r / Wo, xo = r % Wo;
       float o[8];
@@ -263,13 +267,15 @@ __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ part, 
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  const int n = p.B * nchunk;
-  for (int i = lane; i < n; i += 32) {
-    const int b = i / nchunk;
+  for (int b = 0; b < p.B; ++b) {
     const float2 st = *reinterpret_cast<const float2*>(p.stats + ((int64_t)b * p.groups + c / cpg) * 2);
-    const float2 v = *reinterpret_cast<const float2*>(part + ((int64_t)i * C + c) * 2);
-    s1 += (double)v.x;
-    s2 += (double)st.y * ((double)v.y - (double)st.x * (double)v.x);
+    float q1 = 0.f, q2 = 0.f;
+    for (int k = lane; k < nchunk; k += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
+      q1 += v.x; q2 += v.y;
+    }
+    s1 += (double)q1;
+    s2 += (double)st.y * ((double)q2 - (double)st.x * (double)q1);
   }
   s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
   if (lane != 0) return;
@@ -299,7 +305,8 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_apply_kernel(GnParams p, const T
   const uint32_t thresh = drop_thresh(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const int HW = p.H * p.W;
-  const int r0 = blockIdx.x * GN_ROWS, r1 = min(HW, r0 + GN_ROWS);
+  const int rows = gn_rows(HW);
+  const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
   for (int r = r0 + pr; r < r1; r += ppi) {
     const int64_t pix = (int64_t)b * HW + r;
     float x[8], g[8], o[8];
@@ -329,7 +336,7 @@ int check(const GnParams& p) {
   return 0;
 }
 
-inline int nchunks(const GnParams& p) { return cdiv((int64_t)p.H * p.W, GN_ROWS); }
+inline int nchunks(const GnParams& p) { return cdiv((int64_t)p.H * p.W, gn_rows(p.H * p.W)); }
 inline int grid_for(int64_t n) {
   int64_t g = (n + GN_NT - 1) / GN_NT;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -339,7 +346,7 @@ inline int grid_for(int64_t n) {
 }  // namespace
 
 size_t gn_partial_floats(int B, int C, int H, int W) {
-  return (size_t)B * cdiv((int64_t)H * W, GN_ROWS) * C * 2 + (size_t)B * C * 4 + 64;
+  return (size_t)B * cdiv((int64_t)H * W, gn_rows(H * W)) * C * 2 + (size_t)B * C * 4 + 64;
 }
 
 int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
@@ -352,7 +359,7 @@ int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
   PUB_LAUNCH_CHECK();
   gn_finalize_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc);
   PUB_LAUNCH_CHECK();
-  dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), GN_ROWS), p.B);
+  dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), gn_rows(p.H * p.W)), p.B);
   if (dtype == PUB_BF16) gn_apply_kernel<bf16><<<agrid, GN_NT, 0, s>>>(p, (bf16*)y);
   else gn_apply_kernel<float><<<agrid, GN_NT, 0, s>>>(p, (float*)y);
   PUB_LAUNCH_CHECK();

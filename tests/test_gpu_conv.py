@@ -134,3 +134,33 @@ def test_dgrad_via_transposed_pack():
         torch.cuda.synchronize()
         e = rel_err(dx.float().permute(0, 3, 1, 2), x.grad)
         assert e < tol, f"dgrad {dt} backend={backend} rel_err={e:.3e}"
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cin", [3, 6])
+def test_first_layer_small_cin_kernels(dt, cin):
+    """The engines stage the 3 / 6-variable network input in an 8-channel padded NHWC buffer; forward and
+    weight gradient then run on the dedicated small-Cin kernels (conv_smallc_kernel / wgrad_smallc_kernel)."""
+    N = _setup()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, W, cout = 3, 32, 32, 32
+    buf = torch.randn(B, H, W, 8, device="cuda", generator=g).to(dt)
+    buf[..., cin:] = float("nan")                      # padding channels must never be read into the result
+    x0 = buf[..., :cin]
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    ndt = N.BF16 if dt == torch.bfloat16 else N.F32
+    wp = N.pack_conv_weight(w, ndt)
+    wq = wp.float().permute(1, 2, 0).reshape(cout, cin, 3, 3)
+    y = N.conv2d_nhwc(x0, wp, b, ksize=3, relu=True, backend=N.BACKEND_SIMT)
+    ref = _ref_conv(x0, wq, b, relu=True)
+    tol = 1e-4 if dt == torch.float32 else 1e-2
+    assert rel_err(y.float(), ref) < tol
+    dy = torch.randn(B, H, W, cout, device="cuda", generator=g).to(dt)
+    dw, db = N.conv2d_wgrad_nhwc(x0, dy, 3, backend=N.BACKEND_SIMT)
+    wz = torch.zeros(cout, cin, 3, 3, device="cuda", requires_grad=True)
+    bz = torch.zeros(cout, device="cuda", requires_grad=True)
+    F.conv2d(x0.float().permute(0, 3, 1, 2), wz, bz, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert rel_err(dw, wz.grad) < (1e-4 if dt == torch.float32 else 2e-3)
+    assert rel_err(db, bz.grad) < (1e-4 if dt == torch.float32 else 2e-3)
