@@ -80,13 +80,19 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+
+    def read(self):
+        """Summary of the samples taken since mark() (nvidia-smi keeps running: attaching / detaching an NVML
+        client next to a timed region perturbs it)."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for li, line in enumerate(open(self.path)):
@@ -318,12 +324,14 @@ def run_b200(args):
     l0 = N.lib().pub_launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
+    c0 = time.perf_counter()
     for i in range(args.steps):
         loss = step_device(x, y)
         evs[i + 1].record()
+    cpu_enqueue = (time.perf_counter() - c0) / args.steps
     barrier()
     launches = (N.lib().pub_launch_count() - l0)
-    clocks = sampler.stop()
+    clocks = sampler.read()
     t_dev = evs[0].elapsed_time(evs[-1]) * 1e-3
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     # ---- end to end through the public API: pinned host inputs -> H2D -> step -> D2H of the loss
@@ -334,6 +342,7 @@ def run_b200(args):
         lv = step_device(xd, yd).item()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - w0
+    sampler.stop()
     if world > 1:
         tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -350,7 +359,7 @@ def run_b200(args):
         "config": workload_config(args),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * t_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": 1e3 * cpu_enqueue,
         "clocks": clocks,
         "model_tflops_per_gpu": value / world * gflop / 1e3,
         "final_loss": float(loss),

@@ -105,11 +105,12 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(ConvParams p, int pix_
   const int co = blockIdx.y * 32 + lane;
   const int cin = p.c0, taps = p.ks * p.ks, half = p.ks / 2;
   const bool cov = co < p.cout;
-  float wr[9][8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) wr[t][c] = (cov && t < taps && c < cin) ? to_f<T>(w[((int64_t)t * p.cout + co) * cin + c]) : 0.f;
+  __shared__ float ws[9 * 8][32];  // [tap*8 + ci][lane]: conflict-free, 0 for unused taps / channels
+  for (int i = warp; i < 72; i += 8) {
+    const int t = i >> 3, c = i & 7;
+    ws[i][lane] = (cov && t < taps && c < cin) ? to_f<T>(w[((int64_t)t * p.cout + co) * cin + c]) : 0.f;
+  }
+  __syncthreads();
   const float bias = (cov && p.bias) ? p.bias[co] : 0.f;
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
@@ -119,19 +120,26 @@ __global__ void __launch_bounds__(256) conv_smallc_kernel(ConvParams p, int pix_
   T* yo = (T*)p.y;
   const T* res = (const T*)p.res;
   const T* mask = (const T*)p.mask;
-#pragma unroll 2
   for (int64_t m = wbeg; m < wend; ++m) {
+    // branch-free: every tap loads from a clamped (always in-bounds) address so that the 9 loads issue back to back;
+    // out-of-image taps are discarded by the select below
+    float xv[9][8];
+    bool ok[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int tt = t < taps ? t : 0;
+      const int yy = y + tt / p.ks - half, xx = x + tt % p.ks - half;
+      ok[t] = t < taps && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      const int yc = min(max(yy, 0), p.H - 1), xc = min(max(xx, 0), p.W - 1);
+      Vec8<T>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv[t]);
+    }
     float acc = bias;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      if (t < taps) {
-        const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-          float xv[8];
-          Vec8<T>::load(x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0, xv);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc = fmaf(wr[t][c], xv[c], acc);   // wr == 0 for the padding channels
-        }
+      for (int c = 0; c < 8; ++c) {
+        const float xs = (ok[t] && c < cin) ? xv[t][c] : 0.f;   // padding channels are uninitialised memory
+        acc = fmaf(ws[t * 8 + c][lane], xs, acc);
       }
     }
     if (cov) {
@@ -256,22 +264,34 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
   const int64_t per_warp = (pend - pbeg + 7) / 8;
   const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
   int x = (int)(wbeg % p.W), y = (int)((wbeg / p.W) % p.H), b = (int)(wbeg / ((int64_t)p.W * p.H));
-#pragma unroll 2
   for (int64_t m = wbeg; m < wend; ++m) {
     const float g = co < p.cout ? to_f<T>(dy[m * p.ld_dy + co]) : 0.f;
+    if (vec) {
+      // branch-free clamped loads (issued back to back), out-of-image taps discarded by the select
+      float xv[9][8];
+      bool ok[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (t < taps) {
-        const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-          const T* xp = x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0;
-          if (vec) {  // the input buffer is padded to 8 channels: one 16/32-byte warp-uniform load per tap
-            float xv[8];
-            Vec8<T>::load(xp, xv);
+      for (int t = 0; t < 9; ++t) {
+        const int tt = t < taps ? t : 0;
+        const int yy = y + tt / p.ks - half, xx = x + tt % p.ks - half;
+        ok[t] = t < taps && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        const int yc = min(max(yy, 0), p.H - 1), xc = min(max(xx, 0), p.W - 1);
+        Vec8<T>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv[t]);
+      }
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-              if (c < cin) acc[t][c] = fmaf(g, xv[c], acc[t][c]);
-          } else {
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          const float xs = (ok[t] && c < cin) ? xv[t][c] : 0.f;
+          acc[t][c] = fmaf(g, xs, acc[t][c]);
+        }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t < taps) {
+          const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+            const T* xp = x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
               if (c < cin) acc[t][c] = fmaf(g, to_f<T>(xp[c]), acc[t][c]);

@@ -30,6 +30,34 @@ __device__ __forceinline__ void load_vec(const GnParams& p, int64_t pix, int v, 
   else Vec8<T>::load((const T*)p.x1 + pix * p.ld1 + (c - p.c0), f);
 }
 
+// Raw (still packed) 8-channel vectors: 4 registers for bf16, 8 for f32.  The hot kernels issue the loads of
+// GN_UNROLL rows back to back as raw vectors (memory-level parallelism) and unpack them only when consumed.
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <typename T>
+__device__ __forceinline__ const T* vec_ptr(const GnParams& p, int64_t pix, int v) {
+  const int c = v * 8;
+  return c < p.c0 ? (const T*)p.x0 + pix * p.ld0 + c : (const T*)p.x1 + pix * p.ld1 + (c - p.c0);
+}
+constexpr int GN_UNROLL = 4;
+
 // coef[b][c][2] -> a[8], bb[8] for channels v*8 .. v*8+7
 __device__ __forceinline__ void load_affine(const float* coef, int b, int C, int v, float (&a)[8], float (&bb)[8]) {
   const float4* q = reinterpret_cast<const float4*>(coef + ((int64_t)b * C + v * 8) * 2);
@@ -87,8 +115,7 @@ __device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__
 
 // ---------------------------------------------------------------- per-channel two-value partial sums
 // MODE 0: (x, x^2)          -- forward statistics
-// MODE 1: (du, du * x)      -- backward; du = g_y * silu'(a x + b).  (sum du*xhat is formed in the finalize
-//                              kernels as rstd * (sum du*x - mean * sum du).)
+// MODE 1: (du, du * (x - mean_g))  -- backward; du = g_y * silu'(a x + b); sum du*xhat = rstd * second sum
 template <typename T, int MODE>
 __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* __restrict__ dy, float* __restrict__ part) {
   extern __shared__ float sm[];  // [ppi][V][16]
@@ -104,25 +131,67 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (pr < ppi) {
-    float a[8], bb[8];
-    if (MODE == 1) load_affine(p.coef, b, C, v, a, bb);
+    float a[8], bb[8], mean[8];
+    if (MODE == 1) {
+      load_affine(p.coef, b, C, v, a, bb);
+      const int cpg = C / p.groups;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mean[j] = p.stats[((int64_t)b * p.groups + (v * 8 + j) / cpg) * 2];
+    }
     const uint32_t thresh = drop_thresh(p.p_drop);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    for (int r = r0 + pr; r < r1; r += ppi) {
-      const int64_t pix = (int64_t)b * HW + r;
-      float x[8];
-      load_vec<T>(p, pix, v, x);
-      if (MODE == 0) {
+    if (MODE == 0 || p.resample == 0) {
+      // fast path: loads of GN_UNROLL rows are issued first (raw), then consumed
+      for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
+        Raw8<T> xr[GN_UNROLL], gr[GN_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
-      } else {
-        float g[8];
+        for (int u = 0; u < GN_UNROLL; ++u) {
+          const int r = rb + u * ppi;
+          if (r < r1) {
+            const int64_t pix = (int64_t)b * HW + r;
+            xr[u].load(vec_ptr<T>(p, pix, v));
+            if (MODE == 1) gr[u].load(dy + pix * C + v * 8);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+          const int r = rb + u * ppi;
+          if (r < r1) {
+            float x[8];
+            xr[u].unpack(x);
+            if (MODE == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
+            } else {
+              float g[8];
+              gr[u].unpack(g);
+              if (p.p_drop > 0.f) {
+                bool keep[8];
+                dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + v * 8, thresh, keep);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
+                s1[j] += du;
+                s2[j] = fmaf(du, x[j] - mean[j], s2[j]);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int r = r0 + pr; r < r1; r += ppi) {
+        const int64_t pix = (int64_t)b * HW + r;
+        float x[8], g[8];
+        load_vec<T>(p, pix, v, x);
         load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
           s1[j] += du;
-          s2[j] = fmaf(du, x[j], s2[j]);
+          s2[j] = fmaf(du, x[j] - mean[j], s2[j]);
         }
       }
     }
@@ -182,26 +251,37 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     const int rows = gn_rows(HW);
     const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
-    for (int r = r0 + pr; r < r1; r += ppi) {
-      const int64_t pix = (int64_t)b * HW + r;
-      float x[8], o[8];
-      load_vec<T>(p, pix, v, x);
+    for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
+      Raw8<T> xr[GN_UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = silu_f(fmaf(a[j], x[j], bb[j]));
-      if (p.p_drop > 0.f) {
-        bool keep[8];
-        dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int r = rb + u * ppi;
+        if (r < r1) xr[u].load(vec_ptr<T>(p, (int64_t)b * HW + r, v));
       }
-      if (p.resample == 0) {
-        Vec8<T>::store(y + pix * C + v * 8, o);
-      } else {  // nearest 2x upsample: write the 2x2 children
-        const int yy = r / p.W, xx = r % p.W;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
-          Vec8<T>::store(y + q * C + v * 8, o);
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int r = rb + u * ppi;
+        if (r >= r1) continue;
+        const int64_t pix = (int64_t)b * HW + r;
+        float x[8], o[8];
+        xr[u].unpack(x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = silu_f(fmaf(a[j], x[j], bb[j]));
+        if (p.p_drop > 0.f) {
+          bool keep[8];
+          dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
+        }
+        if (p.resample == 0) {
+          Vec8<T>::store(y + pix * C + v * 8, o);
+        } else {  // nearest 2x upsample: write the 2x2 children
+          const int yy = r / p.W, xx = r % p.W;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
+            Vec8<T>::store(y + q * C + v * 8, o);
+          }
         }
       }
     }
@@ -230,25 +310,34 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
 }
 
 // backward finalize 1: per (b, g) -> bcoef[b][c] = (c1, c2, c3):  dx = c1*du + c2*x + c3
-// partials hold P1 = sum du, P2 = sum du*x;  sum du*xhat = rstd * (P2 - mean * P1)
-__global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef) {
+// partials hold P1 = sum du, P2 = sum du*(x - mean);  sum du*xhat = rstd * P2
+__global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef,
+                                    float* __restrict__ bsum) {
   const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= p.B * p.groups) return;
   const int b = wid / p.groups, g = wid % p.groups;
+  // per channel: sum the chunk partials (lanes stride over chunks, fixed tree), keep (S1, rstd*S2) per (b, c)
+  // for the parameter-gradient kernel, and fold them into the group sums
+  const float rstd_g = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
   double q1 = 0.0, q2 = 0.0;
-  for (int i = lane; i < nchunk * cpg; i += 32) {
-    const int k = i / cpg, c = g * cpg + i % cpg;
+  for (int ci = 0; ci < cpg; ++ci) {
+    const int c = g * cpg + ci;
+    float a1 = 0.f, a2 = 0.f;
+    for (int k = lane; k < nchunk; k += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
+      a1 += v.x; a2 += v.y;
+    }
+    a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { bsum[((int64_t)b * C + c) * 2] = a1; bsum[((int64_t)b * C + c) * 2 + 1] = rstd_g * a2; }
     const float sc = p.film ? 1.f + p.film[c] : 1.f;
     const double gp = (double)p.gamma[c] * sc;
-    const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
-    q1 += gp * (double)v.x; q2 += gp * (double)v.y;
+    q1 += gp * (double)a1; q2 += gp * (double)a2;
   }
-  q1 = warp_sum_d(q1); q2 = warp_sum_d(q2);
   const float mean = p.stats[((int64_t)b * p.groups + g) * 2], rstd = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
   const double n = (double)cpg * p.H * p.W;
   const double m1 = q1 / n;
-  const double m2 = (double)rstd * (q2 - (double)mean * q1) / n;
+  const double m2 = (double)rstd * q2 / n;
   const float c2 = (float)(-(double)rstd * rstd * m2);
   const float c3 = (float)(-(double)rstd * m1 + (double)rstd * rstd * m2 * mean);
   for (int i = lane; i < cpg; i += 32) {
@@ -259,26 +348,18 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
   }
 }
 
-// backward finalize 2: per channel parameter gradients; one warp per channel, lanes stride over the
-// (batch, chunk) partials, fixed shuffle tree -> deterministic
-__global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ dgamma,
+// backward finalize 2: per channel parameter gradients = sum over the batch of the per-(b, c) sums written by
+// gn_bwd_group_kernel (thread per channel, coalesced, fixed order)
+__global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ bsum, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ dfilm) {
-  const int C = p.c0 + p.c1, cpg = C / p.groups;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int C = p.c0 + p.c1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
   for (int b = 0; b < p.B; ++b) {
-    const float2 st = *reinterpret_cast<const float2*>(p.stats + ((int64_t)b * p.groups + c / cpg) * 2);
-    float q1 = 0.f, q2 = 0.f;
-    for (int k = lane; k < nchunk; k += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
-      q1 += v.x; q2 += v.y;
-    }
-    s1 += (double)q1;
-    s2 += (double)st.y * ((double)q2 - (double)st.x * (double)q1);
+    const float2 v = *reinterpret_cast<const float2*>(bsum + ((int64_t)b * C + c) * 2);
+    s1 += (double)v.x; s2 += (double)v.y;
   }
-  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
-  if (lane != 0) return;
   const float sc = p.film ? 1.f + p.film[c] : 1.f;
   dgamma[c] = (float)(s2 * sc);
   dbeta[c] = (float)(s1 * sc);
@@ -307,6 +388,49 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_apply_kernel(GnParams p, const T
   const int HW = p.H * p.W;
   const int rows = gn_rows(HW);
   const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
+  if (p.resample == 0) {
+    for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
+      Raw8<T> xr[GN_UNROLL], gr[GN_UNROLL], ar[GN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int r = rb + u * ppi;
+        if (r < r1) {
+          const int64_t pix = (int64_t)b * HW + r;
+          xr[u].load(vec_ptr<T>(p, pix, v));
+          gr[u].load(dy + pix * C + v * 8);
+          if (addend) ar[u].load(addend + pix * ld_add + v * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int r = rb + u * ppi;
+        if (r >= r1) continue;
+        const int64_t pix = (int64_t)b * HW + r;
+        float x[8], g[8], o[8];
+        xr[u].unpack(x);
+        gr[u].unpack(g);
+        if (p.p_drop > 0.f) {
+          bool keep[8];
+          dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
+          o[j] = fmaf(c1[j], du, fmaf(c2[j], x[j], c3[j]));
+        }
+        if (addend) {
+          float ad[8];
+          ar[u].unpack(ad);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += ad[j];
+        }
+        Vec8<T>::store(dx + pix * C + v * 8, o);
+      }
+    }
+    return;
+  }
   for (int r = r0 + pr; r < r1; r += ppi) {
     const int64_t pix = (int64_t)b * HW + r;
     float x[8], g[8], o[8];
@@ -346,7 +470,7 @@ inline int grid_for(int64_t n) {
 }  // namespace
 
 size_t gn_partial_floats(int B, int C, int H, int W) {
-  return (size_t)B * cdiv((int64_t)H * W, gn_rows(H * W)) * C * 2 + (size_t)B * C * 4 + 64;
+  return (size_t)B * cdiv((int64_t)H * W, gn_rows(H * W)) * C * 2 + (size_t)B * C * 6 + 64;
 }
 
 int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
@@ -376,9 +500,10 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   if (dtype == PUB_BF16) gn_partial_kernel<bf16, 1><<<grid, GN_NT, smem, s>>>(p, (const bf16*)dy, p.partial);
   else gn_partial_kernel<float, 1><<<grid, GN_NT, smem, s>>>(p, (const float*)dy, p.partial);
   PUB_LAUNCH_CHECK();
-  gn_bwd_group_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc, bcoef);
+  float* bsum = bcoef + (size_t)p.B * C * 4;
+  gn_bwd_group_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc, bcoef, bsum);
   PUB_LAUNCH_CHECK();
-  gn_bwd_param_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(p, p.partial, nc, dgamma, dbeta, dfilm);
+  gn_bwd_param_kernel<<<cdiv(C, 64), 64, 0, s>>>(p, bsum, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   if (dx) {
     if (dtype == PUB_BF16)
