@@ -164,7 +164,8 @@ typedef struct {
   float* out;                    /* [B,M,C,H,W] f32                                            */
   int32_t B, H, W, F, L, C, M;
 } pub_fcomb_args;
-int pub_fcomb_forward(const pub_fcomb_args* a, pub_stream_t s);
+size_t pub_fcomb_forward_workspace(const pub_fcomb_args* a);
+int pub_fcomb_forward(const pub_fcomb_args* a, void* workspace, size_t workspace_bytes, pub_stream_t s);
 size_t pub_fcomb_backward_workspace(const pub_fcomb_args* a);
 /* dfeat: same layout/dtype as feat would have if contiguous (NHWC dt, or NCHW f32); may be NULL */
 int pub_fcomb_backward(const pub_fcomb_args* a, const float* dout, void* dfeat, float* dz,
@@ -194,9 +195,10 @@ int pub_scale_by_device_scalar(float* y, const float* scale, int64_t n, pub_stre
  * preds [T,M,3,HW] f32; transform=1: preds are standardised residuals, converted with
  * lrinterp [T,3,HW] and std_hr[3] to real units before scoring against hr [T,3,HW].
  * ---------------------------------------------------------------------------------- */
+size_t pub_ensemble_metrics_workspace(int T, int C, int HW);
 int pub_ensemble_metrics(const float* preds, const float* hr, const float* lrinterp, const float* std_hr,
                          int transform, int T, int M, int C, int HW, float* crps_tc, float* mae_tc,
-                         pub_stream_t s);
+                         void* workspace, size_t workspace_bytes, pub_stream_t s);
 
 /* ------------------------------------------------------------------------------------
  * Optimizer: torch.optim.AdamW step (src/train_prob_unet_model.py:139-141) over a device

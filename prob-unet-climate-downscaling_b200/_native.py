@@ -75,9 +75,9 @@ EXPORTS = [
     "pub_unet_num_params", "pub_unet_workspace_bytes", "pub_unet_forward", "pub_unet_backward",
     "pub_unet_dropout_mask", "pub_encoder_create", "pub_encoder_destroy", "pub_encoder_num_params",
     "pub_encoder_workspace_bytes", "pub_encoder_forward", "pub_encoder_backward", "pub_rsample_forward",
-    "pub_rsample_backward", "pub_kl_normal_forward", "pub_kl_normal_backward", "pub_fcomb_forward",
+    "pub_rsample_backward", "pub_kl_normal_forward", "pub_kl_normal_backward", "pub_fcomb_forward_workspace", "pub_fcomb_forward",
     "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss",
-    "pub_scale_by_device_scalar", "pub_ensemble_metrics", "pub_adamw_step",
+    "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
 ]
 
 
@@ -92,7 +92,8 @@ def lib():
         l.pub_last_error.restype = C.c_char_p
         l.pub_launch_count.restype = C.c_ulonglong
         for name in ("pub_conv2d_wgrad_workspace", "pub_unet_workspace_bytes", "pub_encoder_workspace_bytes",
-                     "pub_fcomb_backward_workspace", "pub_loss_workspace"):
+                     "pub_fcomb_backward_workspace", "pub_loss_workspace", "pub_fcomb_forward_workspace",
+                     "pub_ensemble_metrics_workspace"):
             if hasattr(l, name):
                 getattr(l, name).restype = C.c_size_t
         _lib = l
@@ -605,7 +606,9 @@ class _FcombFn(torch.autograd.Function):
         z = z.contiguous().float()
         out = torch.empty(B, M, mod.num_classes, H, W, device=z.device, dtype=torch.float32)
         a = _fcomb_args(mod, feat, z, nhwc, out)
-        check(lib().pub_fcomb_forward(C.byref(a), stream()), "pub_fcomb_forward")
+        nws = lib().pub_fcomb_forward_workspace(C.byref(a))
+        ws = torch.empty(nws, device=z.device, dtype=torch.uint8)
+        check(lib().pub_fcomb_forward(C.byref(a), ptr(ws), C.c_size_t(nws), stream()), "pub_fcomb_forward")
         ctx.mod, ctx.nhwc = mod, nhwc
         ctx.save_for_backward(feat, z, *params)
         return out
@@ -724,6 +727,9 @@ def ensemble_metrics(preds, hr, lrinterp=None, std_hr=None):
     tr = lrinterp is not None
     sh = std_hr.reshape(-1).contiguous().float() if tr else None
     li = lrinterp.contiguous().float() if tr else None
+    nws = lib().pub_ensemble_metrics_workspace(T, Cc, H * W)
+    ws = torch.empty(nws, device=preds.device, dtype=torch.uint8)
     check(lib().pub_ensemble_metrics(ptr(preds.contiguous().float()), ptr(hr.contiguous().float()), ptr(li), ptr(sh),
-                                     int(tr), T, M, Cc, H * W, ptr(crps), ptr(mae), stream()), "pub_ensemble_metrics")
+                                     int(tr), T, M, Cc, H * W, ptr(crps), ptr(mae), ptr(ws), C.c_size_t(nws), stream()),
+          "pub_ensemble_metrics")
     return crps, mae

