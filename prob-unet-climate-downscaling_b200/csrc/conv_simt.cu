@@ -94,62 +94,131 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
   }
 }
 
-// Forward conv of the Cin <= 8 first layers (3 / 6 climate variables): lane = output channel (its 9 x Cin
-// weights live in registers), each warp walks a contiguous pixel range; the padded 8-channel pixel is one
-// warp-uniform 16/32-byte load per tap.  Replaces the 16-wide K chunks of the generic kernel (Cin = 3 wastes 13/16).
-template <typename T>
-__global__ void __launch_bounds__(256) conv_smallc_kernel(ConvParams p, int pix_per_cta) {
+// First `CIN` channels of the 8-channel padded input pixel (16 B of bf16 / 32 B of f32): loads only what is used.
+template <typename T, int CIN> struct PixLoad;
+template <int CIN> struct PixLoad<float, CIN> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[CIN]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float t[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int i = 0; i < (CIN < 4 ? CIN : 4); ++i) v[i] = t[i];
+    if (CIN > 4) {
+      const float4 b = *reinterpret_cast<const float4*>(p + 4);
+      const float u[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 4; i < CIN; ++i) v[i] = u[i - 4];
+    }
+  }
+};
+template <int CIN> struct PixLoad<bf16, CIN> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[CIN]) {
+    if (CIN <= 4) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+      const float t[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) v[i] = t[i];
+    } else {
+      float t[8];
+      Vec8<bf16>::load(p, t);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) v[i] = t[i];
+    }
+  }
+};
+
+// Forward conv of the Cin <= 8 first layers (3 / 6 climate variables -> 32 channels).  Thread = output pixel with
+// its 32 output channels in registers; the [tap][ci][co] weights are smem broadcasts (one LDS.128 feeds 4 FMAs), the
+// 9 input pixels are 8/16/32-byte loads coalesced across the warp.  27 (Cin = 3) FMA instructions per pixel and
+// warp instead of 72 + 72 shared loads of the lane-per-channel version it replaces (1.1 ms -> HBM-bound output write).
+template <typename T, int CIN>
+__global__ void __launch_bounds__(128) conv_smallc_kernel(ConvParams p) {
+  __shared__ __align__(16) float ws[9 * CIN][32];  // [tap*CIN + ci][co]
+  __shared__ float bs[32];
   const T* x0 = (const T*)p.x0;
   const T* w = (const T*)p.w;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int co = blockIdx.y * 32 + lane;
   const int cin = p.c0, taps = p.ks * p.ks, half = p.ks / 2;
-  const bool cov = co < p.cout;
-  __shared__ float ws[9 * 8][32];  // [tap*8 + ci][lane]: conflict-free, 0 for unused taps / channels
-  for (int i = warp; i < 72; i += 8) {
-    const int t = i >> 3, c = i & 7;
-    ws[i][lane] = (cov && t < taps && c < cin) ? to_f<T>(w[((int64_t)t * p.cout + co) * cin + c]) : 0.f;
+  const int n0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < 9 * CIN * 32; i += 128) {
+    const int co = i & 31, tc = i >> 5, t = tc / CIN, c = tc % CIN;
+    ws[tc][co] = (n0 + co < p.cout && t < taps && c < cin) ? to_f<T>(w[((int64_t)t * p.cout + n0 + co) * cin + c]) : 0.f;
   }
+  if (threadIdx.x < 32) bs[threadIdx.x] = (p.bias && n0 + threadIdx.x < p.cout) ? p.bias[n0 + threadIdx.x] : 0.f;
   __syncthreads();
-  const float bias = (cov && p.bias) ? p.bias[co] : 0.f;
   const int64_t M = (int64_t)p.B * p.H * p.W;
-  const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
-  const int64_t per_warp = (pend - pbeg + 7) / 8;
-  const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
-  int x = (int)(wbeg % p.W), y = (int)((wbeg / p.W) % p.H), b = (int)(wbeg / ((int64_t)p.W * p.H));
-  T* yo = (T*)p.y;
-  const T* res = (const T*)p.res;
-  const T* mask = (const T*)p.mask;
-  for (int64_t m = wbeg; m < wend; ++m) {
-    // branch-free: every tap loads from a clamped (always in-bounds) address so that the 9 loads issue back to back;
-    // out-of-image taps are discarded by the select below
-    float xv[9][8];
-    bool ok[9];
+  const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (m >= M) return;
+  const int x = (int)(m % p.W), y = (int)((m / p.W) % p.H), b = (int)(m / ((int64_t)p.W * p.H));
+  float acc[32];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int tt = t < taps ? t : 0;
-      const int yy = y + tt / p.ks - half, xx = x + tt % p.ks - half;
-      ok[t] = t < taps && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-      const int yc = min(max(yy, 0), p.H - 1), xc = min(max(xx, 0), p.W - 1);
-      Vec8<T>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv[t]);
-    }
-    float acc = bias;
+  for (int j = 0; j < 32; ++j) acc[j] = bs[j];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
+  for (int t = 0; t < 9; ++t) {
+    if (t < taps) {
+      const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
+      const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      const int yc = min(max(yy, 0), p.H - 1), xc = min(max(xx, 0), p.W - 1);  // always a valid address
+      float xv[CIN];
+      PixLoad<T, CIN>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float xs = (ok[t] && c < cin) ? xv[t][c] : 0.f;   // padding channels are uninitialised memory
-        acc = fmaf(ws[t * 8 + c][lane], xs, acc);
+      for (int c = 0; c < CIN; ++c) {
+        const float xs = (ok && c < cin) ? xv[c] : 0.f;  // padding channels may hold anything
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[t * CIN + c][j]);
+          acc[j] = fmaf(wv.x, xs, acc[j]); acc[j + 1] = fmaf(wv.y, xs, acc[j + 1]);
+          acc[j + 2] = fmaf(wv.z, xs, acc[j + 2]); acc[j + 3] = fmaf(wv.w, xs, acc[j + 3]);
+        }
       }
     }
-    if (cov) {
-      if (res) acc += to_f<T>(res[m * p.ld_res + co]);
-      if (p.relu) acc = fmaxf(acc, 0.f);
-      if (mask && !(to_f<T>(mask[m * p.ld_mask + co]) > 0.f)) acc = 0.f;
-      if (p.round_tf32) acc = round_tf32_f(acc);
-      yo[m * p.ldy + co] = from_f<T>(acc);
+  }
+  const T* res = (const T*)p.res;
+  const T* mask = (const T*)p.mask;
+  T* yo = (T*)p.y + m * p.ldy + n0;
+  const bool fast = n0 + 32 <= p.cout && p.ldy % 8 == 0 && (((uintptr_t)p.y) & 31) == 0 &&
+                    (!res || (p.ld_res % 8 == 0 && (((uintptr_t)p.res) & 31) == 0)) &&
+                    (!mask || (p.ld_mask % 8 == 0 && (((uintptr_t)p.mask) & 31) == 0));
+  if (fast) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = acc[g * 8 + j];
+      if (res) {
+        float f[8];
+        Vec8<T>::load(res + m * p.ld_res + n0 + g * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += f[j];
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (mask) {
+        float f[8];
+        Vec8<T>::load(mask + m * p.ld_mask + n0 + g * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = f[j] > 0.f ? v[j] : 0.f;
+      }
+      if (p.round_tf32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = round_tf32_f(v[j]);
+      }
+      Vec8<T>::store(yo + g * 8, v);
     }
-    if (++x == p.W) { x = 0; if (++y == p.H) { y = 0; ++b; } }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = n0 + j;
+      if (n >= p.cout) continue;
+      float v = acc[j];
+      if (res) v += to_f<T>(res[m * p.ld_res + n]);
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (mask && !(to_f<T>(mask[m * p.ld_mask + n]) > 0.f)) v = 0.f;
+      if (p.round_tf32) v = round_tf32_f(v);
+      yo[j] = from_f<T>(v);
+    }
   }
 }
 
@@ -242,11 +311,13 @@ __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restri
   dw[o] = accumulate ? dw[o] + s : s;
 }
 
-// Weight gradient of the Cin <= 8 first layers (3 / 6 input variables): lane = output channel, the 9 x Cin
-// accumulators live in registers, x values are warp-uniform broadcast loads.  part[cta][tap][co][ci].
-template <typename T, int CMAX>
-__global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float* __restrict__ part, int pix_per_cta) {
-  __shared__ float red[9 * CMAX][32];
+// Weight gradient of the Cin <= 8 first layers (3 / 6 input variables): lane = output channel, the 9 x CIN
+// accumulators live in registers, x values are warp-uniform broadcast loads (only the CIN real channels), the
+// image border is handled by zeroing dy per tap (the clamped x load is always a finite real pixel).  Two pixels
+// per iteration are in flight.  part[cta][tap][co][ci].
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, float* __restrict__ part, int pix_per_cta) {
+  __shared__ float red[9 * CIN][32];
   const T* x0 = (const T*)p.x0;
   const T* dy = (const T*)p.dy;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -254,52 +325,41 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
   const int cin = p.c0, taps = p.ks * p.ks, half = p.ks / 2;
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
-  const bool vec = CMAX == 8 && p.ld0 % 8 == 0 && (((uintptr_t)p.x0) & 31) == 0;
-  float acc[9][CMAX];
+  float acc[9][CIN];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[t][c] = 0.f;
+    for (int c = 0; c < CIN; ++c) acc[t][c] = 0.f;
   // each warp owns a contiguous pixel range; (b, y, x) advance incrementally (no divisions in the loop)
   const int64_t per_warp = (pend - pbeg + 7) / 8;
   const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
   int x = (int)(wbeg % p.W), y = (int)((wbeg / p.W) % p.H), b = (int)(wbeg / ((int64_t)p.W * p.H));
-  for (int64_t m = wbeg; m < wend; ++m) {
-    const float g = co < p.cout ? to_f<T>(dy[m * p.ld_dy + co]) : 0.f;
-    if (vec) {
-      // branch-free clamped loads (issued back to back), out-of-image taps discarded by the select
-      float xv[9][8];
-      bool ok[9];
+  constexpr int UNR = CIN <= 3 ? 2 : 1;  // pixels in flight (register budget: 9*CIN accumulators + UNR*9*CIN inputs)
+  for (int64_t m = wbeg; m < wend; m += UNR) {
+    float g[UNR], xv[UNR][9][CIN];
+    bool ok[UNR][9];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const bool live = m + u < wend;
+      g[u] = (live && co < p.cout) ? to_f<T>(dy[(m + u) * p.ld_dy + co]) : 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int tt = t < taps ? t : 0;
         const int yy = y + tt / p.ks - half, xx = x + tt % p.ks - half;
-        ok[t] = t < taps && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        ok[u][t] = live && t < taps && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
         const int yc = min(max(yy, 0), p.H - 1), xc = min(max(xx, 0), p.W - 1);
-        Vec8<T>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv[t]);
+        PixLoad<T, CIN>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv[u][t]);
       }
+      if (live) { if (++x == p.W) { x = 0; if (++y == p.H) { y = 0; if (m + u + 1 < M) ++b; } } }
+    }
 #pragma unroll
-      for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-          const float xs = (ok[t] && c < cin) ? xv[t][c] : 0.f;
-          acc[t][c] = fmaf(g, xs, acc[t][c]);
-        }
-    } else {
+    for (int u = 0; u < UNR; ++u)
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        if (t < taps) {
-          const int yy = y + t / p.ks - half, xx = x + t % p.ks - half;
-          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-            const T* xp = x0 + (((int64_t)b * p.H + yy) * p.W + xx) * p.ld0;
+        const float gt = ok[u][t] ? g[u] : 0.f;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-              if (c < cin) acc[t][c] = fmaf(g, to_f<T>(xp[c]), acc[t][c]);
-          }
-        }
+        for (int c = 0; c < CIN; ++c) acc[t][c] = fmaf(gt, xv[u][t][c], acc[t][c]);
       }
-    }
-    if (++x == p.W) { x = 0; if (++y == p.H) { y = 0; ++b; } }
   }
   // sum the 8 warps in a fixed order
   for (int w = 0; w < 8; ++w) {
@@ -307,14 +367,14 @@ __global__ void __launch_bounds__(256) wgrad_smallc_kernel(WgradParams p, float*
 #pragma unroll
       for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) red[t * CMAX + c][lane] = (w == 0 ? 0.f : red[t * CMAX + c][lane]) + acc[t][c];
+        for (int c = 0; c < CIN; ++c) red[t * CIN + c][lane] = (w == 0 ? 0.f : red[t * CIN + c][lane]) + acc[t][c];
     }
     __syncthreads();
   }
   for (int i = threadIdx.x; i < taps * 32 * cin; i += 256) {
     const int ci = i % cin, l = (i / cin) % 32, t = i / (cin * 32);
     const int c2 = blockIdx.y * 32 + l;
-    if (c2 < p.cout) part[(((int64_t)blockIdx.x * taps + t) * p.cout + c2) * cin + ci] = red[t * CMAX + ci][l];
+    if (c2 < p.cout) part[(((int64_t)blockIdx.x * taps + t) * p.cout + c2) * cin + ci] = red[t * CIN + ci][l];
   }
 }
 
@@ -404,6 +464,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0, const 
   const int64_t b = i / HW, p = i % HW;
   for (int c = 0; c < c0; ++c) y[i * ldy + c] = from_f<T>(x0[(b * c0 + c) * HW + p]);
   for (int c = 0; c < c1; ++c) y[i * ldy + c0 + c] = from_f<T>(x1[(b * c1 + c) * HW + p]);
+  for (int c = c0 + c1; c < ldy; ++c) y[i * ldy + c] = from_f<T>(0.f);  // padding channels: finite, never NaN
 }
 
 template <typename T>
@@ -425,13 +486,12 @@ int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
   const int64_t M = (int64_t)p.B * p.H * p.W;
   // Cin <= 8 with an 8-channel padded, 32-byte aligned input buffer (how the engines stage the network input)
   if (p.c1 == 0 && p.c0 <= 8 && p.ld0 % 8 == 0 && (((uintptr_t)p.x0) & 31) == 0 && (p.ks == 1 || p.ks == 3)) {
-    int want = 4 * num_sms() / cdiv(p.cout, 32);
-    if (want < 1) want = 1;
-    int ppc = (int)((M + want - 1) / want);
-    if (ppc < 256) ppc = 256;
-    dim3 grid(cdiv(M, ppc), cdiv(p.cout, 32));
-    if (dtype == PUB_BF16) conv_smallc_kernel<bf16><<<grid, 256, 0, s>>>(p, ppc);
-    else conv_smallc_kernel<float><<<grid, 256, 0, s>>>(p, ppc);
+    dim3 grid(cdiv(M, 128), cdiv(p.cout, 32));
+    const int cc = p.c0 <= 3 ? 3 : (p.c0 <= 6 ? 6 : 8);
+#define PUB_SMALLC(TT, CC) conv_smallc_kernel<TT, CC><<<grid, 128, 0, s>>>(p)
+    if (dtype == PUB_BF16) { if (cc == 3) PUB_SMALLC(bf16, 3); else if (cc == 6) PUB_SMALLC(bf16, 6); else PUB_SMALLC(bf16, 8); }
+    else { if (cc == 3) PUB_SMALLC(float, 3); else if (cc == 6) PUB_SMALLC(float, 6); else PUB_SMALLC(float, 8); }
+#undef PUB_SMALLC
     PUB_LAUNCH_CHECK();
     return 0;
   }
@@ -442,7 +502,10 @@ int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
   return 0;
 }
 
-static bool smallc_ok(const WgradParams& p) { return p.c1 == 0 && p.c0 <= 8 && (p.ks == 1 || p.ks == 3); }
+static bool smallc_ok(const WgradParams& p) {
+  // the 8-channel padded, 32-byte aligned staging buffer of the network input (PixLoad reads 8..32 B per pixel)
+  return p.c1 == 0 && p.c0 <= 8 && (p.ks == 1 || p.ks == 3) && p.ld0 % 8 == 0 && (((uintptr_t)p.x0) & 31) == 0;
+}
 static void smallc_plan(const WgradParams& p, int& nctas, int& ppc) {
   const int64_t M = (int64_t)p.B * p.H * p.W;
   int want = 4 * num_sms() / cdiv(p.cout, 32);
@@ -516,8 +579,11 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
     int nctas, ppc;
     smallc_plan(p, nctas, ppc);
     dim3 grid(nctas, cdiv(p.cout, 32));
-    if (dtype == PUB_BF16) wgrad_smallc_kernel<bf16, 8><<<grid, 256, 0, s>>>(p, part, ppc);
-    else wgrad_smallc_kernel<float, 8><<<grid, 256, 0, s>>>(p, part, ppc);
+    const int cc = p.c0 <= 3 ? 3 : (p.c0 <= 6 ? 6 : 8);
+#define PUB_SMALLC(TT, CC) wgrad_smallc_kernel<TT, CC><<<grid, 256, 0, s>>>(p, part, ppc)
+    if (dtype == PUB_BF16) { if (cc == 3) PUB_SMALLC(bf16, 3); else if (cc == 6) PUB_SMALLC(bf16, 6); else PUB_SMALLC(bf16, 8); }
+    else { if (cc == 3) PUB_SMALLC(float, 3); else if (cc == 6) PUB_SMALLC(float, 6); else PUB_SMALLC(float, 8); }
+#undef PUB_SMALLC
     nsplit = nctas;
   } else {
     dim3 grid(cdiv(cin, BN), cdiv(p.cout, BM), taps * nsplit);

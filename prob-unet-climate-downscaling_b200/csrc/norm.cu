@@ -16,7 +16,22 @@ namespace {
 
 constexpr int GN_NT = 256;
 // pixels per chunk (one CTA): small feature maps get small chunks so that the low-resolution layers still fill the GPU
-__host__ __device__ inline int gn_rows(int HW) { return HW >= 16384 ? 256 : (HW >= 1024 ? 128 : 64); }
+// (longer per-thread loops amortise the per-channel constant set-up; >= 4 CTAs per SM remain at B = 64)
+__host__ __device__ inline int gn_rows(int HW) { return HW >= 16384 ? 512 : (HW >= 4096 ? 256 : (HW >= 1024 ? 128 : 64)); }
+
+// MUFU-only sigmoid (ex2 + rcp, no IEEE-division subroutine): rel. error ~1e-6, far inside the 1e-4 parity budget.
+// The kernels below are otherwise issue-bound on the division slow path rather than HBM-bound.
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
+__device__ __forceinline__ float silu_grad_fast(float x) {
+  const float s = sigmoid_fast(x);
+  return fmaf(x * s, 1.f - s, s);
+}
 
 // Every heavy kernel uses the same decomposition: grid = (pixel chunks, batch); inside a CTA thread t owns the
 // 8-channel vector v = t % V for the rows pr, pr + ppi, ... of the chunk (ppi = 256 / V).  The per-channel
@@ -114,11 +129,17 @@ __device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__
 }
 
 // ---------------------------------------------------------------- per-channel two-value partial sums
-// MODE 0: (x, x^2)          -- forward statistics
+// MODE 0: (x, x^2)                 -- forward statistics
 // MODE 1: (du, du * (x - mean_g))  -- backward; du = g_y * silu'(a x + b); sum du*xhat = rstd * second sum
+//         (accumulated as sum du*x and corrected by -mean * sum du when the partial is written: 8 fewer live
+//         registers and one fewer FLOP per element in the hot loop)
+// UNROLL rows are loaded back to back as raw vectors before any is consumed; with <= 64 (MODE 0) / <= 80 (MODE 1)
+// registers three to four CTAs share an SM, so one CTA's loads overlap another's arithmetic.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* __restrict__ dy, float* __restrict__ part) {
+__global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(GnParams p, const T* __restrict__ dy,
+                                                                               float* __restrict__ part) {
   extern __shared__ float sm[];  // [ppi][V][16]
+  constexpr int UNR = MODE == 0 ? 4 : 2;
   const int C = p.c0 + p.c1, V = C / 8;
   const int ppi = GN_NT / V;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -131,30 +152,29 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (pr < ppi) {
-    float a[8], bb[8], mean[8];
-    if (MODE == 1) {
-      load_affine(p.coef, b, C, v, a, bb);
-      const int cpg = C / p.groups;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mean[j] = p.stats[((int64_t)b * p.groups + (v * 8 + j) / cpg) * 2];
-    }
+    float a[8], bb[8];
+    if (MODE == 1) load_affine(p.coef, b, C, v, a, bb);
     const uint32_t thresh = drop_thresh(p.p_drop);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     if (MODE == 0 || p.resample == 0) {
-      // fast path: loads of GN_UNROLL rows are issued first (raw), then consumed
-      for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
-        Raw8<T> xr[GN_UNROLL], gr[GN_UNROLL];
+      // this thread's vector of pixel (b, 0) and its pixel pitch (the two sources of a virtual concat differ)
+      const int c = v * 8;
+      const T* xb = c < p.c0 ? (const T*)p.x0 + (int64_t)b * HW * p.ld0 + c
+                             : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
+      const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
+      const T* gb = MODE == 1 ? dy + (int64_t)b * HW * C + c : nullptr;
+      for (int rb = r0 + pr; rb < r1; rb += UNR * ppi) {
+        Raw8<T> xr[UNR], gr[UNR];
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) {
+        for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * ppi;
           if (r < r1) {
-            const int64_t pix = (int64_t)b * HW + r;
-            xr[u].load(vec_ptr<T>(p, pix, v));
-            if (MODE == 1) gr[u].load(dy + pix * C + v * 8);
+            xr[u].load(xb + r * ldx);
+            if (MODE == 1) gr[u].load(gb + (int64_t)r * C);
           }
         }
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) {
+        for (int u = 0; u < UNR; ++u) {
           const int r = rb + u * ppi;
           if (r < r1) {
             float x[8];
@@ -167,15 +187,15 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
               gr[u].unpack(g);
               if (p.p_drop > 0.f) {
                 bool keep[8];
-                dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + v * 8, thresh, keep);
+                dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
+                const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
                 s1[j] += du;
-                s2[j] = fmaf(du, x[j] - mean[j], s2[j]);
+                s2[j] = fmaf(du, x[j], s2[j]);
               }
             }
           }
@@ -189,9 +209,9 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
         load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
+          const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
           s1[j] += du;
-          s2[j] = fmaf(du, x[j] - mean[j], s2[j]);
+          s2[j] = fmaf(du, x[j], s2[j]);
         }
       }
     }
@@ -199,12 +219,13 @@ __global__ void __launch_bounds__(GN_NT) gn_partial_kernel(GnParams p, const T* 
     for (int j = 0; j < 8; ++j) { sm[(pr * V + v) * 16 + j] = s1[j]; sm[(pr * V + v) * 16 + 8 + j] = s2[j]; }
   }
   __syncthreads();
-  for (int i = t; i < V * 16; i += GN_NT) {  // fixed-order sum over the row slots
-    float s = 0.f;
-    for (int q = 0; q < ppi; ++q) s += sm[q * V * 16 + i];
-    const int vv = i / 16, jj = i % 16;
-    const int c = vv * 8 + (jj & 7), which = jj >> 3;
-    part[(((int64_t)b * gridDim.x + chunk) * C + c) * 2 + which] = s;
+  // fixed-order sum over the row slots: thread i owns channel i (both sums)
+  for (int c = t; c < C; c += GN_NT) {
+    const int vv = c >> 3, jj = c & 7;
+    float q1 = 0.f, q2 = 0.f;
+    for (int q = 0; q < ppi; ++q) { q1 += sm[(q * V + vv) * 16 + jj]; q2 += sm[(q * V + vv) * 16 + 8 + jj]; }
+    if (MODE == 1) q2 -= p.stats[((int64_t)b * p.groups + c / (C / p.groups)) * 2] * q1;
+    *reinterpret_cast<float2*>(part + (((int64_t)b * gridDim.x + chunk) * C + c) * 2) = make_float2(q1, q2);
   }
 }
 
@@ -239,7 +260,7 @@ __global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, i
 
 // y = resample(dropout(silu(a x + b))); the chunk index runs over INPUT pixels (none / up) or OUTPUT pixels (down)
 template <typename T>
-__global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restrict__ y) {
+__global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __restrict__ y) {
   const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
   const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
   if (pr >= ppi) return;
@@ -251,12 +272,16 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     const int rows = gn_rows(HW);
     const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
+    const int c = v * 8;
+    const T* xb = c < p.c0 ? (const T*)p.x0 + (int64_t)b * HW * p.ld0 + c
+                           : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
+    const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
     for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
       Raw8<T> xr[GN_UNROLL];
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u) {
         const int r = rb + u * ppi;
-        if (r < r1) xr[u].load(vec_ptr<T>(p, (int64_t)b * HW + r, v));
+        if (r < r1) xr[u].load(xb + r * ldx);
       }
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u) {
@@ -266,21 +291,21 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
         float x[8], o[8];
         xr[u].unpack(x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = silu_f(fmaf(a[j], x[j], bb[j]));
+        for (int j = 0; j < 8; ++j) o[j] = silu_fast(fmaf(a[j], x[j], bb[j]));
         if (p.p_drop > 0.f) {
           bool keep[8];
-          dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
+          dropout_keep8(p.seed, p.subseq, pix * C + c, thresh, keep);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
         }
         if (p.resample == 0) {
-          Vec8<T>::store(y + pix * C + v * 8, o);
+          Vec8<T>::store(y + pix * C + c, o);
         } else {  // nearest 2x upsample: write the 2x2 children
           const int yy = r / p.W, xx = r % p.W;
 #pragma unroll
           for (int d = 0; d < 4; ++d) {
             const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
-            Vec8<T>::store(y + q * C + v * 8, o);
+            Vec8<T>::store(y + q * C + c, o);
           }
         }
       }
@@ -300,7 +325,7 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
         float x[8];
         load_vec<T>(p, pix, v, x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += silu_f(fmaf(a[j], x[j], bb[j]));
+        for (int j = 0; j < 8; ++j) o[j] += silu_fast(fmaf(a[j], x[j], bb[j]));
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
@@ -309,7 +334,7 @@ __global__ void __launch_bounds__(GN_NT) gn_apply_kernel(GnParams p, T* __restri
   }
 }
 
-// backward finalize 1: per (b, g) -> bcoef[b][c] = (c1, c2, c3):  dx = c1*du + c2*x + c3
+// backward finalize 1: per (b, g) -> bcoef[b][c] = (c2, c3):  dx = a*du + c2*x + c3  (a = forward coefficient)
 // partials hold P1 = sum du, P2 = sum du*(x - mean);  sum du*xhat = rstd * P2
 __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef,
                                     float* __restrict__ bsum) {
@@ -342,24 +367,25 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
   const float c3 = (float)(-(double)rstd * m1 + (double)rstd * rstd * m2 * mean);
   for (int i = lane; i < cpg; i += 32) {
     const int c = g * cpg + i;
-    const float sc = p.film ? 1.f + p.film[c] : 1.f;
-    float* o = bcoef + ((int64_t)b * C + c) * 4;
-    o[0] = rstd * p.gamma[c] * sc; o[1] = c2; o[2] = c3; o[3] = 0.f;
+    *reinterpret_cast<float2*>(bcoef + ((int64_t)b * C + c) * 2) = make_float2(c2, c3);
   }
 }
 
 // backward finalize 2: per channel parameter gradients = sum over the batch of the per-(b, c) sums written by
-// gn_bwd_group_kernel (thread per channel, coalesced, fixed order)
+// gn_bwd_group_kernel.  One warp per channel: lanes stride over the batch, fixed shuffle tree (a thread per
+// channel walking the batch serially took 50 us per launch -- 3 ms of a training step).
 __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ bsum, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ dfilm) {
   const int C = p.c0 + p.c1;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < p.B; ++b) {
+  for (int b = lane; b < p.B; b += 32) {
     const float2 v = *reinterpret_cast<const float2*>(bsum + ((int64_t)b * C + c) * 2);
     s1 += (double)v.x; s2 += (double)v.y;
   }
+  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+  if (lane != 0) return;
   const float sc = p.film ? 1.f + p.film[c] : 1.f;
   dgamma[c] = (float)(s2 * sc);
   dbeta[c] = (float)(s1 * sc);
@@ -369,64 +395,68 @@ __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ bsum, 
   }
 }
 
+// dx = a*du + c2*x + c3 (+ addend);  a = rstd*gamma*(1+scale) is the forward coefficient, (c2, c3) come from the
+// group sums (bcoef[b][c] = (c2, c3)).  Two rows in flight per thread and <= 80 registers (three CTAs per SM).
 template <typename T>
-__global__ void __launch_bounds__(GN_NT) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
-                                                             const float* __restrict__ bcoef, T* __restrict__ dx,
-                                                             const T* __restrict__ addend, int ld_add) {
+__global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
+                                                                const float* __restrict__ bcoef, T* __restrict__ dx,
+                                                                const T* __restrict__ addend, int ld_add) {
+  constexpr int UNR = 2;
   const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
   const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
   if (pr >= ppi) return;
-  float a[8], bb[8], c1[8], c2[8], c3[8];
+  float a[8], bb[8], c2[8], c3[8];
   load_affine(p.coef, b, C, v, a, bb);
-  {
-    const float4* q = reinterpret_cast<const float4*>(bcoef + ((int64_t)b * C + v * 8) * 4);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const float4 u = q[j]; c1[j] = u.x; c2[j] = u.y; c3[j] = u.z; }
-  }
+  load_affine(bcoef, b, C, v, c2, c3);
   const uint32_t thresh = drop_thresh(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const int HW = p.H * p.W;
   const int rows = gn_rows(HW);
   const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
+  const int c = v * 8;
   if (p.resample == 0) {
-    for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
-      Raw8<T> xr[GN_UNROLL], gr[GN_UNROLL], ar[GN_UNROLL];
+    const T* xb = c < p.c0 ? (const T*)p.x0 + (int64_t)b * HW * p.ld0 + c
+                           : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
+    const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
+    const T* gb = dy + (int64_t)b * HW * C + c;
+    const T* ab = addend ? addend + (int64_t)b * HW * ld_add + c : nullptr;
+    T* ob = dx + (int64_t)b * HW * C + c;
+    for (int rb = r0 + pr; rb < r1; rb += UNR * ppi) {
+      Raw8<T> xr[UNR], gr[UNR], ar[UNR];
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
+      for (int u = 0; u < UNR; ++u) {
         const int r = rb + u * ppi;
         if (r < r1) {
-          const int64_t pix = (int64_t)b * HW + r;
-          xr[u].load(vec_ptr<T>(p, pix, v));
-          gr[u].load(dy + pix * C + v * 8);
-          if (addend) ar[u].load(addend + pix * ld_add + v * 8);
+          xr[u].load(xb + r * ldx);
+          gr[u].load(gb + (int64_t)r * C);
+          if (ab) ar[u].load(ab + (int64_t)r * ld_add);
         }
       }
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
+      for (int u = 0; u < UNR; ++u) {
         const int r = rb + u * ppi;
         if (r >= r1) continue;
-        const int64_t pix = (int64_t)b * HW + r;
         float x[8], g[8], o[8];
         xr[u].unpack(x);
         gr[u].unpack(g);
         if (p.p_drop > 0.f) {
           bool keep[8];
-          dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
+          dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
-          o[j] = fmaf(c1[j], du, fmaf(c2[j], x[j], c3[j]));
+          const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
+          o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
         }
-        if (addend) {
+        if (ab) {
           float ad[8];
           ar[u].unpack(ad);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += ad[j];
         }
-        Vec8<T>::store(dx + pix * C + v * 8, o);
+        Vec8<T>::store(ob + (int64_t)r * C, o);
       }
     }
     return;
@@ -438,16 +468,16 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_apply_kernel(GnParams p, const T
     load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float du = g[j] * silu_grad_f(fmaf(a[j], x[j], bb[j]));
-      o[j] = fmaf(c1[j], du, fmaf(c2[j], x[j], c3[j]));
+      const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
+      o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
     }
     if (addend) {
       float ad[8];
-      Vec8<T>::load(addend + pix * ld_add + v * 8, ad);
+      Vec8<T>::load(addend + pix * ld_add + c, ad);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += ad[j];
     }
-    Vec8<T>::store(dx + pix * C + v * 8, o);
+    Vec8<T>::store(dx + pix * C + c, o);
   }
 }
 
@@ -500,10 +530,10 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   if (dtype == PUB_BF16) gn_partial_kernel<bf16, 1><<<grid, GN_NT, smem, s>>>(p, (const bf16*)dy, p.partial);
   else gn_partial_kernel<float, 1><<<grid, GN_NT, smem, s>>>(p, (const float*)dy, p.partial);
   PUB_LAUNCH_CHECK();
-  float* bsum = bcoef + (size_t)p.B * C * 4;
+  float* bsum = bcoef + (size_t)p.B * C * 2;
   gn_bwd_group_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc, bcoef, bsum);
   PUB_LAUNCH_CHECK();
-  gn_bwd_param_kernel<<<cdiv(C, 64), 64, 0, s>>>(p, bsum, dgamma, dbeta, dfilm);
+  gn_bwd_param_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(p, bsum, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   if (dx) {
     if (dtype == PUB_BF16)
