@@ -289,6 +289,289 @@ __global__ void __launch_bounds__(NT) fcomb_bwd_kernel(FcombDev a, const float* 
   for (int i = t; i < a.M * F; i += NT) o[2 * F * F + CO * F + F + 4 + i] = Sacc[i];
 }
 
+// ---- backward, bf16 path: the same algebra on warp-level tensor-core MMAs (mma.sync.m16n8k16, bf16 x bf16 -> f32)
+//
+// One warp owns a 16-pixel tile and keeps EVERYTHING in registers in MMA fragment layout: the accumulator fragment
+// of one product is re-packed (f32 -> bf16 pairs) into the A fragment of the next (h1 -> h2 -> dp2 -> dh1), and the
+// four reductions over pixels (dW1, dW0f, dW2, db1) are MMAs with K = pixels whose operands are the 8x8 register
+// transposes (movmatrix) of those same fragments.  No shared-memory tiles and no block barriers in the member loop:
+// ~30 MMAs + ~30 register transposes per (member, 16 pixels) replace ~3000 FMAs + ~900 shared loads per
+// (member, pixel) of the fp32 kernel above (6.9 ms -> <1 ms at B = 64, 128^2, M = 15).
+//
+// Fragment conventions (g = lane / 4, t = lane % 4):
+//   A (16 x 16, row): a0 = (row g, k 2t..2t+1)  a1 = (row g+8, k 2t..)  a2 = (row g, k 2t+8..)  a3 = (row g+8, k 2t+8..)
+//   B (16 x 8,  col): b0 = (k 2t..2t+1, n g)    b1 = (k 2t+8.., n g)
+//   C (16 x 8):       c0,c1 = (row g, n 2t..2t+1)   c2,c3 = (row g+8, n 2t..2t+1)
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 8x8 b16 transpose across the warp (thread holds row g, columns 2t..2t+1 before and after)
+__device__ __forceinline__ uint32_t movm(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// accumulator fragments of a 16 x 32 tile (4 n-tiles) -> the two k16 A fragments of the same tile
+__device__ __forceinline__ void c_to_a(const float (&c)[4][4], uint32_t (&a)[2][4]) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    a[s][0] = pack2(c[2 * s][0], c[2 * s][1]);
+    a[s][1] = pack2(c[2 * s][2], c[2 * s][3]);
+    a[s][2] = pack2(c[2 * s + 1][0], c[2 * s + 1][1]);
+    a[s][3] = pack2(c[2 * s + 1][2], c[2 * s + 1][3]);
+  }
+}
+// X [16 px x 32 ch] given as its two k16 A fragments -> X^T as A fragments of two m-tiles (ch 0-15 / 16-31, K = px)
+__device__ __forceinline__ void a_transpose(const uint32_t (&a)[2][4], uint32_t (&at)[2][4]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    at[u][0] = movm(a[u][0]);   // (ch 0-7,  px 0-7)
+    at[u][1] = movm(a[u][2]);   // (ch 8-15, px 0-7)
+    at[u][2] = movm(a[u][1]);   // (ch 0-7,  px 8-15)
+    at[u][3] = movm(a[u][3]);   // (ch 8-15, px 8-15)
+  }
+}
+// the same transposes read as B fragments [K = px][N = 8 channels] of n-tile q (= 2u + h): b0 = at[u][h], b1 = at[u][2 + h]
+
+constexpr int WP = F + 8;  // smem row pitch (bf16) of the weight matrices: conflict-free B-fragment loads
+
+struct __align__(16) FcombMmaSmem {
+  __nv_bfloat16 w1[F][WP];    // [k][j]
+  __nv_bfloat16 w1t[F][WP];   // [j][k]
+  __nv_bfloat16 w0[F][WP];    // [j][i]   (feature half of layer 0)
+  __nv_bfloat16 w0t[F][WP];   // [i][j]
+  __nv_bfloat16 w2t[F][4];    // [k][c]   (c = 3 padded with 0)
+  float b1[F];
+  float red[2 * F * F + CO * F + F + 4];
+};
+
+__global__ void __launch_bounds__(NT, 2) fcomb_bwd_mma_kernel(FcombDev a, const float* __restrict__ dout,
+                                                               bf16* __restrict__ dfeat, float* __restrict__ part) {
+  __shared__ FcombMmaSmem s;
+  extern __shared__ float dyn[];  // zbs[M][F] | Sacc[4 warps][M][F]
+  float* zbs = dyn;
+  float* Sacc = dyn + a.M * F;
+  const int b = blockIdx.y, HW = a.H * a.W, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < F * F; i += NT) {
+    const int r = i / F, c = i % F;
+    const float v1 = a.w1[i], v0 = a.w0[r * (F + a.L) + c];
+    s.w1[r][c] = __float2bfloat16_rn(v1); s.w1t[c][r] = __float2bfloat16_rn(v1);
+    s.w0[r][c] = __float2bfloat16_rn(v0); s.w0t[c][r] = __float2bfloat16_rn(v0);
+  }
+  for (int i = tid; i < F * 4; i += NT) {
+    const int k = i >> 2, c = i & 3;
+    s.w2t[k][c] = __float2bfloat16_rn(c < CO ? a.w2[c * F + k] : 0.f);
+  }
+  if (tid < F) s.b1[tid] = a.b1[tid];
+  for (int i = tid; i < a.M * F; i += NT) zbs[i] = a.zb[((int64_t)(i / F) * a.B + b) * F + i % F];
+  for (int i = tid; i < 4 * a.M * F; i += NT) Sacc[i] = 0.f;
+  __syncthreads();
+
+  // persistent accumulators (this warp's share; summed over warps / CTAs at the end in a fixed order)
+  float aW1[2][4][4], aW0[2][4][4], aW2[2][4], ab1[2][4], ab2[4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) aW1[u][q][r] = aW0[u][q][r] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) aW2[u][r] = ab1[u][r] = 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ab2[r] = 0.f;
+  const uint32_t ONES = 0x3F803F80u;  // bf16 (1, 1)
+  const uint32_t onesA[4] = {ONES, ONES, ONES, ONES};
+  float* Sw = Sacc + (size_t)warp * a.M * F;
+
+  const int ntile = (HW + 15) / 16;
+  for (int tile = blockIdx.x * 4 + warp; tile < ntile; tile += gridDim.x * 4) {
+    const int p0 = tile * 16 + g, p1 = p0 + 8;           // this thread's two pixel rows
+    const bool v0 = p0 < HW, v1 = p1 < HW;
+    // ---- features as A fragments (two k16 blocks over the 32 channels)
+    uint32_t fa[2][4];
+    {
+      const bf16* f0 = (const bf16*)a.feat + ((int64_t)b * HW + p0) * F;
+      const bf16* f1 = (const bf16*)a.feat + ((int64_t)b * HW + p1) * F;
+#pragma unroll
+      for (int sk = 0; sk < 2; ++sk) {
+        fa[sk][0] = v0 ? *reinterpret_cast<const uint32_t*>(f0 + 16 * sk + 2 * t) : 0u;
+        fa[sk][1] = v1 ? *reinterpret_cast<const uint32_t*>(f1 + 16 * sk + 2 * t) : 0u;
+        fa[sk][2] = v0 ? *reinterpret_cast<const uint32_t*>(f0 + 16 * sk + 8 + 2 * t) : 0u;
+        fa[sk][3] = v1 ? *reinterpret_cast<const uint32_t*>(f1 + 16 * sk + 8 + 2 * t) : 0u;
+      }
+    }
+    // ---- base[px][j] = sum_i f[px][i] W0f[j][i]
+    float base[4][4], dbase[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) base[q][r] = dbase[q][r] = 0.f;
+#pragma unroll
+      for (int sk = 0; sk < 2; ++sk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w0[8 * q + g][16 * sk + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w0[8 * q + g][16 * sk + 8 + 2 * t]);
+        mma16816(base[q], fa[sk], b0, b1);
+      }
+    }
+    for (int m = 0; m < a.M; ++m) {
+      // ---- h1 = relu(base + zb[m])
+      float h1[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 z = *reinterpret_cast<const float2*>(&zbs[m * F + 8 * q + 2 * t]);
+        h1[q][0] = fmaxf(base[q][0] + z.x, 0.f); h1[q][1] = fmaxf(base[q][1] + z.y, 0.f);
+        h1[q][2] = fmaxf(base[q][2] + z.x, 0.f); h1[q][3] = fmaxf(base[q][3] + z.y, 0.f);
+      }
+      uint32_t h1a[2][4];
+      c_to_a(h1, h1a);
+      // ---- upstream gradient of this member as an A fragment [16 px x 16 (3 real) channels]
+      uint32_t da[4] = {0u, 0u, 0u, 0u};
+      {
+        const float* dp = dout + (((int64_t)b * a.M + m) * CO) * HW;
+        float x00 = 0.f, x01 = 0.f, x10 = 0.f, x11 = 0.f;
+        if (t == 0) {
+          if (v0) { x00 = dp[p0]; x01 = dp[(int64_t)HW + p0]; }
+          if (v1) { x10 = dp[p1]; x11 = dp[(int64_t)HW + p1]; }
+        } else if (t == 1) {
+          if (v0) x00 = dp[2 * (int64_t)HW + p0];
+          if (v1) x10 = dp[2 * (int64_t)HW + p1];
+        }
+        da[0] = pack2(x00, x01); da[1] = pack2(x10, x11);
+      }
+      // ---- h2pre = h1 W1^T + b1 ; dp2pre = dout W2
+      float h2[4][4], dp2[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 bb = *reinterpret_cast<const float2*>(&s.b1[8 * q + 2 * t]);
+        h2[q][0] = bb.x; h2[q][1] = bb.y; h2[q][2] = bb.x; h2[q][3] = bb.y;
+#pragma unroll
+        for (int sk = 0; sk < 2; ++sk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w1[8 * q + g][16 * sk + 2 * t]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w1[8 * q + g][16 * sk + 8 + 2 * t]);
+          mma16816(h2[q], h1a[sk], b0, b1);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) dp2[q][r] = 0.f;
+        const uint32_t w2b = t < 2 ? *reinterpret_cast<const uint32_t*>(&s.w2t[8 * q + g][2 * t]) : 0u;
+        mma16816(dp2[q], da, w2b, 0u);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          dp2[q][r] = h2[q][r] > 0.f ? dp2[q][r] : 0.f;   // relu'(pre2)
+          h2[q][r] = fmaxf(h2[q][r], 0.f);
+        }
+      }
+      uint32_t h2a[2][4], dp2a[2][4];
+      c_to_a(h2, h2a);
+      c_to_a(dp2, dp2a);
+      // ---- dh1 = dp2 W1 ; dp1 = relu'(pre1) dh1 ; dbase += dp1 ; S[m] += column sums of dp1
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float dh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sk = 0; sk < 2; ++sk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w1t[8 * q + g][16 * sk + 2 * t]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w1t[8 * q + g][16 * sk + 8 + 2 * t]);
+          mma16816(dh, dp2a[sk], b0, b1);
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float v = h1[q][r] > 0.f ? dh[r] : 0.f;
+          dbase[q][r] += v;
+          if (r & 1) s1 += v; else s0 += v;
+        }
+        // sum over the 8 row groups g (lane bits 2..4): fixed xor tree
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        if (g == 0) { Sw[m * F + 8 * q + 2 * t] += s0; Sw[m * F + 8 * q + 2 * t + 1] += s1; }
+      }
+      // ---- reductions over the 16 pixels (K = px): operands are register transposes of the fragments above
+      uint32_t dp2t[2][4], h1t[2][4], h2t[2][4];
+      a_transpose(dp2a, dp2t);
+      a_transpose(h1a, h1t);
+      a_transpose(h2a, h2t);
+      const uint32_t dt0 = movm(da[0]), dt1 = movm(da[1]);   // dout as B fragment [K = px][N = c]
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)   // dW1[k][j] += dp2[px][k] h1[px][j]
+          mma16816(aW1[u][q], dp2t[u], h1t[q >> 1][q & 1], h1t[q >> 1][2 + (q & 1)]);
+        mma16816(ab1[u], dp2t[u], ONES, ONES);          // db1[k]  += dp2[px][k]
+        mma16816(aW2[u], h2t[u], dt0, dt1);             // dW2[c][k] += dout[px][c] h2[px][k]   (stored [k][c])
+      }
+      mma16816(ab2, onesA, dt0, dt1);                    // db2[c] += dout[px][c]
+    }
+    // ---- dW0f[j][i] += dbase[px][j] f[px][i] ; dfeat[px][i] = sum_j dbase[px][j] W0f[j][i]
+    uint32_t dba[2][4], dbt[2][4], ft[2][4];
+    c_to_a(dbase, dba);
+    a_transpose(dba, dbt);
+    a_transpose(fa, ft);
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mma16816(aW0[u][q], dbt[u], ft[q >> 1][q & 1], ft[q >> 1][2 + (q & 1)]);
+    if (dfeat) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float df[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sk = 0; sk < 2; ++sk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w0t[8 * q + g][16 * sk + 2 * t]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w0t[8 * q + g][16 * sk + 8 + 2 * t]);
+          mma16816(df, dba[sk], b0, b1);
+        }
+        if (v0) *reinterpret_cast<uint32_t*>(dfeat + ((int64_t)b * HW + p0) * F + 8 * q + 2 * t) = pack2(df[0], df[1]);
+        if (v1) *reinterpret_cast<uint32_t*>(dfeat + ((int64_t)b * HW + p1) * F + 8 * q + 2 * t) = pack2(df[2], df[3]);
+      }
+    }
+  }
+  // ---- CTA partial: the four warps add their accumulators into s.red in warp order (fixed), then one store
+  for (int i = tid; i < 2 * F * F + CO * F + F + 4; i += NT) s.red[i] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < 4; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int row = 16 * u + g + (r >> 1) * 8, col = 8 * q + 2 * t + (r & 1);
+            s.red[row * F + col] += aW1[u][q][r];
+            s.red[F * F + row * F + col] += aW0[u][q][r];
+          }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int k = 16 * u + g + (r >> 1) * 8, c = 2 * t + (r & 1);
+          if (c < CO) s.red[2 * F * F + c * F + k] += aW2[u][r];
+        }
+        if (t == 0) {
+          s.red[2 * F * F + CO * F + 16 * u + g] += ab1[u][0];
+          s.red[2 * F * F + CO * F + 16 * u + g + 8] += ab1[u][2];
+        }
+      }
+      if (g == 0) {
+        if (2 * t < CO) s.red[2 * F * F + CO * F + F + 2 * t] += ab2[0];
+        if (2 * t + 1 < CO) s.red[2 * F * F + CO * F + F + 2 * t + 1] += ab2[1];
+      }
+    }
+    __syncthreads();
+  }
+  float* o = part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * part_stride(a.M);
+  for (int i = tid; i < 2 * F * F + CO * F + F + 4; i += NT) o[i] = s.red[i];
+  for (int i = tid; i < a.M * F; i += NT)
+    o[2 * F * F + CO * F + F + 4 + i] = (Sacc[i] + Sacc[a.M * F + i]) + (Sacc[2 * a.M * F + i] + Sacc[3 * a.M * F + i]);
+}
+
 // final reduction over CTAs (fixed order) + the latent-half gradients
 __global__ void fcomb_bwd_final_kernel(const float* __restrict__ part, int nx, int B, int M, int L,
                                        const float* __restrict__ z, const float* __restrict__ w0,
@@ -418,15 +701,29 @@ int pub_fcomb_backward(const pub_fcomb_args* a, const float* dout, void* dfeat, 
   const FcombDev d = make_dev(a, zb);
   const int gx = bwd_grid_x(a->B, a->H * a->W);
   dim3 grid(gx, a->B);
+  if (!a->feat_nchw && a->dtype == PUB_BF16) {
+    // bf16 compute path: tensor-core kernel (no block-wide tiles; 5 floats of dynamic smem per (member, channel))
+    const size_t dynm = (size_t)a->M * F * 4 * 5;
+    static bool attr_m = false;
+    if (!attr_m) {
+      PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_m = true;
+    }
+    fcomb_bwd_mma_kernel<<<grid, NT, dynm, st>>>(d, dout, (bf16*)dfeat, part);
+    PUB_LAUNCH_CHECK();
+    fcomb_bwd_final_kernel<<<16, 256, 0, st>>>(part, gx, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0, dw1, db1, dw2, db2, Stot);
+    PUB_LAUNCH_CHECK();
+    fcomb_bwd_latent_kernel<<<8, 256, 0, st>>>(Stot, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0);
+    PUB_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t dyn = (size_t)a->M * F * 4 * 2;
   static bool attr = false;
   if (!attr) {  // static (tiles + weights, ~45 KB) + dynamic smem exceeds the 48 KB default limit for M > 8
-    PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  if (!a->feat_nchw && a->dtype == PUB_BF16) fcomb_bwd_kernel<bf16><<<grid, NT, dyn, st>>>(d, dout, dfeat, part);
-  else fcomb_bwd_kernel<float><<<grid, NT, dyn, st>>>(d, dout, dfeat, part);
+  fcomb_bwd_kernel<float><<<grid, NT, dyn, st>>>(d, dout, dfeat, part);
   PUB_LAUNCH_CHECK();
   fcomb_bwd_final_kernel<<<16, 256, 0, st>>>(part, gx, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0, dw1, db1, dw2, db2, Stot);
   PUB_LAUNCH_CHECK();
