@@ -70,7 +70,7 @@ class AdamWEntry(C.Structure):
 
 # every symbol include/probunet_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "pub_last_error", "pub_version", "pub_launch_count", "pub_conv2d_forward", "pub_pack_conv_weight", "pub_conv2d_wgrad_workspace",
+    "pub_last_error", "pub_version", "pub_launch_count", "pub_debug_option", "pub_debug_pointer", "pub_conv2d_forward", "pub_pack_conv_weight", "pub_conv2d_wgrad_workspace",
     "pub_conv2d_wgrad", "pub_nchw_to_nhwc", "pub_nhwc_to_nchw", "pub_unet_create", "pub_unet_destroy",
     "pub_unet_num_params", "pub_unet_workspace_bytes", "pub_unet_forward", "pub_unet_backward",
     "pub_unet_dropout_mask", "pub_encoder_create", "pub_encoder_destroy", "pub_encoder_num_params",

@@ -1,4 +1,5 @@
 // C-ABI entry points (include/probunet_b200.h) for the primitive ops + shared host helpers.
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -9,6 +10,8 @@ namespace pub {
 
 static thread_local std::string g_err;
 unsigned long long g_launch_count = 0;
+int g_opt_conv_halo = -1;
+long long* g_halo_trace = nullptr;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -83,6 +86,20 @@ extern "C" {
 const char* pub_last_error(void) { return g_err.c_str(); }
 int pub_version(void) { return 100; }
 unsigned long long pub_launch_count(void) { return g_launch_count; }
+
+int pub_debug_option(const char* name, int value) {
+  PUB_REQUIRE(name != nullptr, "pub_debug_option: null name");
+  if (strcmp(name, "conv_halo") == 0) { g_opt_conv_halo = value; return 0; }
+  set_error("pub_debug_option: unknown option '%s'", name);
+  return -1;
+}
+
+int pub_debug_pointer(const char* name, void* p) {
+  PUB_REQUIRE(name != nullptr, "pub_debug_pointer: null name");
+  if (strcmp(name, "halo_trace") == 0) { g_halo_trace = (long long*)p; return 0; }
+  set_error("pub_debug_pointer: unknown name '%s'", name);
+  return -1;
+}
 
 int pub_conv2d_forward(const pub_conv_args* a, pub_stream_t s) {
   PUB_REQUIRE(a && a->x0 && a->w && a->y, "pub_conv2d_forward: null argument");

@@ -16,6 +16,8 @@
 // tcgen05.commit releases stages and publishes the accumulator.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -183,6 +185,21 @@ struct TcConvArgs {
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// One lane of a CONVERGED warp (the CUTLASS idiom): the whole warp runs the issuing loop, so every descriptor is
+// computed once on the uniform datapath, and only the tcgen05 instruction itself is predicated.  Issuing from inside
+// `if (lane == 0)` instead makes the compiler treat all operands as per-thread values: ~60 dependent instructions
+// (R2UR, ELECT/BRA.U.ANY loops) per tap, measured at ~200 cycles per MMA -- the single issuing thread, not the
+// tensor pipe, was the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ------------------------------------------------------------------ forward / dgrad kernel
@@ -365,6 +382,327 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
           }
         }
       }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------ halo forward / dgrad kernel (3x3)
+// The per-tap TMA im2col above fetches every activation 9 times from L2 (one box per tap), which bounds all
+// layers with N <= 128 by L2 -> smem bandwidth (and by the TMA's rate of 64-byte rows for C = 32).  Here each
+// activation is fetched ONCE per tile: producer warps copy the (16+2) x (8+2) pixel halo of an 8-wide x 16-tall
+// output tile into shared memory as ordinary K-major swizzled rows
+//      A[halo pixel = hy*10 + hx][ROWB bytes of channels]       (SWIZZLE_128B for 128-byte rows, 64B for 64)
+// The M = 128 operand rows of a tile are 16 groups of 8 consecutive halo pixels, 10 pixels apart (SBO = 10 rows),
+// and a filter tap (dy, dx) is nothing but a start-address offset of ((dy+1)*10 + (dx+1)) rows: the nine taps of a
+// K block are nine descriptors over the same bytes.  The swizzle XOR is a function of the absolute smem address
+// (the descriptor's base-offset field carries the row phase of the shifted start), so rows keep their meaning
+// under any row shift.  [The unswizzled "plane" layout, where a shift is also just an offset, was measured at
+// ~200 cycles per MMA regardless of N -- SWIZZLE_NONE operand fetch is several times slower.]
+// Image borders are zero-filled by the producers (same padding).  Weights arrive by TMA (resident slab or a ring
+// of [tap][N][KC] tiles).
+//
+// Warp roles (320 threads): 0 = weight TMA, 1 = MMA issuer, 2..5 = epilogue, 6..9 = halo producers: a
+// cp.async (LDGSTS, zero-fill) pipeline HALO_LOOK K blocks deep -- no register staging.
+constexpr int HALO_W = 10, HALO_H = 18, HALO_PX = HALO_W * HALO_H;
+constexpr int HTHREADS = 320;
+constexpr int HALO_LOOK = 3;   // K blocks in flight per producer thread (A ring depth >= HALO_LOOK + 1)
+
+struct HaloArgs {
+  const void* x0; const void* x1; int ld0, ld1;   // pixel strides in elements
+  int c0, c1;
+  int B, H, W;
+  int tiles_x, tiles_y, m_tiles;
+  int BN, cout;
+  int astages, bstages, resident;
+  const float* bias;
+  const void* res; int ld_res;
+  const void* mask; int ld_mask;
+  void* y; int ldy;
+  int relu;
+  int no_base_offset; // bring-up switch (PUB_HALO_NOBASE): leave the descriptor base-offset field 0
+  long long* trace;   // optional event trace of CTA (0,0) (tools/halo_trace.py): [role][1024] clock64 stamps
+};
+
+// role r, event counter n: stamps clock64 into trace[r*1024 + n]
+#define HALO_TR(r, n)                                                                   \
+  do {                                                                                  \
+    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (n) < 1024) a.trace[(r) * 1024 + (n)++] = clock64(); \
+  } while (0)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int ROWB_, int ES>
+__global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmW, HaloArgs a) {
+  typedef typename std::conditional<ES == 2, bf16, float>::type T;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t ROWB = ROWB_;
+  constexpr int KC = ROWB_ / ES;                                   // channels per K block
+  constexpr int CPR = ROWB_ / 16;                                  // 16-byte chunks per row: 8 / 4
+  constexpr int LOGC = ROWB_ == 128 ? 3 : 2;
+  constexpr uint32_t LAYOUT = (ROWB_ == 128) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t A_STAGE = (HALO_PX * ROWB + 1023u) & ~1023u;  // 23552 / 12288 B (swizzle pattern aligned)
+  constexpr int NSLOT = (HALO_PX * CPR + 127) / 128;               // 16-byte vectors per producer thread: 12 / 6
+  const uint32_t B_BYTES = (uint32_t)a.BN * ROWB;
+
+  // warp index through a shuffle: provably warp-uniform, so the role branches and everything computed inside the
+  // MMA-issuer warp stay on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int cblk0 = a.c0 / KC, cblk = (a.c0 + a.c1) / KC;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wbase = base;   // resident slab [cb][tap] or ring of single (cb, tap) tiles
+  const uint32_t abase = base + (uint32_t)(a.resident ? cblk * 9 : a.bstages) * B_BYTES;
+
+  __shared__ __align__(8) uint64_t bars[4 * MAX_STAGES + 5];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[MAX_STAGES]);
+  const uint32_t bfull0 = smem_u32(&bars[2 * MAX_STAGES]), bempty0 = smem_u32(&bars[3 * MAX_STAGES]);
+  const uint32_t accfull0 = smem_u32(&bars[4 * MAX_STAGES]), accempty0 = smem_u32(&bars[4 * MAX_STAGES + 2]);
+  const uint32_t wbar = smem_u32(&bars[4 * MAX_STAGES + 4]);
+
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * a.BN) ncols <<= 1;
+  const int n0 = blockIdx.y * a.BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(afull0 + 8 * i, 128); mbar_init(aempty0 + 8 * i, 1);
+      mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1);
+    }
+    mbar_init(accfull0, 1); mbar_init(accfull0 + 8, 1);
+    mbar_init(accempty0, 4); mbar_init(accempty0 + 8, 4);
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmW);
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- weight TMA
+      if (a.resident) {
+        mbar_expect_tx(wbar, (uint32_t)(cblk * 9) * B_BYTES);
+        for (int cb = 0; cb < cblk; ++cb)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_3d(wbase + (uint32_t)(cb * 9 + tap) * B_BYTES, &tmW, wbar, cb * KC, n0, tap);
+      } else {
+        int slot = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x)
+          for (int cb = 0; cb < cblk; ++cb)
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(bempty0 + 8 * slot, phase ^ 1);
+              mbar_expect_tx(bfull0 + 8 * slot, B_BYTES);
+              tma_load_3d(wbase + (uint32_t)slot * B_BYTES, &tmW, bfull0 + 8 * slot, cb * KC, n0, tap);
+              if (++slot == a.bstages) { slot = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: the whole warp runs the loop converged, one elected lane issues (see elect_one)
+    const uint32_t idesc = make_idesc(128, a.BN, 0, 0, ES == 2 ? 1u : 2u);
+    const uint64_t adesc0 = make_desc(abase, 16, HALO_W * ROWB, LAYOUT);
+    const uint64_t bdesc0 = make_desc(wbase, 16, 8 * ROWB, LAYOUT);
+    const uint32_t bstep = B_BYTES >> 4;
+    if (a.resident) mbar_wait(wbar, 0);
+    int astage = 0; uint32_t aphase = 0;
+    int bslot = 0; uint32_t bphase = 0;
+    int it = 0;
+    int trn = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(accempty0 + 8 * buf, (uint32_t)(((it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      if (lane == 0) HALO_TR(1, trn);
+      const uint32_t dcol = tmem_base + (uint32_t)(buf * a.BN);
+      for (int cb = 0; cb < cblk; ++cb) {
+        mbar_wait(afull0 + 8 * astage, aphase);
+        tc_fence_after();
+        if (lane == 0) HALO_TR(1, trn);
+        // the swizzle XOR is a function of the absolute smem address, so a row shift of the start address needs no
+        // base-offset correction (setting (start >> 7) & 7 there gives wrong results -- measured)
+        const uint64_t ad_stage = adesc0 + (uint64_t)((uint32_t)astage * (A_STAGE >> 4));
+        uint64_t bd_cb = bdesc0 + (uint64_t)((uint32_t)(cb * 9) * bstep);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          uint64_t bd;
+          if (a.resident) {
+            bd = bd_cb + (uint64_t)((uint32_t)tap * bstep);
+          } else {
+            mbar_wait(bfull0 + 8 * bslot, bphase);
+            tc_fence_after();
+            bd = bdesc0 + (uint64_t)((uint32_t)bslot * bstep);
+          }
+          // tap (dy, dx): the operand starts (dy+1)*10 + (dx+1) rows into the halo tile
+          const uint64_t ad = ad_stage + (uint64_t)((uint32_t)((tap / 3) * HALO_W + tap % 3) * (ROWB >> 4));
+          const uint32_t first = (uint32_t)(cb | tap);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < (int)ROWB / 32; ++k)   // one MMA consumes 32 B of K; +32 B inside the swizzled row
+              umma<ES>(dcol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (first | (uint32_t)k) != 0u);
+            if (!a.resident) umma_commit(bempty0 + 8 * bslot);
+          }
+          __syncwarp();
+          if (!a.resident) { if (++bslot == a.bstages) { bslot = 0; bphase ^= 1; } }
+        }
+        if (elect_one()) umma_commit(aempty0 + 8 * astage);
+        __syncwarp();
+        if (lane == 0) HALO_TR(1, trn);
+        if (++astage == a.astages) { astage = 0; aphase ^= 1; }
+      }
+      if (elect_one()) umma_commit(accfull0 + 8 * buf);
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int xl = row & 7, yl = row >> 3;
+    int it = 0;
+    int trn = 0;
+    const bool trw = warp == 2 && lane == 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int tx = t % a.tiles_x; t /= a.tiles_x;
+      const int ty = t % a.tiles_y; t /= a.tiles_y;
+      const int64_t pix = ((int64_t)t * a.H + ty * 16 + yl) * a.W + tx * 8 + xl;
+      const int buf = it & 1;
+      mbar_wait(accfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      if (trw) HALO_TR(2, trn);
+      for (int cb = 0; cb < a.BN; cb += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.BN + cb), r);
+        if (cb + 32 >= a.BN) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
+        }
+        const int n = n0 + cb;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
+        }
+        if (a.res) {
+          const T* rp = (const T*)a.res + pix * a.ld_res + n;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            Vec8<T>::load(rp + g * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.mask) {
+          const T* mp = (const T*)a.mask + pix * a.ld_mask + n;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            Vec8<T>::load(mp + g * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
+          }
+        }
+        T* yp = (T*)a.y + pix * a.ldy + n;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = ES == 4 ? round_tf32(v[g * 8 + j]) : v[g * 8 + j];
+          Vec8<T>::store(yp + g * 8, f);
+        }
+      }
+      if (trw) HALO_TR(2, trn);
+    }
+  } else {
+    // ---------------- halo producers (128 threads)
+    const int ptid = threadIdx.x - 192;
+    // slot j of this thread: vector q = j*128 + ptid  ->  halo pixel q / CPR, 16-byte chunk q % CPR: a quarter warp
+    // copies 128 contiguous global bytes into one (ROWB = 128) or two (ROWB = 64) swizzled smem rows: coalesced
+    // and bank-conflict free.  Everything that does not depend on the tile is precomputed:
+    //   pixoff = hy*W + hx                       (pixels, relative to the halo origin)
+    //   meta   = swizzled smem offset in the stage [0,16) | border flags [16,21) | channel offset of the chunk [24,32)
+    //            flags: 1 top halo row, 2 bottom halo row, 4 left halo column, 8 right halo column, 16 unused slot
+    int32_t pixoff[NSLOT];
+    uint32_t meta[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+      const int q = j * 128 + ptid;
+      const int chunk = q & (CPR - 1), px = q >> LOGC;
+      const int hy = px / HALO_W, hx = px % HALO_W;
+      const uint32_t fl = (hy == 0 ? 1u : 0u) | (hy == HALO_H - 1 ? 2u : 0u) | (hx == 0 ? 4u : 0u) |
+                          (hx == HALO_W - 1 ? 8u : 0u) | (px < HALO_PX ? 0u : 16u);
+      const uint32_t rowoff = (uint32_t)px * ROWB;
+      // Swizzle<3,4,3> (128B) / Swizzle<2,4,3> (64B) on the byte offset (stage bases are 1024-byte aligned)
+      const uint32_t phase = (rowoff >> 7) & (ROWB_ == 128 ? 7u : 3u);
+      const uint32_t soff = rowoff + (((uint32_t)chunk ^ phase) << 4);
+      pixoff[j] = hy * a.W + hx;
+      meta[j] = soff | (fl << 16) | ((uint32_t)(chunk * (16 / ES)) << 24);
+    }
+    const int my_tiles = blockIdx.x < a.m_tiles ? (a.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_tiles * cblk;        // work items (tile, cb) in the order the MMA warp consumes them
+    int is_tile = blockIdx.x, is_cb = 0;      // next item to issue
+    int istage = 0; uint32_t iphase = 0;      // stage of the next item to issue
+    int pstage = 0;                           // stage of the next item to publish
+    int trn = 0;
+    auto issue_item = [&]() {
+      int t = is_tile;
+      const int tx = t % a.tiles_x; t /= a.tiles_x;
+      const int ty = t % a.tiles_y; t /= a.tiles_y;
+      const uint32_t edge = (ty == 0 ? 1u : 0u) | (ty == a.tiles_y - 1 ? 2u : 0u) | (tx == 0 ? 4u : 0u) |
+                            (tx == a.tiles_x - 1 ? 8u : 0u) | 16u;
+      const bool s1 = is_cb >= cblk0;
+      const int64_t ld = s1 ? a.ld1 : a.ld0;
+      const T* srcbase = s1 ? (const T*)a.x1 + (is_cb - cblk0) * KC : (const T*)a.x0 + is_cb * KC;
+      // halo origin (may lie outside the image for border tiles: never dereferenced there)
+      const T* origin = srcbase + (((int64_t)t * a.H + ty * 16 - 1) * a.W + tx * 8 - 1) * ld;
+      mbar_wait(aempty0 + 8 * istage, iphase ^ 1);
+      const uint32_t sb = abase + (uint32_t)istage * A_STAGE;
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) {
+        if (!((meta[j] >> 20) & 1u)) {
+          const bool ok = ((meta[j] >> 16) & edge) == 0u;
+          const T* ptr = ok ? origin + (int64_t)pixoff[j] * ld + (meta[j] >> 24) : srcbase;
+          cp_async16(sb + (meta[j] & 0xFFFFu), ptr, ok ? 16u : 0u);   // src-size 0: 16 bytes of zeros (same padding)
+        }
+      }
+      if (++istage == a.astages) { istage = 0; iphase ^= 1; }
+      if (++is_cb == cblk) { is_cb = 0; is_tile += gridDim.x; }
+    };
+    int issued = 0;
+#pragma unroll
+    for (int d = 0; d < HALO_LOOK; ++d) {
+      if (issued < total) { issue_item(); ++issued; }
+      cp_async_commit();
+    }
+    for (int i = 0; i < total; ++i) {
+      cp_async_wait<HALO_LOOK - 1>();   // this thread's copies of item i have landed
+      if (ptid == 0) HALO_TR(0, trn);
+      fence_proxy_async();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(afull0 + 8 * pstage);
+      if (++pstage == a.astages) pstage = 0;
+      if (ptid == 0) HALO_TR(0, trn);
+      if (issued < total) { issue_item(); ++issued; }
+      cp_async_commit();
+      if (ptid == 0) HALO_TR(0, trn);
     }
   }
   tc_fence_before();
@@ -608,9 +946,91 @@ bool conv_tc_supported(const ConvParams& p, int dtype) {
   return pick_patch(p.H, p.W, 128, tw, th, tb);
 }
 
+namespace {
+bool halo_enabled() {
+  if (g_opt_conv_halo < 0) { const char* e = getenv("PUB_CONV_HALO"); g_opt_conv_halo = (e && e[0] == '0') ? 0 : 1; }
+  return g_opt_conv_halo != 0;
+}
+int halo_nobase() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PUB_HALO_NOBASE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+// Which 3x3 layers take the halo kernel.  g_opt_conv_halo: 0 never, 1 (default) where it measured faster than the
+// per-tap kernel on B200 (tools/conv_ab.py, B = 64: profiles/r01_conv_ab_halo_vs_tap.txt), 2 wherever it is legal.
+// It wins where the per-tap kernel is bound by TMA rows / L2 re-reads of the activations (K blocks of 32 channels,
+// 64 -> 64) and where N = 256 keeps the tensor pipe busy; with a streamed (non-resident) weight ring and N <= 128
+// the per-tap kernel's wider stages are still ahead.
+bool conv_halo_ok(const ConvParams& p, int dtype) {
+  if (!halo_enabled() || p.ks != 3 || p.W % 8 || p.H % 16 || (dtype != PUB_BF16 && dtype != PUB_TF32)) return false;
+  if (g_opt_conv_halo == 2) return true;
+  const int cin = p.c0 + p.c1;
+  if (dtype == PUB_TF32) return cin >= 256 && p.cout >= 128;   // tf32 K blocks are 128-byte rows already: only the deep layers gain
+  return p.c0 % 64 != 0 || p.c1 % 64 != 0 || (cin == 64 && p.cout == 64) || (cin >= 256 && p.cout >= 256);
+}
+
+int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
+  const int cin = p.c0 + p.c1, es = esize(dtype);
+  const int KC = es == 4 ? 32 : ((p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32);
+  const int rowb = KC * es;
+  const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  HaloArgs a{};
+  a.x0 = p.x0; a.x1 = p.x1; a.ld0 = p.ld0; a.ld1 = p.ld1; a.c0 = p.c0; a.c1 = p.c1;
+  a.B = p.B; a.H = p.H; a.W = p.W;
+  a.tiles_x = p.W / 8; a.tiles_y = p.H / 16; a.m_tiles = p.B * a.tiles_x * a.tiles_y;
+  a.BN = pick_bn(p.cout); a.cout = p.cout;
+  a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.mask = p.mask; a.ld_mask = p.ld_mask;
+  a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
+  a.no_base_offset = halo_nobase();
+  a.trace = g_halo_trace;
+  const int n_tiles = p.cout / a.BN;
+  const int cblk = cin / KC;
+  const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);
+  const size_t wres_bytes = (size_t)cblk * 9 * b_bytes;
+  const bool small_tmem = 2 * a.BN <= 256;            // two CTAs per SM are possible
+  const size_t budget2 = 110 * 1024 - 2048, budget1 = 222 * 1024 - 2048;
+  const int min_a = HALO_LOOK + 1;
+  bool two;
+  if (small_tmem && wres_bytes + min_a * a_stage <= budget2) {
+    a.resident = 1; two = true;
+    a.astages = (int)((budget2 - wres_bytes) / a_stage);
+  } else if (wres_bytes + min_a * a_stage <= budget1) {
+    a.resident = 1; two = false;
+    a.astages = (int)((budget1 - wres_bytes) / a_stage);
+  } else {
+    a.resident = 0; two = false;
+    a.astages = min_a;
+    a.bstages = (int)((budget1 - a.astages * a_stage) / b_bytes);
+    if (a.bstages > MAX_STAGES) a.bstages = MAX_STAGES;
+    PUB_REQUIRE(a.bstages >= 2, "conv_halo: weight ring does not fit");
+  }
+  if (a.astages > 6) a.astages = 6;
+  const size_t smem = 1024 + (a.resident ? wres_bytes : (size_t)a.bstages * b_bytes) + (size_t)a.astages * a_stage;
+  int gx = (two ? 2 : 1) * num_sms() / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > a.m_tiles) gx = a.m_tiles;
+  CUtensorMap tmW;
+  PUB_TRY(make_weight_map(&tmW, p.w, es, cin, p.cout, 9, KC, a.BN, sw));
+  static bool attr = false;
+  if (!attr) {
+    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 2>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<64, 2>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 4>, 225 * 1024));
+    attr = true;
+  }
+  dim3 grid(gx, n_tiles);
+  if (es == 4) conv_halo_kernel<128, 4><<<grid, HTHREADS, smem, s>>>(tmW, a);
+  else if (rowb == 128) conv_halo_kernel<128, 2><<<grid, HTHREADS, smem, s>>>(tmW, a);
+  else conv_halo_kernel<64, 2><<<grid, HTHREADS, smem, s>>>(tmW, a);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
 int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
   PUB_REQUIRE(conv_tc_supported(p, dtype), "conv_tc: unsupported shape (c0=%d c1=%d cout=%d H=%d W=%d ks=%d dtype=%d)",
               p.c0, p.c1, p.cout, p.H, p.W, p.ks, dtype);
+  if (conv_halo_ok(p, dtype)) return conv_halo(p, dtype, s);
   const int cin = p.c0 + p.c1, es = esize(dtype);
   // channels per K block: bf16 -> 64 (128 B rows) when both sources allow it, else 32 (64 B rows); tf32 -> 32 (128 B rows)
   const int KC = es == 4 ? 32 : ((p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32);

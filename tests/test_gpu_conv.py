@@ -164,3 +164,36 @@ def test_first_layer_small_cin_kernels(dt, cin):
     torch.cuda.synchronize()
     assert rel_err(dw, wz.grad) < (1e-4 if dt == torch.float32 else 2e-3)
     assert rel_err(db, bz.grad) < (1e-4 if dt == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("mode", ["tc_bf16", "tc_tf32"])
+@pytest.mark.parametrize("case", [c for c in CASES if c[6] == 3 and c[1] % 16 == 0 and c[2] % 8 == 0 and c[3] % 32 == 0])
+def test_conv_halo_kernel_on_every_legal_shape(case, mode):
+    """By default only the shapes where it measured faster go to conv_halo_kernel (one halo load per tile, taps as
+    start-address offsets of the swizzled operand); force it on every legal 3x3 shape, residual + mask epilogue."""
+    N = _setup()
+    B, H, W, c0, c1, cout, ks = case
+    ndt = N.BF16 if mode == "tc_bf16" else N.TF32
+    cast = to_tf32 if mode == "tc_tf32" else (lambda t: t.to(torch.bfloat16))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x0 = cast(torch.randn(B, H, W, c0 + 32, device="cuda", generator=g))[..., :c0]
+    x1 = cast(torch.randn(B, H, W, c1, device="cuda", generator=g)) if c1 else None
+    w = torch.randn(cout, c0 + c1, ks, ks, device="cuda", generator=g) / ((c0 + c1) * ks * ks) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    res = cast(torch.randn(B, H, W, cout, device="cuda", generator=g))
+    mask = cast(torch.randn(B, H, W, cout, device="cuda", generator=g))
+    wp = N.pack_conv_weight(w, ndt)
+    wq = wp.float().permute(1, 2, 0).reshape(cout, c0 + c1, ks, ks)
+    xin = x0 if x1 is None else torch.cat([x0, x1], dim=3)
+    ref = _ref_conv(xin, wq, b, res=res, mask=mask)
+    out = {}
+    try:
+        for opt in (0, 2):
+            N.lib().pub_debug_option(b"conv_halo", opt)
+            out[opt] = N.conv2d_nhwc(x0, wp, b, x1=x1, ksize=ks, backend=N.BACKEND_TCGEN05, dtype=ndt, res=res, mask=mask)
+            torch.cuda.synchronize()
+    finally:
+        N.lib().pub_debug_option(b"conv_halo", 1)
+    tol = 1e-2 if mode == "tc_bf16" else 1e-3
+    assert rel_err(out[2].float(), ref) < tol and rel_err(out[0].float(), ref) < tol
+    assert rel_err(out[2].float(), out[0].float()) < 1e-2 * tol + (4e-3 if mode == "tc_bf16" else 2e-4)   # same products, other order
