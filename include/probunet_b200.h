@@ -192,6 +192,13 @@ int pub_ensemble_loss(const float* ens, const float* target, int B, int M, int C
 /* out/target [B,C,HW] -> loss[0] = mean |out-target|, loss[1+c] = per-variable means; dout optional */
 int pub_l1_loss(const float* out, const float* target, int B, int C, int HW, float* loss, float* dout,
                 void* workspace, size_t workspace_bytes, pub_stream_t s);
+/* WMSE + (1 - MS-SSIM) of the reference's active elbo (src/prob_unet_utils.py:270-305 + pytorch_msssim.ms_ssim,
+ * win_size 7, 5 levels): pred/target [B,C,H,W] f32 NCHW, H and W divisible by 16 and > 96.
+ * out3 = { lam*wmse + (1-lam)*(1-msssim), wmse, 1-msssim } (device); dpred (optional) = d out3[0] / d pred.
+ * data_range = clamp(max(target) - min(target), 1e-5) is reduced on the device (no host sync). */
+size_t pub_msssim_workspace(int B, int C, int H, int W);
+int pub_wmse_msssim_loss(const float* pred, const float* target, int B, int C, int H, int W, float alpha, float beta,
+                         float lam, float* out3, float* dpred, void* workspace, size_t workspace_bytes, pub_stream_t s);
 /* y[i] *= *scale (device scalar): applies the upstream gradient to a stored local gradient */
 int pub_scale_by_device_scalar(float* y, const float* scale, int64_t n, pub_stream_t s);
 

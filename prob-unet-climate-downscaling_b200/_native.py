@@ -76,7 +76,7 @@ EXPORTS = [
     "pub_unet_dropout_mask", "pub_encoder_create", "pub_encoder_destroy", "pub_encoder_num_params",
     "pub_encoder_workspace_bytes", "pub_encoder_forward", "pub_encoder_backward", "pub_rsample_forward",
     "pub_rsample_backward", "pub_kl_normal_forward", "pub_kl_normal_backward", "pub_fcomb_forward_workspace", "pub_fcomb_forward",
-    "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss",
+    "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss", "pub_msssim_workspace", "pub_wmse_msssim_loss",
     "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
 ]
 
@@ -93,7 +93,7 @@ def lib():
         l.pub_launch_count.restype = C.c_ulonglong
         for name in ("pub_conv2d_wgrad_workspace", "pub_unet_workspace_bytes", "pub_encoder_workspace_bytes",
                      "pub_fcomb_backward_workspace", "pub_loss_workspace", "pub_fcomb_forward_workspace",
-                     "pub_ensemble_metrics_workspace"):
+                     "pub_ensemble_metrics_workspace", "pub_msssim_workspace"):
             if hasattr(l, name):
                 getattr(l, name).restype = C.c_size_t
         _lib = l
@@ -709,9 +709,42 @@ def l1_loss(out, target):
     return _L1Fn.apply(out, target)
 
 
-def wmse_ms_ssim(pred, target, alpha, beta, lam, data_range):
-    raise NotImplementedError("the WMSE-MS-SSIM reconstruction term (src/prob_unet_utils.py:270-305) has no sm_100a "
-                              "kernel yet -- set model.loss_type to 'afcrps', 'crps' or 'l1' (see DESIGN.md, next rows)")
+class _MsSsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, alpha, beta, lam):
+        B, Cc, H, W = pred.shape
+        pred, target = pred.contiguous().float(), target.contiguous().float()
+        out3 = torch.empty(3, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty_like(pred) if ctx.needs_input_grad[0] else None
+        n = lib().pub_msssim_workspace(B, Cc, H, W)
+        if n == 0:
+            raise NativeError(f"pub_msssim_workspace: {lib().pub_last_error().decode()}")
+        ws = torch.empty(n, device=pred.device, dtype=torch.uint8)
+        check(lib().pub_wmse_msssim_loss(ptr(pred), ptr(target), B, Cc, H, W, C.c_float(alpha), C.c_float(beta),
+                                         C.c_float(lam), ptr(out3), ptr(dpred), ptr(ws), C.c_size_t(n), stream()),
+              "pub_wmse_msssim_loss")
+        ctx.dpred = dpred
+        loss, wmse, ms = out3[0], out3[1], out3[2]
+        ctx.mark_non_differentiable(wmse, ms)
+        return loss, wmse, ms
+
+    @staticmethod
+    def backward(ctx, dl, _dw, _dm):
+        d, ctx.dpred = ctx.dpred, None
+        if d is None:
+            return None, None, None, None, None
+        check(lib().pub_scale_by_device_scalar(ptr(d), ptr(dl.contiguous().float()), C.c_int64(d.numel()), stream()),
+              "pub_scale_by_device_scalar")
+        return d, None, None, None, None
+
+
+def wmse_ms_ssim(pred, target, alpha, beta, lam, data_range=None):
+    """-> (lam*WMSE + (1-lam)*(1-MS-SSIM), WMSE, 1-MS-SSIM) as 0-dim device tensors (src/prob_unet_utils.py:270-305).
+    data_range is always inferred from the target on the device, as the reference's elbo does."""
+    require_cuda(pred, target)
+    if data_range is not None:
+        raise NotImplementedError("an explicit data_range is never passed on the reference's hot path")
+    return _MsSsimFn.apply(pred, target, float(alpha), float(beta), float(lam))
 
 
 # ======================================================================================

@@ -231,3 +231,50 @@ def test_three_training_steps_track_the_oracle(golden):
     # differences, so the per-tensor parameter tolerance is looser than the loss tolerance
     worst = max(rel_err(p, leaves[n]) for n, p in m.named_parameters())
     assert worst < 5e-3, worst
+
+
+def test_wmse_msssim_kernel_value_and_gradient_match_the_oracle():
+    """csrc/msssim.cu vs oracle.wmse_ms_ssim_loss (restatement of src/prob_unet_utils.py:270-305 + pytorch_msssim 1.0.0)
+    and its autograd gradient, lam = 0 (the reference default: pure 1 - MS-SSIM) and lam = 0.3."""
+    import prob_unet_utils as U
+    g = torch.Generator().manual_seed(5)
+    y = torch.nn.functional.avg_pool2d(torch.randn(2, 3, 136, 136, generator=g), 9, 1)
+    y = y / y.std()
+    for lam in (0.0, 0.3):
+        x = (y + 0.3 * torch.randn(2, 3, 128, 128, generator=g)).requires_grad_(True)
+        ref = O.wmse_ms_ssim_loss(x, y, lam=lam)
+        ref[0].backward()
+        xc = x.detach().cuda().requires_grad_(True)
+        out = U.wmse_ms_ssim_loss(xc, y.cuda(), lam=lam, return_components=True)
+        (out[0] * 2.0).backward()
+        for a, b in zip(out, ref):
+            assert abs(float(a) - float(b)) < 1e-5 * abs(float(b)) + 1e-7, (lam, float(a), float(b))
+        assert rel_err(xc.grad, 2.0 * x.grad) < 1e-4, (lam, rel_err(xc.grad, 2.0 * x.grad))
+
+
+def test_elbo_msssim_variant_at_128(golden):
+    """The reference's ACTIVE elbo (src/prob_unet.py:229-267): 5-tuple return, golden values from the real reference
+    (with the restated ms_ssim stubbed in, tests/golden/make_golden.py) at 128x128, B = 1.
+
+    The de-zeroed seed-42 model predicts values of +-1900 against a target range of 18, so sigma_x^2 = E[x^2] - mu^2
+    cancels ~7 digits in fp32: the ORACLE's own 1 - MS-SSIM moves by 0.85 % when its input moves by 2.6e-6 (measured,
+    tools/_dbg_ms.py).  Tight parity of the kernel is therefore asserted on well-conditioned fields in
+    test_wmse_msssim_kernel_value_and_gradient_match_the_oracle; here the ill-conditioned term gets a 2 % band and
+    everything around it (total, KL, WMSE, arity, KL-driven gradients) the usual tolerance."""
+    x, y, eps = (torch.from_numpy(golden[k]).cuda() for k in ("B_x", "B_y", "B_eps"))
+    for name in ("fp32", "bf16"):
+        m = canonical_model(compute_dtype=name, loss_type="mse+ssim", device="cuda")
+        m.zero_grad(set_to_none=True)
+        total, recon, kl, wmse, ms = m.elbo(x, y, None, M=eps.shape[0], eps=eps)
+        total.backward()
+        assert isinstance(recon, list) and isinstance(wmse, float) and isinstance(ms, float)
+        assert abs(float(total) - float(golden["B_total"])) / abs(float(golden["B_total"])) < 5 * TOL[name]
+        assert rel_err(kl, golden["B_kl"]) < 5 * TOL[name]
+        assert abs(wmse - float(golden["B_wmse"])) / float(golden["B_wmse"]) < 5 * TOL[name]
+        assert abs(recon[0] - float(golden["B_recon"])) / abs(float(golden["B_recon"])) < 2e-2
+        assert abs(ms - float(golden["B_msssim_loss"])) / float(golden["B_msssim_loss"]) < 2e-2
+        names, norms = list(golden["grad_names"]), golden["B_gradnorm"]
+        kl_driven = [i for i, n in enumerate(names) if n.startswith("prior.")]
+        _check_grads(m, [names[i] for i in kl_driven], [norms[i] for i in kl_driven], GTOL[name])
+        for n, p_ in m.named_parameters():
+            assert p_.grad is not None and bool(torch.isfinite(p_.grad).all()), n
