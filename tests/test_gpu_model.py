@@ -278,3 +278,53 @@ def test_elbo_msssim_variant_at_128(golden):
         _check_grads(m, [names[i] for i in kl_driven], [norms[i] for i in kl_driven], GTOL[name])
         for n, p_ in m.named_parameters():
             assert p_.grad is not None and bool(torch.isfinite(p_.grad).all()), n
+
+
+def test_dispatcher_ops_match_the_module_path(setup, golden):
+    """torch.ops.probunet_b200.* (custom_ops.py) give the same numbers and gradients as the module path."""
+    import custom_ops  # noqa: F401
+    import _native as N
+    import torch.nn.functional as F
+    name, m, sd = setup
+    ops = torch.ops.probunet_b200
+    g = torch.Generator(device="cuda").manual_seed(4)
+    # conv (+ReLU) forward/backward vs F.conv2d
+    x = torch.randn(2, 32, 32, 32, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    w = (torch.randn(64, 32, 3, 3, device="cuda", generator=g) / 17).requires_grad_(True)
+    b = torch.randn(64, device="cuda", generator=g).requires_grad_(True)
+    y = ops.conv2d_nhwc(x, w, b, True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = w.detach().bfloat16().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, br, padding=1))
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_err(y.float().permute(0, 3, 1, 2), yr) < 1e-2
+    assert rel_err(x.grad.float().permute(0, 3, 1, 2), xr.grad) < 2e-2 and rel_err(w.grad, wr.grad) < 2e-2
+    assert rel_err(b.grad, br.grad) < 2e-2
+    # fcomb op == module call, including gradients wrt features and z
+    x_in, y_in, eps = _inputs(golden)
+    with torch.no_grad():
+        feat = m.unet(x_in)
+    z = torch.randn(3, 2, 32, device="cuda", generator=g)
+    params = [p for l in (m.fcomb.layers[0], m.fcomb.layers[2], m.fcomb.layers[4]) for p in (l.weight, l.bias)]
+    f1, z1 = feat.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    o1 = ops.fcomb(f1, z1, *params)
+    f2, z2 = feat.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    o2 = m.fcomb.forward_members(f2, z2)
+    assert rel_err(o1, o2) < 1e-6
+    go = torch.randn_like(o1)
+    g1 = torch.autograd.grad(o1, [f1, z1], go)
+    g2 = torch.autograd.grad(o2, [f2, z2], go)
+    assert rel_err(g1[0], g2[0]) < 1e-5 and rel_err(g1[1], g2[1]) < 1e-5
+    # losses + KL
+    ens = o2.detach().clone().requires_grad_(True)
+    l_op, _ = ops.ensemble_loss(ens, y_in, 0, 0.95)
+    l_op.backward()
+    ens2 = o2.detach().clone().requires_grad_(True)
+    l_mod = N.ensemble_loss(ens2, y_in, "afcrps", 0.95)
+    l_mod.backward()
+    assert abs(float(l_op) - float(l_mod)) < 1e-6 * abs(float(l_mod)) and rel_err(ens.grad, ens2.grad) < 1e-6
+    mq, sq, mp, sp = (torch.randn(4, 32, device="cuda", generator=g) for _ in range(4))
+    sq, sp = sq.abs() + 0.1, sp.abs() + 0.1
+    assert rel_err(ops.kl_normal(mq, sq, mp, sp), N.kl_normal(mq, sq, mp, sp)) < 1e-6

@@ -101,3 +101,21 @@ def test_two_rank_gloo_gradient_sync_and_gather(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_custom_ops_are_registered_with_fake_kernels():
+    """torch.ops.probunet_b200.* (custom_ops.py): schemas exist and shape propagation works without a GPU."""
+    import custom_ops
+    for name in custom_ops.OPS:
+        assert hasattr(torch.ops.probunet_b200, name), name
+    x = torch.empty(2, 16, 16, 32, device="meta", dtype=torch.bfloat16)
+    w = torch.empty(64, 32, 3, 3, device="meta")
+    assert torch.ops.probunet_b200.conv2d_nhwc(x, w, None, False).shape == (2, 16, 16, 64)
+    feat, z = torch.empty(2, 32, 16, 16, device="meta"), torch.empty(5, 2, 8, device="meta")
+    ws = [torch.empty(s, device="meta") for s in ((32, 40, 1, 1), (32,), (32, 32, 1, 1), (32,), (3, 32, 1, 1), (3,))]
+    assert torch.ops.probunet_b200.fcomb(feat, z, *ws).shape == (2, 5, 3, 16, 16)
+    loss, dens = torch.ops.probunet_b200.ensemble_loss(torch.empty(2, 5, 3, 8, 8, device="meta"),
+                                                       torch.empty(2, 3, 8, 8, device="meta"), 0, 0.95)
+    assert loss.shape == () and dens.shape == (2, 5, 3, 8, 8)
+    with pytest.raises(Exception):                       # no CPU kernel is registered
+        torch.ops.probunet_b200.kl_normal(*[torch.zeros(2, 4) for _ in range(4)])
