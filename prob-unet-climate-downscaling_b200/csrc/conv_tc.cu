@@ -435,6 +435,9 @@ struct HaloArgs {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {   // L1-allocating
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -720,6 +723,7 @@ struct TcWgradArgs {
   int tiles_total, tiles_per_split;
   int stages;
   float* part;            // [split][tap][cout][cin] f32
+  int box3;               // 3x3, 8x8 patches: x as three (8+2) x 8 boxes, dx taps as row offsets (see wgrad_tc_kernel)
 };
 
 constexpr int WG_P = 64;  // pixels (K) per stage
@@ -727,6 +731,14 @@ constexpr int WG_P = 64;  // pixels (K) per stage
 // ES = 2: bf16 operands, 32-channel groups are 64 B rows (SWIZZLE_64B, 8-row swizzle atoms), 16 pixels per MMA
 // ES = 4: tf32 operands, 32-channel groups are 128 B rows; MN-major tf32 only exists with the
 //         SWIZZLE_128B_BASE32B layout (32-byte chunks XOR row%4, 4-row atoms; TMA mode 128B_ATOM_32B), 8 pixels per MMA
+// box3 mode (3x3, H and W multiples of 8): the K tile is an 8 x 8 pixel patch and x arrives as THREE boxes of
+// (8+2) x 8 pixels, one per kernel row dy; the horizontal taps dx are start-address offsets of one row (64 / 128 B)
+// into the same box -- the swizzle XOR is a function of the absolute smem address, so a row shift keeps every byte
+// where the MMA expects it.  K groups (8 pixels = one patch row) are 10 rows apart (SBO), the three dy boxes are the
+// N groups of ONE MMA (LBO = box pitch): 3 MMAs of N = 96 per K step instead of 9 tap boxes.  The producer is bound
+// by the TMA's rate of rows (~4.7 cycles per 64-byte row): 304 rows per K tile instead of 640.
+constexpr int WG_BOXROWS = 80;   // (8 + 2) x 8 pixels
+
 template <int ES>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                             const __grid_constant__ CUtensorMap tmX1,
@@ -734,6 +746,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
                                                             TcWgradArgs a) {
   constexpr uint32_t ROW = 32 * ES;                      // bytes of one 32-channel row
   constexpr uint32_t WG_GROUP_BYTES = WG_P * ROW;        // one 32-channel x 64-pixel box
+  constexpr uint32_t WG_BOX_BYTES = (WG_BOXROWS * ROW + 1023u) & ~1023u;   // one dy box (box3 mode), pattern aligned
   constexpr uint32_t WG_A_BYTES = 4 * WG_GROUP_BYTES;
   constexpr uint32_t LAYOUT = ES == 2 ? 4u : 1u;         // SWIZZLE_64B : SWIZZLE_128B_BASE32B
   constexpr uint32_t SBO_WG = ES == 2 ? 8 * ROW : 4 * ROW;  // pitch between swizzle atoms along K (8 rows / 4 rows)
@@ -745,8 +758,9 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   __shared__ uint32_t tmem_slot;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]),
                  accbar = smem_u32(&bars[2 * MAX_STAGES]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t B_BYTES = (uint32_t)a.taps * WG_GROUP_BYTES;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const bool box3 = a.box3 != 0;
+  const uint32_t B_BYTES = box3 ? 3u * WG_BOX_BYTES : (uint32_t)a.taps * WG_GROUP_BYTES;
   const uint32_t STAGE_BYTES = WG_A_BYTES + B_BYTES;
   uint32_t ncols = 32;
   while ((int)ncols < a.taps * 32) ncols <<= 1;
@@ -785,46 +799,75 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
         const int b = r, y0 = ty * a.TH, x0 = tx * a.TW;
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + WG_A_BYTES;
-        mbar_expect_tx(full0 + 8 * stage, (uint32_t)(ngroups + a.taps) * WG_GROUP_BYTES);
-        for (int g = 0; g < ngroups; ++g)
-          tma_load_4d(sa + g * WG_GROUP_BYTES, &tmDY, full0 + 8 * stage, co0 + g * 32, x0, y0, b);
-        for (int tap = 0; tap < a.taps; ++tap)
-          tma_load_4d(sb + tap * WG_GROUP_BYTES, tmX, full0 + 8 * stage, cx, x0 + tap % a.ks - half,
-                      y0 + tap / a.ks - half, b);
+        if (box3) {
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)ngroups * WG_GROUP_BYTES + 3u * WG_BOXROWS * ROW);
+          for (int g = 0; g < ngroups; ++g)
+            tma_load_4d(sa + g * WG_GROUP_BYTES, &tmDY, full0 + 8 * stage, co0 + g * 32, x0, y0, b);
+          for (int dy = 0; dy < 3; ++dy)   // (8+2) x 8 pixels starting one pixel left of the patch, row y0 + dy - 1
+            tma_load_4d(sb + dy * WG_BOX_BYTES, tmX, full0 + 8 * stage, cx, x0 - 1, y0 + dy - 1, b);
+        } else {
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)(ngroups + a.taps) * WG_GROUP_BYTES);
+          for (int g = 0; g < ngroups; ++g)
+            tma_load_4d(sa + g * WG_GROUP_BYTES, &tmDY, full0 + 8 * stage, co0 + g * 32, x0, y0, b);
+          for (int tap = 0; tap < a.taps; ++tap)
+            tma_load_4d(sb + tap * WG_GROUP_BYTES, tmX, full0 + 8 * stage, cx, x0 + tap % a.ks - half,
+                        y0 + tap / a.ks - half, b);
+        }
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // A = dy  [K=64 px][M=128 co]  MN-major: 4 groups of 32 channels, LBO = group pitch
-      // B = x   [K=64 px][N = taps x 32 ci]  MN-major: the tap tiles lie WG_GROUP_BYTES apart in smem, which is
-      //         exactly the LBO stride between 32-element N groups -> all taps of a K step are ONE wide-N MMA
-      //         (two for 3x3: N = 160 + 128), landing side by side in TMEM.
-      const int n1 = a.taps > 5 ? 5 : a.taps, n2 = a.taps - n1;  // taps per MMA
-      const uint32_t idesc1 = make_idesc(128, n1 * 32, 1, 1, ES == 2 ? 1u : 2u);
-      const uint32_t idesc2 = n2 ? make_idesc(128, n2 * 32, 1, 1, ES == 2 ? 1u : 2u) : 0u;
-      const uint64_t adesc0 = make_desc(base, WG_GROUP_BYTES, SBO_WG, LAYOUT);
-      const uint64_t bdesc0 = make_desc(base + WG_A_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
-      const uint32_t sstep = STAGE_BYTES >> 4;
-      int stage = 0; uint32_t phase = 0;
-      bool first = true;
-      for (int t = t_beg; t < t_end; ++t) {
-        mbar_wait(full0 + 8 * stage, phase);
-        tc_fence_after();
-        const uint64_t ad = adesc0 + (uint64_t)(stage * sstep), bd = bdesc0 + (uint64_t)(stage * sstep);
+    // A = dy  [K=64 px][M=128 co]  MN-major: 4 groups of 32 channels, LBO = group pitch
+    // B = x   [K=64 px][N = taps x 32 ci]  MN-major.  9-box mode: the tap tiles lie WG_GROUP_BYTES apart in smem, which
+    //         is exactly the LBO stride between 32-element N groups -> all taps of a K step are ONE wide-N MMA (two
+    //         for 3x3: N = 160 + 128).  box3 mode: per dx one MMA of N = 96 whose N groups are the three dy boxes.
+    // The whole warp runs the loop converged; one elected lane issues (see elect_one).
+    const uint32_t fmt = ES == 2 ? 1u : 2u;
+    const int n1 = a.taps > 5 ? 5 : a.taps, n2 = a.taps - n1;  // taps per MMA (9-box mode)
+    const uint32_t idesc1 = make_idesc(128, n1 * 32, 1, 1, fmt);
+    const uint32_t idesc2 = n2 ? make_idesc(128, n2 * 32, 1, 1, fmt) : 0u;
+    const uint32_t idesc3 = make_idesc(128, 96, 1, 1, fmt);
+    const uint64_t adesc0 = make_desc(base, WG_GROUP_BYTES, SBO_WG, LAYOUT);
+    const uint64_t bdesc0 = make_desc(base + WG_A_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
+    // box3: K groups (patch rows) are 10 rows apart; in the tf32 layout an atom holds 4 rows, i.e. half a patch row
+    const uint64_t bdesc3 = make_desc(base + WG_A_BYTES + ROW, WG_BOX_BYTES, ES == 2 ? 10 * ROW : SBO_WG, LAYOUT);
+    const uint32_t sstep = STAGE_BYTES >> 4;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t first = 1;
+    for (int t = t_beg; t < t_end; ++t) {
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * sstep);
+      if (elect_one()) {
+        if (box3) {
+          const uint64_t bd = bdesc3 + (uint64_t)((uint32_t)stage * sstep);
 #pragma unroll
-        for (int k = 0; k < WG_P / KROWS; ++k) {
-          const uint32_t acc = (!first || k != 0) ? 1u : 0u;
-          const uint64_t ko = (uint64_t)(k * (KSTEP_BYTES >> 4));
-          umma<ES>(tmem_base, ad + ko, bd + ko, idesc1, acc);
-          if (n2) umma<ES>(tmem_base + (uint32_t)(n1 * 32), ad + ko, bd + ko + (uint64_t)((n1 * WG_GROUP_BYTES) >> 4), idesc2, acc);
+          for (int k = 0; k < WG_P / KROWS; ++k) {
+            const uint32_t acc = (!first || k != 0) ? 1u : 0u;
+            const uint64_t ka = (uint64_t)(k * (KSTEP_BYTES >> 4));
+            const uint64_t kb = (uint64_t)(k * ((KROWS / 8) * 10 * ROW >> 4));   // KROWS/8 patch rows per K step
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)   // columns [dx*96, dx*96+96) = taps (dy = 0..2, dx)
+              umma<ES>(tmem_base + (uint32_t)(dx * 96), ad + ka, bd + kb + (uint64_t)((dx - 1) * (int)(ROW >> 4)), idesc3, acc);
+          }
+        } else {
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)stage * sstep);
+#pragma unroll
+          for (int k = 0; k < WG_P / KROWS; ++k) {
+            const uint32_t acc = (!first || k != 0) ? 1u : 0u;
+            const uint64_t ko = (uint64_t)(k * (KSTEP_BYTES >> 4));
+            umma<ES>(tmem_base, ad + ko, bd + ko, idesc1, acc);
+            if (n2) umma<ES>(tmem_base + (uint32_t)(n1 * 32), ad + ko, bd + ko + (uint64_t)((n1 * WG_GROUP_BYTES) >> 4), idesc2, acc);
+          }
         }
-        first = false;
         umma_commit(empty0 + 8 * stage);
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(accbar);
+      __syncwarp();
+      first = 0;
+      if (++stage == a.stages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(accbar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
@@ -833,7 +876,9 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     tc_fence_after();
     for (int tap = 0; tap < a.taps; ++tap) {
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * 32), r);
+      // box3 keeps the accumulators ordered [dx][dy]
+      const int col = box3 ? ((tap % 3) * 3 + tap / 3) * 32 : tap * 32;
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       if (co < a.cout) {
         float* o = a.part + (((int64_t)split * a.taps + tap) * a.cout + co) * cin + ci0;
 #pragma unroll
@@ -1089,26 +1134,31 @@ int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
 
 // ------------------------------------------------------------------ wgrad host side
 namespace {
-struct WgPlan { int tw, th, tiles_x, tiles_y, tiles_total, nsplit, tiles_per_split, stages; size_t smem; };
+struct WgPlan { int tw, th, tiles_x, tiles_y, tiles_total, nsplit, tiles_per_split, stages, box3; size_t smem; };
 bool wgrad_plan(const WgradParams& p, int es, WgPlan& pl) {
   int tb;
-  if (!pick_patch(p.H, p.W, WG_P, pl.tw, pl.th, tb) || tb != 1) return false;
+  pl.box3 = g_opt_wgrad_box3 != 0 && p.ks == 3 && p.H % 8 == 0 && p.W % 8 == 0;
+  if (pl.box3) { pl.tw = 8; pl.th = 8; }
+  else if (!pick_patch(p.H, p.W, WG_P, pl.tw, pl.th, tb) || tb != 1) return false;
   pl.tiles_x = p.W / pl.tw; pl.tiles_y = p.H / pl.th;
   pl.tiles_total = p.B * pl.tiles_x * pl.tiles_y;
   const int cin = p.c0 + p.c1;
   const int ctas = (cin / 32) * cdiv(p.cout, 128);
-  int want = cdiv(2 * num_sms(), ctas);
+  const size_t group = (size_t)WG_P * 32 * es;
+  const size_t stage = pl.box3 ? 4 * group + 3 * align_up((size_t)WG_BOXROWS * 32 * es, 1024)
+                               : (4 + (size_t)p.ks * p.ks) * group;
+  // two CTAs per SM when three stages fit in half the shared memory (TMEM: 512 columns for 3x3 -> one CTA; the
+  // allocation blocks, so co-residency only helps 1x1), otherwise one CTA per SM and a single wave of splits
+  pl.stages = (int)((212 * 1024) / stage);
+  if (pl.stages > 6) pl.stages = 6;
+  pl.smem = pl.stages * stage + 1024;
+  int want = cdiv(num_sms(), ctas);
   if (want < 1) want = 1;
   int max_split = pl.tiles_total / 4;  // at least 4 K tiles per CTA
   if (max_split < 1) max_split = 1;
   if (want > max_split) want = max_split;
   pl.tiles_per_split = cdiv(pl.tiles_total, want);
   pl.nsplit = cdiv(pl.tiles_total, pl.tiles_per_split);
-  const size_t group = (size_t)WG_P * 32 * es;
-  const size_t stage = (4 + (size_t)p.ks * p.ks) * group;
-  pl.stages = (int)((212 * 1024) / stage);
-  if (pl.stages > 6) pl.stages = 6;
-  pl.smem = pl.stages * stage + 1024;
   return pl.stages >= 2;
 }
 }  // namespace
@@ -1142,12 +1192,13 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   a.c0 = p.c0; a.c1 = p.c1; a.cout = p.cout; a.taps = taps; a.ks = p.ks;
   a.B = p.B; a.H = p.H; a.W = p.W; a.TW = pl.tw; a.TH = pl.th;
   a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
-  a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages;
+  a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages; a.box3 = pl.box3;
   a.part = (float*)ws;
   const CUtensorMapSwizzle sw = es == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX0, tmX1, tmDY;
-  PUB_TRY(make_act_map(&tmX0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
-  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
+  const int xbw = pl.box3 ? pl.tw + 2 : pl.tw;   // box3: one (8+2) x 8 box per kernel row
+  PUB_TRY(make_act_map(&tmX0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, 32, xbw, pl.th, 1, sw));
+  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, 32, xbw, pl.th, 1, sw));
   else tmX1 = tmX0;
   PUB_TRY(make_act_map(&tmDY, p.dy, es, p.cout, p.ld_dy, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
   static bool attr = false;

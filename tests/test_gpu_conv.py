@@ -197,3 +197,34 @@ def test_conv_halo_kernel_on_every_legal_shape(case, mode):
     tol = 1e-2 if mode == "tc_bf16" else 1e-3
     assert rel_err(out[2].float(), ref) < tol and rel_err(out[0].float(), ref) < tol
     assert rel_err(out[2].float(), out[0].float()) < 1e-2 * tol + (4e-3 if mode == "tc_bf16" else 2e-4)   # same products, other order
+
+
+@pytest.mark.parametrize("mode", ["tc_bf16", "tc_tf32"])
+@pytest.mark.parametrize("case", [c for c in CASES if c[6] == 3 and c[1] % 8 == 0 and c[2] % 8 == 0 and c[3] % 32 == 0
+                                  and c[0] * c[1] * c[2] <= 4096 * 4])
+def test_wgrad_box3_and_tap_boxes_agree(case, mode):
+    """3x3 weight gradient: three (8+2) x 8 boxes with the horizontal taps as row offsets of the swizzled operand
+    (default) against the nine-tap-box producer and against autograd."""
+    N = _setup()
+    B, H, W, c0, c1, cout, ks = case
+    ndt = N.BF16 if mode == "tc_bf16" else N.TF32
+    cast = to_tf32 if mode == "tc_tf32" else (lambda t: t.to(torch.bfloat16))
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x0 = cast(torch.randn(B, H, W, c0, device="cuda", generator=g))
+    x1 = cast(torch.randn(B, H, W, c1, device="cuda", generator=g)) if c1 else None
+    dy = cast(torch.randn(B, H, W, cout, device="cuda", generator=g))
+    out = {}
+    try:
+        for opt in (0, 1):
+            N.lib().pub_debug_option(b"wgrad_box3", opt)
+            out[opt] = N.conv2d_wgrad_nhwc(x0, dy, ks, x1=x1, backend=N.BACKEND_TCGEN05, dtype=ndt)
+            torch.cuda.synchronize()
+    finally:
+        N.lib().pub_debug_option(b"wgrad_box3", 1)
+    xin = (x0 if x1 is None else torch.cat([x0, x1], dim=3)).float().permute(0, 3, 1, 2)
+    w = torch.zeros(cout, c0 + c1, ks, ks, device="cuda", requires_grad=True)
+    F.conv2d(xin, w, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    tol = 2e-3
+    assert rel_err(out[1][0], w.grad) < tol, f"box3 {mode} {case}: {rel_err(out[1][0], w.grad):.3e}"
+    assert rel_err(out[0][0], w.grad) < tol, f"tap boxes {mode} {case}: {rel_err(out[0][0], w.grad):.3e}"
+    assert rel_err(out[1][1], out[0][1]) < 1e-6
