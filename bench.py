@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--res", type=int, default=128)
     ap.add_argument("--members", type=int, default=15, help="ELBO ensemble size M (src/main.py:136)")
-    ap.add_argument("--loss", default="afcrps", choices=["afcrps", "crps", "l1"])
+    ap.add_argument("--loss", default="afcrps", choices=["afcrps", "crps", "l1", "mse+ssim"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--latent", type=int, default=32)
     ap.add_argument("--no-aux", action="store_true", help="skip the roofline sweep / cpu baseline / ensemble aux")
@@ -130,7 +130,7 @@ def cpu_train_steps(args, steps, warmup, batch):
     f = make_fields(batch, args.res, args.res, 16 if args.res >= 128 else 8, seed=1234 + 3)
     x, y = f["inputs"], f["targets"]
     g = torch.Generator().manual_seed(44)
-    M = args.members if args.loss != "l1" else 1
+    M = args.members if args.loss in ("afcrps", "crps") else 1
     enc, dec = O.unet_topology(cfg.unet())
     keys = [(b.key, b.cout, (b.up, b.down)) for b in enc + dec if not b.is_conv]
     times = []
@@ -143,7 +143,7 @@ def cpu_train_steps(args, steps, warmup, batch):
             h = h * 2 if up else (h // 2 if down else h)
             masks[k] = torch.rand(batch, c, h, h, generator=g) >= 0.1
         opt.zero_grad()
-        out = O.elbo(full, cfg, x, y, eps, "afcrps" if args.loss != "l1" else "l1", drop_masks=masks)
+        out = O.elbo(full, cfg, x, y, eps, args.loss, drop_masks=masks)
         out[0].backward()
         opt.step()
         _ = float(out[0])
@@ -173,7 +173,7 @@ def run_reference(args):
 
 
 def workload_config(args):
-    M = args.members if args.loss != "l1" else 1
+    M = args.members if args.loss in ("afcrps", "crps") else 1
     return {"workload": f"probunet_train_{args.res}x{args.res}_b{args.batch}pergpu_{args.loss}_M{M}_L{args.latent}",
             "reference_config": "BASELINE.json configs[2]: Prob U-Net training 128x128 batch 64 bf16, data-parallel",
             "per_gpu_batch": args.batch, "resolution": args.res, "elbo_members": M, "loss": args.loss,
@@ -261,7 +261,7 @@ def conv_roofline(model, B, H, pk, pk_kind):
     ach = tot_f / tot_t / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
             "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
-            "kernel": "conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM), all conv launches of one step",
+            "kernel": "conv_tc_kernel / conv_halo_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM), all conv launches of one step",
             "how": "each distinct conv launch of the step replayed alone through the C ABI with CUDA events on the "
                    "launching stream, L2 flushed (256 MiB write) before every timed launch, median of 3; "
                    "achieved = sum(count*2*B*H*W*Cin*Cout*k*k) / sum(count*time)",
@@ -291,7 +291,7 @@ def run_b200(args):
     pk, pk_kind = peaks()
 
     B, R = args.batch, args.res
-    M = args.members if args.loss != "l1" else 1
+    M = args.members if args.loss in ("afcrps", "crps") else 1
     model = canonical_model(latent_dim=args.latent, loss_type=args.loss, compute_dtype=args.dtype, device="cuda")
     model.train()                                      # dropout on, as the reference trains
     N.manual_seed(1000 + rank)
@@ -303,7 +303,7 @@ def run_b200(args):
 
     def step_device(xd, yd):
         opt.zero_grad(set_to_none=True)
-        out = model.elbo(xd, yd, None, M=M) if args.loss != "l1" else model.elbo(xd, yd, None)
+        out = model.elbo(xd, yd, None, M=M) if args.loss in ("afcrps", "crps") else model.elbo(xd, yd, None)
         out[0].backward()
         opt.step()
         return out[0]
@@ -362,7 +362,7 @@ def run_b200(args):
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": 1e3 * cpu_enqueue,
         "clocks": clocks,
         "model_tflops_per_gpu": value / world * gflop / 1e3,
-        "final_loss": float(loss),
+        "final_loss": float(loss.detach()),
         "grad_sync": {"collectives_per_step": sync.calls // max(1, (max(args.warmup, 3) + 2 * args.steps)),
                       "bytes_per_step": sync.bytes // max(1, (max(args.warmup, 3) + 2 * args.steps)), "world": world},
     }
@@ -372,6 +372,15 @@ def run_b200(args):
             model.eval()
             roof, detail = conv_roofline(model, B, R, pk, pk_kind)
             roof["share_of_step"] = roof["conv_time_per_step_ms"] / line["ms_per_step"]
+            # DRAM traffic of the same kernel family over one step, from the committed ncu launch list
+            # (profiles/r01b_launches_step.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed)
+            try:
+                fam = json.load(open(os.path.join(ROOT, "profiles", "r01b_launches_step_family.json")))["conv_family"]
+                roof["traffic"] = fam["dram_bytes"]
+                roof["traffic_source"] = ("profiles/r01b_launches_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                          f"{fam['launches']} conv-family launches of one step; ncu share of step {fam['share_of_step']:.3f})")
+            except Exception:
+                pass
             line["roofline"] = roof
             line["roofline_detail_top"] = sorted(detail, key=lambda d: -d["us"] * d["count"])[:8]
         except Exception as ex:  # never lose the headline line

@@ -2,6 +2,8 @@
 // This is the PARITY path (fp32 rel-err <= 1e-4 vs the reference) and the fallback for the
 // shapes the tcgen05 kernels do not take (Cin = 3/6 first layers).  Replaces F.conv2d at
 // src/networks.py:89 / src/prob_unet.py:41-46 and convolution_backward's weight gradient.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -311,6 +313,39 @@ __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restri
   dw[o] = accumulate ? dw[o] + s : s;
 }
 
+// split-K reduction of dW AND the final reduction of the bias-gradient column sums in one launch
+// (blocks [0, nbw): wgrad_reduce_kernel's work; blocks [nbw, ...): colsum_final_kernel's, one warp per channel)
+__global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ part, float* __restrict__ dw,
+                                                           int nsplit, int taps, int cout, int cin, int nbw,
+                                                           const float* __restrict__ bpart, int nchunk,
+                                                           float* __restrict__ dbias, int accumulate) {
+  if ((int)blockIdx.x < nbw) {
+    const int64_t n = (int64_t)taps * cout * cin;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    int k = 0;
+    for (; k + 8 <= nsplit; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(part + (int64_t)(k + j) * n + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; k < nsplit; ++k) s += __ldg(part + (int64_t)k * n + i);
+    const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
+    const int64_t o = ((int64_t)co * cin + ci) * taps + tap;  // OIHW with (ky,kx) == tap
+    dw[o] = accumulate ? dw[o] + s : s;
+  } else {
+    const int c = ((int)blockIdx.x - nbw) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= cout) return;
+    double s = 0.0;
+    for (int k = lane; k < nchunk; k += 32) s += (double)bpart[(int64_t)k * cout + c];
+    s = warp_sum_d(s);
+    if (lane == 0) dbias[c] = accumulate ? dbias[c] + (float)s : (float)s;
+  }
+}
+
 // Weight gradient of the Cin <= 8 first layers (3 / 6 input variables): lane = output channel, the 9 x CIN
 // accumulators live in registers, x values are warp-uniform broadcast loads (only the CIN real channels), the
 // image border is handled by zeroing dy per tap (the clamped x load is always a finite real pixel).  Two pixels
@@ -334,6 +369,15 @@ __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, flo
   const int64_t per_warp = (pend - pbeg + 7) / 8;
   const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
   int x = (int)(wbeg % p.W), y = (int)((wbeg / p.W) % p.H), b = (int)(wbeg / ((int64_t)p.W * p.H));
+  // The kernel is issue-bound on address arithmetic, not on memory: per tap only a select (border -> centre pixel,
+  // whose contribution is then zeroed through dy), one 64-bit add and the load remain; the nine tap offsets and the
+  // border tests are hoisted.
+  int tapoff[9];   // elements; |offset| <= (W + 1) * ld0
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int tt = t < taps ? t : 0;
+    tapoff[t] = ((tt / p.ks - half) * p.W + (tt % p.ks - half)) * p.ld0;
+  }
   constexpr int UNR = CIN <= 3 ? 2 : 1;  // pixels in flight (register budget: 9*CIN accumulators + UNR*9*CIN inputs)
   for (int64_t m = wbeg; m < wend; m += UNR) {
     float g[UNR], xv[UNR][9][CIN];
@@ -342,13 +386,15 @@ __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, flo
     for (int u = 0; u < UNR; ++u) {
       const bool live = m + u < wend;
       g[u] = (live && co < p.cout) ? to_f<T>(dy[(m + u) * p.ld_dy + co]) : 0.f;
+      const T* xc = x0 + (((int64_t)b * p.H + y) * p.W + x) * p.ld0;       // centre pixel (always valid)
+      const bool top = y == 0, bot = y == p.H - 1, lef = x == 0, rig = x == p.W - 1;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const int tt = t < taps ? t : 0;
-        const int yy = y + tt / p.ks - half, xx = x + tt % p.ks - half;
-        ok[u][t] = live && t < taps && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-        const int yc = min(max(yy, 0), p.H - 1), xc = min(max(xx, 0), p.W - 1);
-        PixLoad<T, CIN>::load(x0 + (((int64_t)b * p.H + yc) * p.W + xc) * p.ld0, xv[u][t]);
+        // (dy, dx) of tap t for ks = 3; for ks = 1 only t = 0 is live and it is the centre
+        const int ty = p.ks == 3 ? t / 3 - 1 : 0, tx = p.ks == 3 ? t % 3 - 1 : 0;
+        const bool oob = (ty < 0 && top) || (ty > 0 && bot) || (tx < 0 && lef) || (tx > 0 && rig);
+        ok[u][t] = live && t < taps && !oob;
+        PixLoad<T, CIN>::load(xc + (oob ? 0 : tapoff[t]), xv[u][t]);
       }
       if (live) { if (++x == p.W) { x = 0; if (++y == p.H) { y = 0; if (m + u + 1 < M) ++b; } } }
     }
@@ -456,6 +502,31 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
+constexpr int PACK_MAX = 96;
+struct PackTable { PackEntry e[PACK_MAX]; int start[PACK_MAX + 1]; int n; };   // start: element offsets / 256 (blocks)
+
+// one CTA = 256 consecutive elements of one entry (entries are padded to whole CTAs)
+template <typename T>
+__global__ void pack_weights_batched_kernel(const __grid_constant__ PackTable t, int rtf32) {
+  int lo = 0, hi = t.n;                       // largest k with start[k] <= blockIdx.x
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (t.start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid; }
+  const PackEntry& e = t.e[lo];
+  const int taps = e.ks * e.ks;
+  const int64_t n = (int64_t)taps * e.cout * e.cin;
+  const int64_t i = (int64_t)(blockIdx.x - t.start[lo]) * 256 + threadIdx.x;
+  if (i >= n) return;
+  T* out = (T*)e.out;
+  if (!e.tflip) {  // out[tap][co][ci]
+    const int ci = (int)(i % e.cin), co = (int)((i / e.cin) % e.cout), tap = (int)(i / ((int64_t)e.cin * e.cout));
+    const float v = e.w[((int64_t)co * e.cin + ci) * taps + tap];
+    out[i] = from_f<T>(rtf32 ? round_tf32_f(v) : v);
+  } else {  // out[tap][ci][co] = w[co][ci][mirror(tap)]
+    const int co = (int)(i % e.cout), ci = (int)((i / e.cout) % e.cin), tap = (int)(i / ((int64_t)e.cin * e.cout));
+    const float v = e.w[((int64_t)co * e.cin + ci) * taps + (taps - 1 - tap)];
+    out[i] = from_f<T>(rtf32 ? round_tf32_f(v) : v);
+  }
+}
+
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
                                     T* __restrict__ y, int ldy, int B, int64_t HW) {
@@ -542,10 +613,21 @@ size_t wgrad_simt_workspace(const WgradParams& p) {
   return align_up(a, 256) + align_up(b, 256);
 }
 
+int wgrad_finish(const float* part, float* dw, int nsplit, int taps, int cout, int cin, const float* bpart, int nchunk,
+                 float* dbias, int accumulate, cudaStream_t s) {
+  const int64_t n = (int64_t)taps * cout * cin;
+  const int nbw = cdiv(n, 128), nbb = dbias ? cdiv(cout, 4) : 0;
+  wgrad_finish_kernel<<<nbw + nbb, 128, 0, s>>>(part, dw, nsplit, taps, cout, cin, nbw, bpart, nchunk, dbias, accumulate);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out == nullptr: partial sums only (part[chunk][C]); returns the chunk count through *nchunk_out
 int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, float* out, int accumulate,
-           cudaStream_t s) {
+           cudaStream_t s, int* nchunk_out) {
   const int rows = 1024;
   const int nchunk = cdiv(M, rows);
+  if (nchunk_out) *nchunk_out = nchunk;
   if (C % 8 == 0 && ld % 8 == 0 && C <= 2048 && (((uintptr_t)x) & 31) == 0) {
     const size_t smem = (size_t)(256 / (C / 8)) * (C / 8) * 8 * sizeof(float);
     if (dtype == PUB_BF16) colsum_vec_kernel<bf16><<<nchunk, 256, smem, s>>>((const bf16*)x, ld, C, M, rows, part);
@@ -556,6 +638,7 @@ int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, floa
     else colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)x, ld, C, M, rows, part);
   }
   PUB_LAUNCH_CHECK();
+  if (!out) return 0;
   colsum_final_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(part, nchunk, C, out, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
@@ -592,12 +675,10 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
   }
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
-  PUB_TRY(wgrad_reduce(part, p.dw, nsplit, taps, p.cout, cin, accumulate, s));
-  if (p.dbias) {
-    float* bpart = (float*)((char*)ws + align_up((size_t)nsplit * n * sizeof(float), 256));
-    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, p.dbias, accumulate, s));
-  }
-  return 0;
+  float* bpart = (float*)((char*)ws + align_up((size_t)nsplit * n * sizeof(float), 256));
+  int nchunk = 0;
+  if (p.dbias) PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, nullptr, 0, s, &nchunk));
+  return wgrad_finish(part, p.dw, nsplit, taps, p.cout, cin, bpart, nchunk, p.dbias, accumulate, s);
 }
 
 int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype, int tflip, cudaStream_t s) {
@@ -605,6 +686,25 @@ int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype,
   if (dtype == PUB_BF16) pack_weight_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(w, (bf16*)out, cout, cin, ks, tflip, 0);
   else pack_weight_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(w, (float*)out, cout, cin, ks, tflip, dtype == PUB_TF32);
   PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int pack_weights_batched(const PackEntry* e, int n, int dtype, cudaStream_t s) {
+  for (int b0 = 0; b0 < n; b0 += PACK_MAX) {
+    PackTable t;
+    t.n = std::min(PACK_MAX, n - b0);
+    int blocks = 0;
+    for (int k = 0; k < t.n; ++k) {
+      t.e[k] = e[b0 + k];
+      t.start[k] = blocks;
+      blocks += cdiv((int64_t)e[b0 + k].ks * e[b0 + k].ks * e[b0 + k].cout * e[b0 + k].cin, 256);
+    }
+    t.start[t.n] = blocks;
+    if (blocks == 0) continue;
+    if (dtype == PUB_BF16) pack_weights_batched_kernel<bf16><<<blocks, 256, 0, s>>>(t, 0);
+    else pack_weights_batched_kernel<float><<<blocks, 256, 0, s>>>(t, dtype == PUB_TF32);
+    PUB_LAUNCH_CHECK();
+  }
   return 0;
 }
 

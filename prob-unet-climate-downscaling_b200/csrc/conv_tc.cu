@@ -1212,12 +1212,10 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   else wgrad_tc_kernel<4><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
-  PUB_TRY(wgrad_reduce(a.part, p.dw, pl.nsplit, taps, p.cout, cin, accumulate, s));
-  if (p.dbias) {
-    float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * n * sizeof(float), 256));
-    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, p.dbias, accumulate, s));
-  }
-  return 0;
+  float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * n * sizeof(float), 256));
+  int nchunk = 0;
+  if (p.dbias) PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, nullptr, 0, s, &nchunk));
+  return wgrad_finish(a.part, p.dw, pl.nsplit, taps, p.cout, cin, bpart, nchunk, p.dbias, accumulate, s);
 }
 
 }  // namespace pub

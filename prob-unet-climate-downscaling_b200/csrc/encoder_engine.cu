@@ -26,7 +26,8 @@ struct EPlan {
   std::vector<void*> pooled;  // per stage (index 0 unused)
   std::vector<int> ch, hh, ww;  // per conv output
   float *gap, *ls, *dgap, *dls;
-  void *wpack, *ga, *gb, *wg_ws;
+  std::vector<void*> wp;      // packed weights per conv (forward OR mirrored layout)
+  void *ga, *gb, *wg_ws;
   size_t wg_ws_bytes, total;
 };
 
@@ -35,7 +36,7 @@ int build(const pub_encoder* e, int B, int H, int W, void* base, size_t cap, EPl
   const size_t es = dtype_size(e->dtype);
   pl.B = B; pl.H = H; pl.W = W; pl.es = es;
   pl.x_in = ar.take((size_t)B * H * W * 8 * es);
-  pl.act.clear(); pl.pooled.clear(); pl.ch.clear(); pl.hh.clear(); pl.ww.clear();
+  pl.act.clear(); pl.pooled.clear(); pl.ch.clear(); pl.hh.clear(); pl.ww.clear(); pl.wp.clear();
   int h = H, w = W, cin = e->in_ch;
   size_t max_act = (size_t)B * H * W * 8 * es, max_w = 0, max_wg = 0;
   for (size_t st = 0; st < e->filters.size(); ++st) {
@@ -50,6 +51,7 @@ int build(const pub_encoder* e, int B, int H, int W, void* base, size_t cap, EPl
     for (int k = 0; k < 3; ++k) {
       PUB_REQUIRE(f % 8 == 0, "encoder: filter counts must be multiples of 8");
       pl.act.push_back(ar.take((size_t)B * h * w * f * es));
+      pl.wp.push_back(ar.take((size_t)9 * f * cin * es));
       pl.ch.push_back(f); pl.hh.push_back(h); pl.ww.push_back(w);
       max_act = std::max(max_act, (size_t)B * h * w * std::max(f, cin) * es);
       max_w = std::max(max_w, (size_t)9 * f * std::max(cin, 8) * es);
@@ -66,7 +68,7 @@ int build(const pub_encoder* e, int B, int H, int W, void* base, size_t cap, EPl
   pl.ls = ar.take_n<float>((size_t)B * e->latent);
   pl.dgap = ar.take_n<float>((size_t)B * F);
   pl.dls = ar.take_n<float>((size_t)B * e->latent);
-  pl.wpack = ar.take(max_w);
+  (void)max_w;
   pl.ga = ar.take(max_act);
   pl.gb = ar.take(max_act);
   pl.wg_ws_bytes = max_wg;
@@ -161,6 +163,12 @@ int pub_encoder_forward(pub_encoder* e, int B, int H, int W, const float* x_nchw
   PUB_TRY(build(e, B, H, W, ws, ws_bytes, pl));
   const int dt = e->dtype;
   PUB_TRY(nchw_to_nhwc(x_nchw, cx, t_nchw, t_nchw ? ct : 0, pl.x_in, 8, B, H, W, dt, s));
+  {
+    std::vector<PackEntry> pe;
+    int ci = e->in_ch;
+    for (int k = 0; k < e->nconv; ++k) { pe.push_back({P[2 * k], pl.wp[k], pl.ch[k], ci, 3, 0}); ci = pl.ch[k]; }
+    PUB_TRY(pack_weights_batched(pe.data(), (int)pe.size(), dt, s));
+  }
   const void* cur = pl.x_in;
   int cin = e->in_ch, ld = 8, h = H, w = W;
   for (int k = 0; k < e->nconv; ++k) {
@@ -169,9 +177,8 @@ int pub_encoder_forward(pub_encoder* e, int B, int H, int W, const float* x_nchw
       PUB_TRY(maxpool2(cur, cin, pl.pooled[st], B, h, w, dt, s));
       cur = pl.pooled[st]; h /= 2; w /= 2;
     }
-    PUB_TRY(pack_weight(P[2 * k], pl.wpack, f, cin, 3, dt, 0, s));
     ConvParams c{};
-    c.x0 = cur; c.c0 = cin; c.ld0 = ld; c.w = pl.wpack; c.bias = P[2 * k + 1];
+    c.x0 = cur; c.c0 = cin; c.ld0 = ld; c.w = pl.wp[k]; c.bias = P[2 * k + 1];
     c.y = pl.act[k]; c.ldy = f; c.B = B; c.H = h; c.W = w; c.cout = f; c.ks = 3; c.relu = 1;
     PUB_TRY(conv_forward(c, dt, backend, s));
     cur = pl.act[k]; cin = f; ld = f;
@@ -197,6 +204,11 @@ int pub_encoder_backward(pub_encoder* e, int B, int H, int W, const float* dmu, 
   heads_bwd_kernel<<<32, 256, 0, s>>>(dmu, dsigma, pl.ls, pl.gap, hp[0], hp[2], B, F, L, pl.dls, hg[0], hg[1], hg[2],
                                       hg[3], pl.dgap);
   PUB_LAUNCH_CHECK();
+  {
+    std::vector<PackEntry> pe;
+    for (int k = 1; k < n; ++k) pe.push_back({P[2 * k], pl.wp[k], pl.ch[k], pl.ch[k - 1], 3, 1});
+    PUB_TRY(pack_weights_batched(pe.data(), (int)pe.size(), dt, s));
+  }
   void* ga = pl.ga;
   void* gb = pl.gb;
   PUB_TRY(global_mean_bwd(pl.dgap, pl.act[n - 1], F, B, (int64_t)pl.hh[n - 1] * pl.ww[n - 1], ga, dt, s));
@@ -212,9 +224,8 @@ int pub_encoder_backward(pub_encoder* e, int B, int H, int W, const float* dmu, 
     wp.B = B; wp.H = h; wp.W = w; wp.cout = f; wp.ks = 3;
     PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
     if (k == 0) break;
-    PUB_TRY(pack_weight(P[2 * k], pl.wpack, f, cin, 3, dt, 1, s));
     ConvParams c{};
-    c.x0 = ga; c.c0 = f; c.ld0 = f; c.w = pl.wpack; c.y = gb; c.ldy = cin; c.B = B; c.H = h; c.W = w; c.cout = cin; c.ks = 3;
+    c.x0 = ga; c.c0 = f; c.ld0 = f; c.w = pl.wp[k]; c.y = gb; c.ldy = cin; c.B = B; c.H = h; c.W = w; c.cout = cin; c.ks = 3;
     if (!pooled_in) { c.mask = pl.act[k - 1]; c.ld_mask = cin; }
     PUB_TRY(conv_forward(c, dt, backend, s));
     if (pooled_in) {

@@ -29,8 +29,15 @@ int conv_simt(const ConvParams& p, int dtype, cudaStream_t s);
 size_t wgrad_simt_workspace(const WgradParams& p);
 int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s);
 int wgrad_reduce(const float* part, float* dw, int nsplit, int taps, int cout, int cin, int accumulate, cudaStream_t s);
-int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, float* out, int accumulate, cudaStream_t s);
+int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, float* out, int accumulate, cudaStream_t s,
+           int* nchunk_out = nullptr);
+int wgrad_finish(const float* part, float* dw, int nsplit, int taps, int cout, int cin, const float* bpart, int nchunk,
+                 float* dbias, int accumulate, cudaStream_t s);
 int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype, int tflip, cudaStream_t s);
+// all weight tensors of a sub-network in ONE launch (a training step packs ~190 of them; one launch each cost
+// more in launch gaps than in work)
+struct PackEntry { const float* w; void* out; int cout, cin, ks, tflip; };
+int pack_weights_batched(const PackEntry* e, int n, int dtype, cudaStream_t s);
 int nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, int ldy, int B, int H, int W, int dtype,
                  cudaStream_t s);
 int nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, int dtype, int accumulate, cudaStream_t s);

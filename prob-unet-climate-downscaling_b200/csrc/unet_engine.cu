@@ -23,6 +23,7 @@ struct BlockPlan {
   int pidx;                 // first index into the param table
   // workspace buffers
   void *a0, *h, *a1, *out, *dx;
+  void *wp0, *wp1, *wps;    // packed weights of conv0 / conv1 / skip (plain conv: wp0), forward OR mirrored layout
   float *stats0, *coef0, *stats1, *coef1;
 };
 
@@ -53,7 +54,8 @@ struct Plan {
   void* dy_in;     // NHWC copy of dout
   void* dx_last;   // grad wrt last decoder block output
   // scratch
-  void *wpack, *gn_scratch, *skipbuf, *s1, *s2, *sadd, *gsum, *wg_ws;
+  void *wp_out;             // packed out_conv weights
+  void *gn_scratch, *skipbuf, *s1, *s2, *sadd, *gsum, *wg_ws;
   size_t wg_ws_bytes;
   size_t total;
 };
@@ -91,6 +93,7 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
       pidx += 2;
       b.out = ar.take(n_out * b.d.cout * es);
       b.dx = nullptr;
+      b.wp0 = ar.take((size_t)9 * b.d.cin * b.d.cout * es);
     } else {
       PUB_REQUIRE(b.d.cin % 8 == 0 && b.d.cout % 8 == 0, "unet plan: block channels must be multiples of 8");
       pidx += 9 + (b.d.has_skip_conv ? 2 : 0);
@@ -99,6 +102,9 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
       b.a1 = ar.take(n_out * b.d.cout * es);
       b.out = ar.take(n_out * b.d.cout * es);
       b.dx = ar.take(n_in * b.d.cin * es);
+      b.wp0 = ar.take((size_t)9 * b.d.cin * b.d.cout * es);
+      b.wp1 = ar.take((size_t)9 * b.d.cout * b.d.cout * es);
+      b.wps = b.d.has_skip_conv ? ar.take((size_t)b.d.cin * b.d.cout * es) : nullptr;
       b.stats0 = ar.take_n<float>((size_t)B * groups_of(b.d.cin) * 2);
       b.coef0 = ar.take_n<float>((size_t)B * b.d.cin * 2);
       b.stats1 = ar.take_n<float>((size_t)B * groups_of(b.d.cout) * 2);
@@ -137,7 +143,8 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
     max_wg = std::max(max_wg, wgrad_workspace(wp, u->dtype, PUB_BACKEND_AUTO));
     max_wg = std::max(max_wg, wgrad_simt_workspace(wp));
   }
-  pl.wpack = ar.take(max_w);
+  pl.wp_out = ar.take((size_t)9 * curC * u->out_ch * es);
+  (void)max_w;
   pl.gn_scratch = ar.take(max_gn * sizeof(float));
   pl.skipbuf = ar.take(max_act);
   pl.s1 = ar.take(max_act);
@@ -179,6 +186,22 @@ ConvParams conv_params(const void* x0, int c0, int ld0, const void* x1, int c1, 
   c.res = res; c.ld_res = ld_res; c.mask = nullptr; c.ld_mask = 0; c.y = y; c.ldy = ldy;
   c.B = B; c.H = H; c.W = W; c.cout = cout; c.ks = ks; c.relu = 0;
   return c;
+}
+
+// every conv weight of the network in one launch: forward layout [tap][co][ci] or the mirrored / transposed layout
+// of the data gradient
+int pack_all(const pub_unet* u, const Plan& pl, const float* const* P, int tflip, int dt, cudaStream_t s) {
+  std::vector<PackEntry> e;
+  for (const BlockPlan& b : pl.bp) {
+    const float* const* p = P + b.pidx;
+    if (b.d.is_conv) { e.push_back({p[0], b.wp0, b.d.cout, b.d.cin, 3, tflip}); continue; }
+    e.push_back({p[2], b.wp0, b.d.cout, b.d.cin, 3, tflip});
+    e.push_back({p[7], b.wp1, b.d.cout, b.d.cout, 3, tflip});
+    if (b.d.has_skip_conv) e.push_back({p[9], b.wps, b.d.cout, b.d.cin, 1, tflip});
+  }
+  const float* const* p = P + (u->nparams - 4);
+  e.push_back({p[2], pl.wp_out, u->out_ch, u->final_c, 3, tflip});
+  return pack_weights_batched(e.data(), (int)e.size(), dt, s);
 }
 
 // keep-mask of the engine's dropout stream, written in NCHW order (test hook)
@@ -245,6 +268,7 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
   const int dt = u->dtype;
   const float pdrop = training ? u->dropout : 0.f;
   PUB_TRY(nchw_to_nhwc(x_nchw, u->in_ch, nullptr, 0, pl.x_in, 8, B, H, W, dt, s));
+  PUB_TRY(pack_all(u, pl, P, 0, dt, s));
   for (size_t i = 0; i < pl.bp.size(); ++i) {
     BlockPlan& b = pl.bp[i];
     View v0 = src_view(pl, b.src0, 8);
@@ -252,8 +276,7 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
     View v1 = b.src1 >= 0 ? src_view(pl, b.src1, 0) : View{nullptr, 0, 0};
     const float* const* p = P + b.pidx;
     if (b.d.is_conv) {
-      PUB_TRY(pack_weight(p[0], pl.wpack, b.d.cout, b.d.cin, 3, dt, 0, s));
-      ConvParams c = conv_params(v0.p, b.c0, v0.ld, nullptr, 0, 0, pl.wpack, p[1], nullptr, 0, b.out, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+      ConvParams c = conv_params(v0.p, b.c0, v0.ld, nullptr, 0, 0, b.wp0, p[1], nullptr, 0, b.out, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
       PUB_TRY(conv_forward(c, dt, backend, s));
       continue;
     }
@@ -262,8 +285,7 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
     GnParams g0 = gn_params(pl, v0.p, b.c0, v0.ld, v1.p, b.c1, v1.ld, b.Hi, b.Wi, p[0], p[1], nullptr, mode, 0.f, 0, 0, b.stats0, b.coef0);
     PUB_TRY(gn_forward(g0, b.a0, dt, s));
     // h = conv0(a0) + bias
-    PUB_TRY(pack_weight(p[2], pl.wpack, b.d.cout, b.d.cin, 3, dt, 0, s));
-    ConvParams c0 = conv_params(b.a0, b.d.cin, b.d.cin, nullptr, 0, 0, pl.wpack, p[3], nullptr, 0, b.h, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+    ConvParams c0 = conv_params(b.a0, b.d.cin, b.d.cin, nullptr, 0, 0, b.wp0, p[3], nullptr, 0, b.h, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
     PUB_TRY(conv_forward(c0, dt, backend, s));
     // a1 = dropout(silu(shift + norm1(h) * (scale + 1)))
     GnParams g1 = gn_params(pl, b.h, b.d.cout, b.d.cout, nullptr, 0, 0, b.Ho, b.Wo, p[5], p[6], p[4], 0, pdrop, seed, (uint64_t)i, b.stats1, b.coef1);
@@ -271,8 +293,7 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
     // residual branch
     const void* res; int ld_res;
     if (b.d.has_skip_conv) {
-      PUB_TRY(pack_weight(p[9], pl.wpack, b.d.cout, b.d.cin, 1, dt, 0, s));
-      ConvParams cs = conv_params(v0.p, b.c0, v0.ld, v1.p, b.c1, v1.ld, pl.wpack, p[10], nullptr, 0, pl.skipbuf, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 1);
+      ConvParams cs = conv_params(v0.p, b.c0, v0.ld, v1.p, b.c1, v1.ld, b.wps, p[10], nullptr, 0, pl.skipbuf, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 1);
       PUB_TRY(conv_forward(cs, dt, backend, s));
       res = pl.skipbuf; ld_res = b.d.cout;
     } else if (mode) {
@@ -283,8 +304,7 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
       res = v0.p; ld_res = v0.ld;
     }
     // out = conv1(a1) + bias + residual
-    PUB_TRY(pack_weight(p[7], pl.wpack, b.d.cout, b.d.cout, 3, dt, 0, s));
-    ConvParams c1 = conv_params(b.a1, b.d.cout, b.d.cout, nullptr, 0, 0, pl.wpack, p[8], res, ld_res, b.out, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+    ConvParams c1 = conv_params(b.a1, b.d.cout, b.d.cout, nullptr, 0, 0, b.wp1, p[8], res, ld_res, b.out, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
     PUB_TRY(conv_forward(c1, dt, backend, s));
   }
   const BlockPlan& last = pl.bp.back();
@@ -292,9 +312,8 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
   const int fc = u->final_c;
   GnParams go = gn_params(pl, last.out, fc, fc, nullptr, 0, 0, H, W, p[0], p[1], nullptr, 0, 0.f, 0, 0, pl.stats_o, pl.coef_o);
   PUB_TRY(gn_forward(go, pl.a_out, dt, s));
-  PUB_TRY(pack_weight(p[2], pl.wpack, u->out_ch, fc, 3, dt, 0, s));
   void* y = out_nchw ? pl.y_out : out;
-  ConvParams co = conv_params(pl.a_out, fc, fc, nullptr, 0, 0, pl.wpack, p[3], nullptr, 0, y, u->out_ch, B, H, W, u->out_ch, 3);
+  ConvParams co = conv_params(pl.a_out, fc, fc, nullptr, 0, 0, pl.wp_out, p[3], nullptr, 0, y, u->out_ch, B, H, W, u->out_ch, 3);
   PUB_TRY(conv_forward(co, dt, backend, s));
   if (out_nchw) PUB_TRY(nhwc_to_nchw(pl.y_out, u->out_ch, u->out_ch, (float*)out, B, H, W, dt, 0, s));
   return 0;
@@ -316,6 +335,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
     PUB_TRY(nchw_to_nhwc((const float*)dout, u->out_ch, nullptr, 0, pl.dy_in, u->out_ch, B, H, W, dt, s));
     dy = pl.dy_in;
   }
+  PUB_TRY(pack_all(u, pl, P, 1, dt, s));
   const BlockPlan& last = pl.bp.back();
   {
     const float* const* p = P + (u->nparams - 4);
@@ -324,8 +344,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
     wp.x0 = pl.a_out; wp.c0 = fc; wp.ld0 = fc; wp.dy = dy; wp.ld_dy = u->out_ch; wp.dw = g[2]; wp.dbias = g[3];
     wp.B = B; wp.H = H; wp.W = W; wp.cout = u->out_ch; wp.ks = 3;
     PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
-    PUB_TRY(pack_weight(p[2], pl.wpack, u->out_ch, fc, 3, dt, 1, s));
-    ConvParams cd = conv_params(dy, u->out_ch, u->out_ch, nullptr, 0, 0, pl.wpack, nullptr, nullptr, 0, pl.s1, fc, B, H, W, fc, 3);
+    ConvParams cd = conv_params(dy, u->out_ch, u->out_ch, nullptr, 0, 0, pl.wp_out, nullptr, nullptr, 0, pl.s1, fc, B, H, W, fc, 3);
     PUB_TRY(conv_forward(cd, dt, backend, s));
     GnParams go = gn_params(pl, last.out, fc, fc, nullptr, 0, 0, H, W, p[0], p[1], nullptr, 0, 0.f, 0, 0, pl.stats_o, pl.coef_o);
     PUB_TRY(gn_backward(go, pl.s1, pl.dx_last, nullptr, 0, g[0], g[1], nullptr, dt, s));
@@ -358,8 +377,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
       if (dx_nchw) {
-        PUB_TRY(pack_weight(p[0], pl.wpack, b.d.cout, b.d.cin, 3, dt, 1, s));
-        ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, pl.wpack, nullptr, nullptr, 0, pl.s1, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 3);
+        ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, b.wp0, nullptr, nullptr, 0, pl.s1, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 3);
         PUB_TRY(conv_simt(cd, dt, s));
         PUB_TRY(nhwc_to_nchw(pl.s1, b.d.cin, b.d.cin, dx_nchw, B, H, W, dt, 0, s));
       }
@@ -374,8 +392,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.dy = gp; wp.ld_dy = gld; wp.dw = g[9]; wp.dbias = g[10];
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 1;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
-      PUB_TRY(pack_weight(p[9], pl.wpack, b.d.cout, b.d.cin, 1, dt, 1, s));
-      ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, pl.wpack, nullptr, nullptr, 0, pl.sadd, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 1);
+      ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, b.wps, nullptr, nullptr, 0, pl.sadd, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 1);
       PUB_TRY(conv_forward(cd, dt, backend, s));
       addp = pl.sadd; add_ld = b.d.cin;
     } else if (mode) {
@@ -390,8 +407,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.x0 = b.a1; wp.c0 = b.d.cout; wp.ld0 = b.d.cout; wp.dy = gp; wp.ld_dy = gld; wp.dw = g[7]; wp.dbias = g[8];
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
-      PUB_TRY(pack_weight(p[7], pl.wpack, b.d.cout, b.d.cout, 3, dt, 1, s));
-      ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, pl.wpack, nullptr, nullptr, 0, pl.s1, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+      ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, b.wp1, nullptr, nullptr, 0, pl.s1, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
       PUB_TRY(conv_forward(cd, dt, backend, s));
     }
     // ---- norm1 / FiLM / SiLU / dropout
@@ -403,8 +419,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.x0 = b.a0; wp.c0 = b.d.cin; wp.ld0 = b.d.cin; wp.dy = pl.s2; wp.ld_dy = b.d.cout; wp.dw = g[2]; wp.dbias = g[3];
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
-      PUB_TRY(pack_weight(p[2], pl.wpack, b.d.cout, b.d.cin, 3, dt, 1, s));
-      ConvParams cd = conv_params(pl.s2, b.d.cout, b.d.cout, nullptr, 0, 0, pl.wpack, nullptr, nullptr, 0, pl.s1, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 3);
+      ConvParams cd = conv_params(pl.s2, b.d.cout, b.d.cout, nullptr, 0, 0, b.wp0, nullptr, nullptr, 0, pl.s1, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 3);
       PUB_TRY(conv_forward(cd, dt, backend, s));
     }
     // ---- norm0 / SiLU / resample  (+ residual-branch gradient)
