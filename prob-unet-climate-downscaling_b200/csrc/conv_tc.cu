@@ -731,13 +731,14 @@ constexpr int WG_P = 64;  // pixels (K) per stage
 // ES = 2: bf16 operands, 32-channel groups are 64 B rows (SWIZZLE_64B, 8-row swizzle atoms), 16 pixels per MMA
 // ES = 4: tf32 operands, 32-channel groups are 128 B rows; MN-major tf32 only exists with the
 //         SWIZZLE_128B_BASE32B layout (32-byte chunks XOR row%4, 4-row atoms; TMA mode 128B_ATOM_32B), 8 pixels per MMA
-// box3 mode (3x3, H and W multiples of 8): the K tile is an 8 x 8 pixel patch and x arrives as THREE boxes of
-// (8+2) x 8 pixels, one per kernel row dy; the horizontal taps dx are start-address offsets of one row (64 / 128 B)
-// into the same box -- the swizzle XOR is a function of the absolute smem address, so a row shift keeps every byte
-// where the MMA expects it.  K groups (8 pixels = one patch row) are 10 rows apart (SBO), the three dy boxes are the
-// N groups of ONE MMA (LBO = box pitch): 3 MMAs of N = 96 per K step instead of 9 tap boxes.  The producer is bound
-// by the TMA's rate of rows (~4.7 cycles per 64-byte row): 304 rows per K tile instead of 640.
-constexpr int WG_BOXROWS = 80;   // (8 + 2) x 8 pixels
+// box3 mode (3x3, H and W multiples of 8): the K tile is an 8 x 8 pixel patch and x arrives as ONE box of
+// (8+2) x (8+2) pixels (its halo); every tap is a start-address offset of dy*10 + dx rows (64 / 128 B each) into the
+// same box -- the swizzle XOR is a function of the absolute smem address, so a row shift keeps every byte where the
+// MMA expects it.  K groups (8 pixels = one patch row) are 10 rows apart (SBO); the three vertical taps are the
+// N groups of ONE MMA, also 10 rows apart (LBO = SBO, overlapping reads): 3 MMAs of N = 96 per K step instead of 9
+// tap boxes.  The producer is bound by the TMA's rate of rows (~4.7 cycles per 64-byte row): 164 rows per K tile
+// (100 halo + 64 dy) instead of 640.
+constexpr int WG_BOXROWS = 100;   // (8 + 2) x (8 + 2) pixels
 
 template <int ES>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
                  accbar = smem_u32(&bars[2 * MAX_STAGES]);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const bool box3 = a.box3 != 0;
-  const uint32_t B_BYTES = box3 ? 3u * WG_BOX_BYTES : (uint32_t)a.taps * WG_GROUP_BYTES;
+  const uint32_t B_BYTES = box3 ? WG_BOX_BYTES : (uint32_t)a.taps * WG_GROUP_BYTES;
   const uint32_t STAGE_BYTES = WG_A_BYTES + B_BYTES;
   uint32_t ncols = 32;
   while ((int)ncols < a.taps * 32) ncols <<= 1;
@@ -800,11 +801,10 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + WG_A_BYTES;
         if (box3) {
-          mbar_expect_tx(full0 + 8 * stage, (uint32_t)ngroups * WG_GROUP_BYTES + 3u * WG_BOXROWS * ROW);
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)ngroups * WG_GROUP_BYTES + (uint32_t)WG_BOXROWS * ROW);
           for (int g = 0; g < ngroups; ++g)
             tma_load_4d(sa + g * WG_GROUP_BYTES, &tmDY, full0 + 8 * stage, co0 + g * 32, x0, y0, b);
-          for (int dy = 0; dy < 3; ++dy)   // (8+2) x 8 pixels starting one pixel left of the patch, row y0 + dy - 1
-            tma_load_4d(sb + dy * WG_BOX_BYTES, tmX, full0 + 8 * stage, cx, x0 - 1, y0 + dy - 1, b);
+          tma_load_4d(sb, tmX, full0 + 8 * stage, cx, x0 - 1, y0 - 1, b);   // the (8+2) x (8+2) halo of the patch
         } else {
           mbar_expect_tx(full0 + 8 * stage, (uint32_t)(ngroups + a.taps) * WG_GROUP_BYTES);
           for (int g = 0; g < ngroups; ++g)
@@ -829,8 +829,9 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     const uint32_t idesc3 = make_idesc(128, 96, 1, 1, fmt);
     const uint64_t adesc0 = make_desc(base, WG_GROUP_BYTES, SBO_WG, LAYOUT);
     const uint64_t bdesc0 = make_desc(base + WG_A_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
-    // box3: K groups (patch rows) are 10 rows apart; in the tf32 layout an atom holds 4 rows, i.e. half a patch row
-    const uint64_t bdesc3 = make_desc(base + WG_A_BYTES + ROW, WG_BOX_BYTES, ES == 2 ? 10 * ROW : SBO_WG, LAYOUT);
+    // box3: K groups (patch rows) and N groups (vertical taps) are both 10 rows apart; in the tf32 layout an atom holds
+    // 4 rows, i.e. half a patch row.  The descriptor starts at halo row 1 (tap dy = -1, dx = 0); dx adds -1/0/+1 rows.
+    const uint64_t bdesc3 = make_desc(base + WG_A_BYTES + ROW, 10 * ROW, ES == 2 ? 10 * ROW : SBO_WG, LAYOUT);
     const uint32_t sstep = STAGE_BYTES >> 4;
     int stage = 0; uint32_t phase = 0;
     uint32_t first = 1;
@@ -1145,7 +1146,7 @@ bool wgrad_plan(const WgradParams& p, int es, WgPlan& pl) {
   const int cin = p.c0 + p.c1;
   const int ctas = (cin / 32) * cdiv(p.cout, 128);
   const size_t group = (size_t)WG_P * 32 * es;
-  const size_t stage = pl.box3 ? 4 * group + 3 * align_up((size_t)WG_BOXROWS * 32 * es, 1024)
+  const size_t stage = pl.box3 ? 4 * group + align_up((size_t)WG_BOXROWS * 32 * es, 1024)
                                : (4 + (size_t)p.ks * p.ks) * group;
   // two CTAs per SM when three stages fit in half the shared memory (TMEM: 512 columns for 3x3 -> one CTA; the
   // allocation blocks, so co-residency only helps 1x1), otherwise one CTA per SM and a single wave of splits
@@ -1196,9 +1197,9 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   a.part = (float*)ws;
   const CUtensorMapSwizzle sw = es == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX0, tmX1, tmDY;
-  const int xbw = pl.box3 ? pl.tw + 2 : pl.tw;   // box3: one (8+2) x 8 box per kernel row
-  PUB_TRY(make_act_map(&tmX0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, 32, xbw, pl.th, 1, sw));
-  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, 32, xbw, pl.th, 1, sw));
+  const int xbw = pl.box3 ? pl.tw + 2 : pl.tw, xbh = pl.box3 ? pl.th + 2 : pl.th;   // box3: the patch plus its halo
+  PUB_TRY(make_act_map(&tmX0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, 32, xbw, xbh, 1, sw));
+  if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, 32, xbw, xbh, 1, sw));
   else tmX1 = tmX0;
   PUB_TRY(make_act_map(&tmDY, p.dy, es, p.cout, p.ld_dy, p.B, p.H, p.W, 32, pl.tw, pl.th, 1, sw));
   static bool attr = false;
