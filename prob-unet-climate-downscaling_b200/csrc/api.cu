@@ -12,6 +12,7 @@ static thread_local std::string g_err;
 unsigned long long g_launch_count = 0;
 int g_opt_conv_halo = -1;
 int g_opt_wgrad_box3 = 1;
+int g_opt_fcomb_fwd_mma = 1;
 long long* g_halo_trace = nullptr;
 
 void set_error(const char* fmt, ...) {
@@ -92,6 +93,7 @@ int pub_debug_option(const char* name, int value) {
   PUB_REQUIRE(name != nullptr, "pub_debug_option: null name");
   if (strcmp(name, "conv_halo") == 0) { g_opt_conv_halo = value; return 0; }
   if (strcmp(name, "wgrad_box3") == 0) { g_opt_wgrad_box3 = value; return 0; }
+  if (strcmp(name, "fcomb_fwd_mma") == 0) { g_opt_fcomb_fwd_mma = value; return 0; }
   set_error("pub_debug_option: unknown option '%s'", name);
   return -1;
 }

@@ -392,26 +392,23 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
 // ------------------------------------------------------------------ halo forward / dgrad kernel (3x3)
 // The per-tap TMA im2col above fetches every activation 9 times from L2 (one box per tap), which bounds all
 // layers with N <= 128 by L2 -> smem bandwidth (and by the TMA's rate of 64-byte rows for C = 32).  Here each
-// activation is fetched ONCE per tile: producer warps copy the (16+2) x (8+2) pixel halo of an 8-wide x 16-tall
-// output tile into shared memory as ordinary K-major swizzled rows
+// activation is fetched ONCE per tile: one TMA box per K block brings the (16+2) x (8+2) pixel halo of an 8-wide x
+// 16-tall output tile into shared memory as ordinary K-major swizzled rows
 //      A[halo pixel = hy*10 + hx][ROWB bytes of channels]       (SWIZZLE_128B for 128-byte rows, 64B for 64)
-// The M = 128 operand rows of a tile are 16 groups of 8 consecutive halo pixels, 10 pixels apart (SBO = 10 rows),
-// and a filter tap (dy, dx) is nothing but a start-address offset of ((dy+1)*10 + (dx+1)) rows: the nine taps of a
-// K block are nine descriptors over the same bytes.  The swizzle XOR is a function of the absolute smem address
-// (the descriptor's base-offset field carries the row phase of the shifted start), so rows keep their meaning
-// under any row shift.  [The unswizzled "plane" layout, where a shift is also just an offset, was measured at
-// ~200 cycles per MMA regardless of N -- SWIZZLE_NONE operand fetch is several times slower.]
-// Image borders are zero-filled by the producers (same padding).  Weights arrive by TMA (resident slab or a ring
-// of [tap][N][KC] tiles).
+// (out-of-image pixels are zero-filled by the TMA unit = same padding).  The M = 128 operand rows of a tile are 16
+// groups of 8 consecutive halo pixels, 10 pixels apart (SBO = 10 rows), and a filter tap (dy, dx) is nothing but a
+// start-address offset of ((dy+1)*10 + (dx+1)) rows: the nine taps of a K block are nine descriptors over the same
+// bytes.  The swizzle XOR is a function of the absolute smem address (descriptor base-offset field 0 -- setting the
+// row phase there gives wrong results, measured), so rows keep their meaning under any row shift.
+// Bring-up notes (tools/halo_trace.py, ncu): an unswizzled "plane" layout, where a shift is also just an offset, ran
+// at ~200 cycles per MMA; software producers (LDG + STS, then cp.async) were correct but their per-stage
+// fence.proxy.async lowers to MEMBAR.ALL.CTA, which waits for the prefetches in flight and serialises the pipeline.
 //
-// Warp roles (320 threads): 0 = weight TMA, 1 = MMA issuer, 2..5 = epilogue, 6..9 = halo producers: a
-// cp.async (LDGSTS, zero-fill) pipeline HALO_LOOK K blocks deep -- no register staging.
+// Warp roles (224 threads): 0 = halo + resident-weight TMA, 1 = MMA issuer, 2..5 = epilogue, 6 = weight-ring TMA.
 constexpr int HALO_W = 10, HALO_H = 18, HALO_PX = HALO_W * HALO_H;
-constexpr int HTHREADS = 320;
-constexpr int HALO_LOOK = 3;   // K blocks in flight per producer thread (A ring depth >= HALO_LOOK + 1)
+constexpr int HTHREADS = 224;
 
 struct HaloArgs {
-  const void* x0; const void* x1; int ld0, ld1;   // pixel strides in elements
   int c0, c1;
   int B, H, W;
   int tiles_x, tiles_y, m_tiles;
@@ -422,7 +419,6 @@ struct HaloArgs {
   const void* mask; int ld_mask;
   void* y; int ldy;
   int relu;
-  int no_base_offset; // bring-up switch (PUB_HALO_NOBASE): leave the descriptor base-offset field 0
   long long* trace;   // optional event trace of CTA (0,0) (tools/halo_trace.py): [role][1024] clock64 stamps
 };
 
@@ -432,28 +428,17 @@ struct HaloArgs {
     if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (n) < 1024) a.trace[(r) * 1024 + (n)++] = clock64(); \
   } while (0)
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {   // L1-allocating
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <int ROWB_, int ES>
-__global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmW, HaloArgs a) {
+__global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                             const __grid_constant__ CUtensorMap tmA1,
+                                                             const __grid_constant__ CUtensorMap tmW, HaloArgs a) {
   typedef typename std::conditional<ES == 2, bf16, float>::type T;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t ROWB = ROWB_;
   constexpr int KC = ROWB_ / ES;                                   // channels per K block
-  constexpr int CPR = ROWB_ / 16;                                  // 16-byte chunks per row: 8 / 4
-  constexpr int LOGC = ROWB_ == 128 ? 3 : 2;
   constexpr uint32_t LAYOUT = (ROWB_ == 128) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
-  constexpr uint32_t A_STAGE = (HALO_PX * ROWB + 1023u) & ~1023u;  // 23552 / 12288 B (swizzle pattern aligned)
-  constexpr int NSLOT = (HALO_PX * CPR + 127) / 128;               // 16-byte vectors per producer thread: 12 / 6
+  constexpr uint32_t A_TX = HALO_PX * ROWB;                        // bytes one halo box delivers
+  constexpr uint32_t A_STAGE = (A_TX + 1023u) & ~1023u;            // 23552 / 12288 B (swizzle pattern aligned)
   const uint32_t B_BYTES = (uint32_t)a.BN * ROWB;
 
   // warp index through a shuffle: provably warp-uniform, so the role branches and everything computed inside the
@@ -477,14 +462,16 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
-      mbar_init(afull0 + 8 * i, 128); mbar_init(aempty0 + 8 * i, 1);
+      mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1);
       mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1);
     }
     mbar_init(accfull0, 1); mbar_init(accfull0 + 8, 1);
     mbar_init(accempty0, 4); mbar_init(accempty0 + 8, 4);
     mbar_init(wbar, 1);
     fence_barrier_init();
+    prefetch_tmap(&tmA0);
     prefetch_tmap(&tmW);
+    if (a.c1) prefetch_tmap(&tmA1);
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), ncols);
   tc_fence_before();
@@ -494,23 +481,42 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- weight TMA
+      // ---------------- resident weights once, then one halo box per (tile, K block)
       if (a.resident) {
         mbar_expect_tx(wbar, (uint32_t)(cblk * 9) * B_BYTES);
         for (int cb = 0; cb < cblk; ++cb)
           for (int tap = 0; tap < 9; ++tap)
             tma_load_3d(wbase + (uint32_t)(cb * 9 + tap) * B_BYTES, &tmW, wbar, cb * KC, n0, tap);
-      } else {
-        int slot = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x)
-          for (int cb = 0; cb < cblk; ++cb)
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(bempty0 + 8 * slot, phase ^ 1);
-              mbar_expect_tx(bfull0 + 8 * slot, B_BYTES);
-              tma_load_3d(wbase + (uint32_t)slot * B_BYTES, &tmW, bfull0 + 8 * slot, cb * KC, n0, tap);
-              if (++slot == a.bstages) { slot = 0; phase ^= 1; }
-            }
       }
+      int stage = 0; uint32_t phase = 0;
+      int trn = 0;
+      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % a.tiles_x; t /= a.tiles_x;
+        const int ty = t % a.tiles_y; t /= a.tiles_y;
+        for (int cb = 0; cb < cblk; ++cb) {
+          mbar_wait(aempty0 + 8 * stage, phase ^ 1);
+          HALO_TR(0, trn);
+          mbar_expect_tx(afull0 + 8 * stage, A_TX);
+          const uint32_t sa = abase + (uint32_t)stage * A_STAGE;
+          if (cb < cblk0) tma_load_4d(sa, &tmA0, afull0 + 8 * stage, cb * KC, tx * 8 - 1, ty * 16 - 1, t);
+          else tma_load_4d(sa, &tmA1, afull0 + 8 * stage, (cb - cblk0) * KC, tx * 8 - 1, ty * 16 - 1, t);
+          if (++stage == a.astages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0 && !a.resident) {
+      // ---------------- weight ring: one [BN][KC] tile per (K block, tap), in the order the MMA warp consumes them
+      int slot = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x)
+        for (int cb = 0; cb < cblk; ++cb)
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bempty0 + 8 * slot, phase ^ 1);
+            mbar_expect_tx(bfull0 + 8 * slot, B_BYTES);
+            tma_load_3d(wbase + (uint32_t)slot * B_BYTES, &tmW, bfull0 + 8 * slot, cb * KC, n0, tap);
+            if (++slot == a.bstages) { slot = 0; phase ^= 1; }
+          }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: the whole warp runs the loop converged, one elected lane issues (see elect_one)
@@ -533,8 +539,6 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
         mbar_wait(afull0 + 8 * astage, aphase);
         tc_fence_after();
         if (lane == 0) HALO_TR(1, trn);
-        // the swizzle XOR is a function of the absolute smem address, so a row shift of the start address needs no
-        // base-offset correction (setting (start >> 7) & 7 there gives wrong results -- measured)
         const uint64_t ad_stage = adesc0 + (uint64_t)((uint32_t)astage * (A_STAGE >> 4));
         uint64_t bd_cb = bdesc0 + (uint64_t)((uint32_t)(cb * 9) * bstep);
 #pragma unroll
@@ -567,7 +571,7 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
       if (elect_one()) umma_commit(accfull0 + 8 * buf);
       __syncwarp();
     }
-  } else if (warp < 6) {
+  } else {
     // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -634,78 +638,6 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
         }
       }
       if (trw) HALO_TR(2, trn);
-    }
-  } else {
-    // ---------------- halo producers (128 threads)
-    const int ptid = threadIdx.x - 192;
-    // slot j of this thread: vector q = j*128 + ptid  ->  halo pixel q / CPR, 16-byte chunk q % CPR: a quarter warp
-    // copies 128 contiguous global bytes into one (ROWB = 128) or two (ROWB = 64) swizzled smem rows: coalesced
-    // and bank-conflict free.  Everything that does not depend on the tile is precomputed:
-    //   pixoff = hy*W + hx                       (pixels, relative to the halo origin)
-    //   meta   = swizzled smem offset in the stage [0,16) | border flags [16,21) | channel offset of the chunk [24,32)
-    //            flags: 1 top halo row, 2 bottom halo row, 4 left halo column, 8 right halo column, 16 unused slot
-    int32_t pixoff[NSLOT];
-    uint32_t meta[NSLOT];
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) {
-      const int q = j * 128 + ptid;
-      const int chunk = q & (CPR - 1), px = q >> LOGC;
-      const int hy = px / HALO_W, hx = px % HALO_W;
-      const uint32_t fl = (hy == 0 ? 1u : 0u) | (hy == HALO_H - 1 ? 2u : 0u) | (hx == 0 ? 4u : 0u) |
-                          (hx == HALO_W - 1 ? 8u : 0u) | (px < HALO_PX ? 0u : 16u);
-      const uint32_t rowoff = (uint32_t)px * ROWB;
-      // Swizzle<3,4,3> (128B) / Swizzle<2,4,3> (64B) on the byte offset (stage bases are 1024-byte aligned)
-      const uint32_t phase = (rowoff >> 7) & (ROWB_ == 128 ? 7u : 3u);
-      const uint32_t soff = rowoff + (((uint32_t)chunk ^ phase) << 4);
-      pixoff[j] = hy * a.W + hx;
-      meta[j] = soff | (fl << 16) | ((uint32_t)(chunk * (16 / ES)) << 24);
-    }
-    const int my_tiles = blockIdx.x < a.m_tiles ? (a.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int total = my_tiles * cblk;        // work items (tile, cb) in the order the MMA warp consumes them
-    int is_tile = blockIdx.x, is_cb = 0;      // next item to issue
-    int istage = 0; uint32_t iphase = 0;      // stage of the next item to issue
-    int pstage = 0;                           // stage of the next item to publish
-    int trn = 0;
-    auto issue_item = [&]() {
-      int t = is_tile;
-      const int tx = t % a.tiles_x; t /= a.tiles_x;
-      const int ty = t % a.tiles_y; t /= a.tiles_y;
-      const uint32_t edge = (ty == 0 ? 1u : 0u) | (ty == a.tiles_y - 1 ? 2u : 0u) | (tx == 0 ? 4u : 0u) |
-                            (tx == a.tiles_x - 1 ? 8u : 0u) | 16u;
-      const bool s1 = is_cb >= cblk0;
-      const int64_t ld = s1 ? a.ld1 : a.ld0;
-      const T* srcbase = s1 ? (const T*)a.x1 + (is_cb - cblk0) * KC : (const T*)a.x0 + is_cb * KC;
-      // halo origin (may lie outside the image for border tiles: never dereferenced there)
-      const T* origin = srcbase + (((int64_t)t * a.H + ty * 16 - 1) * a.W + tx * 8 - 1) * ld;
-      mbar_wait(aempty0 + 8 * istage, iphase ^ 1);
-      const uint32_t sb = abase + (uint32_t)istage * A_STAGE;
-#pragma unroll
-      for (int j = 0; j < NSLOT; ++j) {
-        if (!((meta[j] >> 20) & 1u)) {
-          const bool ok = ((meta[j] >> 16) & edge) == 0u;
-          const T* ptr = ok ? origin + (int64_t)pixoff[j] * ld + (meta[j] >> 24) : srcbase;
-          cp_async16(sb + (meta[j] & 0xFFFFu), ptr, ok ? 16u : 0u);   // src-size 0: 16 bytes of zeros (same padding)
-        }
-      }
-      if (++istage == a.astages) { istage = 0; iphase ^= 1; }
-      if (++is_cb == cblk) { is_cb = 0; is_tile += gridDim.x; }
-    };
-    int issued = 0;
-#pragma unroll
-    for (int d = 0; d < HALO_LOOK; ++d) {
-      if (issued < total) { issue_item(); ++issued; }
-      cp_async_commit();
-    }
-    for (int i = 0; i < total; ++i) {
-      cp_async_wait<HALO_LOOK - 1>();   // this thread's copies of item i have landed
-      if (ptid == 0) HALO_TR(0, trn);
-      fence_proxy_async();              // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      mbar_arrive(afull0 + 8 * pstage);
-      if (++pstage == a.astages) pstage = 0;
-      if (ptid == 0) HALO_TR(0, trn);
-      if (issued < total) { issue_item(); ++issued; }
-      cp_async_commit();
-      if (ptid == 0) HALO_TR(0, trn);
     }
   }
   tc_fence_before();
@@ -997,22 +929,12 @@ bool halo_enabled() {
   if (g_opt_conv_halo < 0) { const char* e = getenv("PUB_CONV_HALO"); g_opt_conv_halo = (e && e[0] == '0') ? 0 : 1; }
   return g_opt_conv_halo != 0;
 }
-int halo_nobase() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("PUB_HALO_NOBASE"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
-}
-// Which 3x3 layers take the halo kernel.  g_opt_conv_halo: 0 never, 1 (default) where it measured faster than the
-// per-tap kernel on B200 (tools/conv_ab.py, B = 64: profiles/r01_conv_ab_halo_vs_tap.txt), 2 wherever it is legal.
-// It wins where the per-tap kernel is bound by TMA rows / L2 re-reads of the activations (K blocks of 32 channels,
-// 64 -> 64) and where N = 256 keeps the tensor pipe busy; with a streamed (non-resident) weight ring and N <= 128
-// the per-tap kernel's wider stages are still ahead.
+// Which 3x3 layers take the halo kernel: every shape it can tile (8 x 16 output tiles) -- with the halo arriving as
+// one TMA box it measured faster than the per-tap kernel on all 36 bf16 and 10 tf32 layer shapes of a training step
+// (tools/conv_ab.py, B = 64: profiles/r01b_conv_ab_halo_vs_tap.txt; sum over a step 8.7 -> 5.9 ms and 2.8 -> 2.3 ms).
+// g_opt_conv_halo = 0 (pub_debug_option "conv_halo") routes everything through the per-tap kernel for A/B runs.
 bool conv_halo_ok(const ConvParams& p, int dtype) {
-  if (!halo_enabled() || p.ks != 3 || p.W % 8 || p.H % 16 || (dtype != PUB_BF16 && dtype != PUB_TF32)) return false;
-  if (g_opt_conv_halo == 2) return true;
-  const int cin = p.c0 + p.c1;
-  if (dtype == PUB_TF32) return cin >= 256 && p.cout >= 128;   // tf32 K blocks are 128-byte rows already: only the deep layers gain
-  return p.c0 % 64 != 0 || p.c1 % 64 != 0 || (cin == 64 && p.cout == 64) || (cin >= 256 && p.cout >= 256);
+  return halo_enabled() && p.ks == 3 && p.W % 8 == 0 && p.H % 16 == 0 && (dtype == PUB_BF16 || dtype == PUB_TF32);
 }
 
 int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
@@ -1021,13 +943,12 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   const int rowb = KC * es;
   const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   HaloArgs a{};
-  a.x0 = p.x0; a.x1 = p.x1; a.ld0 = p.ld0; a.ld1 = p.ld1; a.c0 = p.c0; a.c1 = p.c1;
+  a.c0 = p.c0; a.c1 = p.c1;
   a.B = p.B; a.H = p.H; a.W = p.W;
   a.tiles_x = p.W / 8; a.tiles_y = p.H / 16; a.m_tiles = p.B * a.tiles_x * a.tiles_y;
   a.BN = pick_bn(p.cout); a.cout = p.cout;
   a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.mask = p.mask; a.ld_mask = p.ld_mask;
   a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
-  a.no_base_offset = halo_nobase();
   a.trace = g_halo_trace;
   const int n_tiles = p.cout / a.BN;
   const int cblk = cin / KC;
@@ -1035,7 +956,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   const size_t wres_bytes = (size_t)cblk * 9 * b_bytes;
   const bool small_tmem = 2 * a.BN <= 256;            // two CTAs per SM are possible
   const size_t budget2 = 110 * 1024 - 2048, budget1 = 222 * 1024 - 2048;
-  const int min_a = HALO_LOOK + 1;
+  const int min_a = 3;
   bool two;
   if (small_tmem && wres_bytes + min_a * a_stage <= budget2) {
     a.resident = 1; two = true;
@@ -1045,7 +966,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
     a.astages = (int)((budget1 - wres_bytes) / a_stage);
   } else {
     a.resident = 0; two = false;
-    a.astages = min_a;
+    a.astages = 4;
     a.bstages = (int)((budget1 - a.astages * a_stage) / b_bytes);
     if (a.bstages > MAX_STAGES) a.bstages = MAX_STAGES;
     PUB_REQUIRE(a.bstages >= 2, "conv_halo: weight ring does not fit");
@@ -1055,7 +976,10 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   int gx = (two ? 2 : 1) * num_sms() / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
-  CUtensorMap tmW;
+  CUtensorMap tmA0, tmA1, tmW;
+  PUB_TRY(make_act_map(&tmA0, p.x0, es, p.c0, p.ld0, p.B, p.H, p.W, KC, HALO_W, HALO_H, 1, sw));
+  if (p.c1) PUB_TRY(make_act_map(&tmA1, p.x1, es, p.c1, p.ld1, p.B, p.H, p.W, KC, HALO_W, HALO_H, 1, sw));
+  else tmA1 = tmA0;
   PUB_TRY(make_weight_map(&tmW, p.w, es, cin, p.cout, 9, KC, a.BN, sw));
   static bool attr = false;
   if (!attr) {
@@ -1065,9 +989,9 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
     attr = true;
   }
   dim3 grid(gx, n_tiles);
-  if (es == 4) conv_halo_kernel<128, 4><<<grid, HTHREADS, smem, s>>>(tmW, a);
-  else if (rowb == 128) conv_halo_kernel<128, 2><<<grid, HTHREADS, smem, s>>>(tmW, a);
-  else conv_halo_kernel<64, 2><<<grid, HTHREADS, smem, s>>>(tmW, a);
+  if (es == 4) conv_halo_kernel<128, 4><<<grid, HTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  else if (rowb == 128) conv_halo_kernel<128, 2><<<grid, HTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  else conv_halo_kernel<64, 2><<<grid, HTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
   PUB_LAUNCH_CHECK();
   return 0;
 }

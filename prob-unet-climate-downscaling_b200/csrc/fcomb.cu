@@ -572,6 +572,139 @@ __global__ void __launch_bounds__(NT, 2) fcomb_bwd_mma_kernel(FcombDev a, const 
     o[2 * F * F + CO * F + F + 4 + i] = (Sacc[i] + Sacc[a.M * F + i]) + (Sacc[2 * a.M * F + i] + Sacc[3 * a.M * F + i]);
 }
 
+// ---- forward, bf16 path on the same warp-level MMAs: base = f W0f^T once per 16-pixel tile, then per member
+// h1 -> h2 -> out stay in registers as fragments.  Plain bf16 operands moved the afCRPS by 0.8 % at the seed-42
+// init (the member-to-member spread is small against |pred|, so operand rounding shows up in |x_j - x_k|), which is
+// outside the 0.5 % budget: every f32 operand is therefore split into two bf16 terms x = hi + lo (lo = x - hi,
+// ~16 mantissa bits together) and each product is three MMAs (lo*hi + hi*lo + hi*hi, f32 accumulate; lo*lo ~ 2^-18
+// is dropped).  54 MMAs per (member, 16 pixels) instead of ~2100 FMAs + 280 shared loads per (member, pixel).
+struct FcombFwdMmaSmem {
+  __nv_bfloat16 w1[2][F][WP];    // [hi|lo][k][j]
+  __nv_bfloat16 w0[2][F][WP];    // [hi|lo][j][i]
+  __nv_bfloat16 w2[2][8][WP];    // [hi|lo][c][k], rows >= CO are zero
+  float b1[F];
+  float b2[4];
+};
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// accumulator fragments of a 16 x 32 tile -> hi and lo A fragments
+__device__ __forceinline__ void c_to_a_split(const float (&c)[4][4], uint32_t (&ah)[2][4], uint32_t (&al)[2][4]) {
+  float lo[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) lo[q][r] = c[q][r] - __bfloat162float(__float2bfloat16_rn(c[q][r]));
+  c_to_a(c, ah);
+  c_to_a(lo, al);
+}
+
+__global__ void __launch_bounds__(NT) fcomb_fwd_mma_kernel(FcombDev a, float* __restrict__ out) {
+  __shared__ __align__(16) FcombFwdMmaSmem s;
+  extern __shared__ float dyn[];  // zbs[M][F]
+  float* zbs = dyn;
+  const int b = blockIdx.y, HW = a.H * a.W, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < F * F; i += NT) {
+    const int r = i / F, c = i % F;
+    split_bf16(a.w1[i], s.w1[0][r][c], s.w1[1][r][c]);
+    split_bf16(a.w0[r * (F + a.L) + c], s.w0[0][r][c], s.w0[1][r][c]);
+  }
+  for (int i = tid; i < 8 * F; i += NT) {
+    const int c = i / F, k = i % F;
+    split_bf16(c < CO ? a.w2[c * F + k] : 0.f, s.w2[0][c][k], s.w2[1][c][k]);
+  }
+  if (tid < F) s.b1[tid] = a.b1[tid];
+  if (tid < 4) s.b2[tid] = tid < CO ? a.b2[tid] : 0.f;
+  for (int i = tid; i < a.M * F; i += NT) zbs[i] = a.zb[((int64_t)(i / F) * a.B + b) * F + i % F];
+  __syncthreads();
+  const float bo0 = s.b2[2 * t < CO ? 2 * t : 3], bo1 = s.b2[2 * t + 1 < CO ? 2 * t + 1 : 3];
+  const int ntile = (HW + 15) / 16;
+  for (int tile = blockIdx.x * 4 + warp; tile < ntile; tile += gridDim.x * 4) {
+    const int p0 = tile * 16 + g, p1 = p0 + 8;
+    const bool v0 = p0 < HW, v1 = p1 < HW;
+    uint32_t fa[2][4];   // the features ARE bf16: no low term
+    {
+      const bf16* f0 = (const bf16*)a.feat + ((int64_t)b * HW + p0) * F;
+      const bf16* f1 = (const bf16*)a.feat + ((int64_t)b * HW + p1) * F;
+#pragma unroll
+      for (int sk = 0; sk < 2; ++sk) {
+        fa[sk][0] = v0 ? *reinterpret_cast<const uint32_t*>(f0 + 16 * sk + 2 * t) : 0u;
+        fa[sk][1] = v1 ? *reinterpret_cast<const uint32_t*>(f1 + 16 * sk + 2 * t) : 0u;
+        fa[sk][2] = v0 ? *reinterpret_cast<const uint32_t*>(f0 + 16 * sk + 8 + 2 * t) : 0u;
+        fa[sk][3] = v1 ? *reinterpret_cast<const uint32_t*>(f1 + 16 * sk + 8 + 2 * t) : 0u;
+      }
+    }
+    float base[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) base[q][r] = 0.f;
+#pragma unroll
+      for (int hl = 1; hl >= 0; --hl)      // small (lo) terms first
+#pragma unroll
+        for (int sk = 0; sk < 2; ++sk) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w0[hl][8 * q + g][16 * sk + 2 * t]);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w0[hl][8 * q + g][16 * sk + 8 + 2 * t]);
+          mma16816(base[q], fa[sk], b0, b1);
+        }
+    }
+    for (int m = 0; m < a.M; ++m) {
+      float h1[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 z = *reinterpret_cast<const float2*>(&zbs[m * F + 8 * q + 2 * t]);
+        h1[q][0] = fmaxf(base[q][0] + z.x, 0.f); h1[q][1] = fmaxf(base[q][1] + z.y, 0.f);
+        h1[q][2] = fmaxf(base[q][2] + z.x, 0.f); h1[q][3] = fmaxf(base[q][3] + z.y, 0.f);
+      }
+      uint32_t h1h[2][4], h1l[2][4];
+      c_to_a_split(h1, h1h, h1l);
+      float h2[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sk = 0; sk < 2; ++sk) {
+          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&s.w1[0][8 * q + g][16 * sk + 2 * t]);
+          const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&s.w1[0][8 * q + g][16 * sk + 8 + 2 * t]);
+          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&s.w1[1][8 * q + g][16 * sk + 2 * t]);
+          const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&s.w1[1][8 * q + g][16 * sk + 8 + 2 * t]);
+          mma16816(acc, h1l[sk], bh0, bh1);    // lo * hi
+          mma16816(acc, h1h[sk], bl0, bl1);    // hi * lo
+          mma16816(acc, h1h[sk], bh0, bh1);    // hi * hi
+        }
+        const float2 bb = *reinterpret_cast<const float2*>(&s.b1[8 * q + 2 * t]);
+        h2[q][0] = fmaxf(acc[0] + bb.x, 0.f); h2[q][1] = fmaxf(acc[1] + bb.y, 0.f);
+        h2[q][2] = fmaxf(acc[2] + bb.x, 0.f); h2[q][3] = fmaxf(acc[3] + bb.y, 0.f);
+      }
+      uint32_t h2h[2][4], h2l[2][4];
+      c_to_a_split(h2, h2h, h2l);
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int sk = 0; sk < 2; ++sk) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&s.w2[0][g][16 * sk + 2 * t]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&s.w2[0][g][16 * sk + 8 + 2 * t]);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&s.w2[1][g][16 * sk + 2 * t]);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&s.w2[1][g][16 * sk + 8 + 2 * t]);
+        mma16816(o, h2l[sk], bh0, bh1);
+        mma16816(o, h2h[sk], bl0, bl1);
+        mma16816(o, h2h[sk], bh0, bh1);
+      }
+      float* op = out + (((int64_t)b * a.M + m) * CO) * HW;
+      if (2 * t < CO) {
+        if (v0) op[(int64_t)(2 * t) * HW + p0] = o[0] + bo0;
+        if (v1) op[(int64_t)(2 * t) * HW + p1] = o[2] + bo0;
+      }
+      if (2 * t + 1 < CO) {
+        if (v0) op[(int64_t)(2 * t + 1) * HW + p0] = o[1] + bo1;
+        if (v1) op[(int64_t)(2 * t + 1) * HW + p1] = o[3] + bo1;
+      }
+    }
+  }
+}
+
 // final reduction over CTAs (fixed order) + the latent-half gradients
 __global__ void fcomb_bwd_final_kernel(const float* __restrict__ part, int nx, int B, int M, int L,
                                        const float* __restrict__ z, const float* __restrict__ w0,
@@ -676,6 +809,16 @@ int pub_fcomb_forward(const pub_fcomb_args* a, void* ws, size_t ws_bytes, pub_st
   PUB_LAUNCH_CHECK();
   const FcombDev d = make_dev(a, zb);
   const int HW = a->H * a->W;
+  if (!a->feat_nchw && a->dtype == PUB_BF16 && g_opt_fcomb_fwd_mma) {
+    const size_t dynm = (size_t)a->M * F * 4;
+    int gxm = cdiv(4 * num_sms(), a->B);
+    const int ntile = cdiv(HW, 64);      // 4 warps x 16 pixels per CTA iteration
+    if (gxm > ntile) gxm = ntile;
+    if (gxm < 1) gxm = 1;
+    fcomb_fwd_mma_kernel<<<dim3(gxm, a->B), NT, dynm, st>>>(d, a->out);
+    PUB_LAUNCH_CHECK();
+    return 0;
+  }
   int gx = cdiv(HW, NT);
   dim3 grid(gx, a->B);
   const size_t dyn = (size_t)a->M * F * 4;

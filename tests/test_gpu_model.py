@@ -258,7 +258,7 @@ def test_elbo_msssim_variant_at_128(golden):
 
     The de-zeroed seed-42 model predicts values of +-1900 against a target range of 18, so sigma_x^2 = E[x^2] - mu^2
     cancels ~7 digits in fp32: the ORACLE's own 1 - MS-SSIM moves by 0.85 % when its input moves by 2.6e-6 (measured,
-    tools/_dbg_ms.py).  Tight parity of the kernel is therefore asserted on well-conditioned fields in
+    tools/msssim_conditioning_probe.py).  Tight parity of the kernel is therefore asserted on well-conditioned fields in
     test_wmse_msssim_kernel_value_and_gradient_match_the_oracle; here the ill-conditioned term gets a 2 % band and
     everything around it (total, KL, WMSE, arity, KL-driven gradients) the usual tolerance."""
     x, y, eps = (torch.from_numpy(golden[k]).cuda() for k in ("B_x", "B_y", "B_eps"))
@@ -328,3 +328,29 @@ def test_dispatcher_ops_match_the_module_path(setup, golden):
     mq, sq, mp, sp = (torch.randn(4, 32, device="cuda", generator=g) for _ in range(4))
     sq, sp = sq.abs() + 0.1, sp.abs() + 0.1
     assert rel_err(ops.kl_normal(mq, sq, mp, sp), N.kl_normal(mq, sq, mp, sp)) < 1e-6
+
+
+def test_fcomb_forward_tensor_core_kernel_close_to_f32_kernel(golden):
+    """bf16 mode runs Fcomb.forward on tensor cores with every f32 operand split into two bf16 terms (hi + lo, three
+    MMAs per product): it must reproduce the f32-FMA kernel on the same bf16 features to ~1e-5 (plain bf16 operands
+    differ by 3.3e-3 and moved the afCRPS by 0.8 %), and stay inside the bf16 budget of the oracle."""
+    import _native as N
+    m = canonical_model(compute_dtype="bf16", device="cuda")
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x, y, _ = _inputs(golden)
+    z = torch.randn(7, 2, 32, generator=torch.Generator().manual_seed(21)).cuda()
+    with torch.no_grad():
+        feat = m.unet(x, _nhwc_out=True)
+        out = {}
+        try:
+            for opt in (0, 1):
+                N.lib().pub_debug_option(b"fcomb_fwd_mma", opt)
+                out[opt] = N.fcomb_apply(m.fcomb, feat, z, nhwc=True)
+                torch.cuda.synchronize()
+        finally:
+            N.lib().pub_debug_option(b"fcomb_fwd_mma", 1)
+        ref_feat = O.unet_forward(sd, x.cpu(), CFG.unet())
+        ref = torch.stack([O.fcomb(sd, ref_feat, z[i].cpu()) for i in range(7)], dim=1)
+    e_kernels = rel_err(out[1], out[0])
+    assert e_kernels < 5e-5, e_kernels
+    assert rel_err(out[1], ref) < TOL["bf16"], (rel_err(out[1], ref), rel_err(out[0], ref))

@@ -28,7 +28,10 @@ NDT = N.TF32 if TF32 else N.BF16
 g = torch.Generator(device="cuda").manual_seed(0)
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
 lib = N.lib()
-tot = {0: 0.0, 2: 0.0}
+# what is compared: CONV_AB_OPT="conv_halo:0,2" (default: per-tap vs halo everywhere) or e.g. "conv_chains:0,1"
+OPT, VALS = os.environ.get("CONV_AB_OPT", "conv_halo:0,2").split(":")
+VA, VB = (int(v) for v in VALS.split(","))
+tot = {VA: 0.0, VB: 0.0}
 rows = []
 for (kind, c0, c1, cout, r, ks), cnt in sorted(inv.items()):
     if kind != "fwd" or ks != 3 or (c0 + c1) % 32 or cout % 32:
@@ -41,8 +44,8 @@ for (kind, c0, c1, cout, r, ks), cnt in sorted(inv.items()):
     y = torch.empty(B, r, r, cout, device="cuda", dtype=torch.float32 if TF32 else torch.bfloat16)
     fl = 2.0 * B * r * r * (c0 + c1) * cout * 9
     res = {}
-    for halo in (0, 2):
-        lib.pub_debug_option(b"conv_halo", halo)
+    for halo in (VA, VB):
+        lib.pub_debug_option(OPT.encode(), halo)
         fn = lambda: N.conv2d_nhwc(x0, w, None, x1=x1, ksize=3, out=y, dtype=NDT)
         fn(); ts = []
         for _ in range(reps):
@@ -53,9 +56,9 @@ for (kind, c0, c1, cout, r, ks), cnt in sorted(inv.items()):
         res[halo] = statistics.median(ts)
         tot[halo] += res[halo] * cnt
     hbm = (B * r * r * (c0 + c1 + cout) * 2) / 6.5e6   # us at 6.5 TB/s (read x once, write y once)
-    rows.append((res[0] * cnt, f"{c0:4d}+{c1:<4d}->{cout:4d} @{r:3d}^2 x{cnt:<3d} tap {res[0]:7.1f} us {fl / res[0] / 1e6:6.0f} TF | "
-                 f"halo {res[2]:7.1f} us {fl / res[2] / 1e6:6.0f} TF | hbm floor {hbm:6.1f} us  mma floor {fl / 2.25e9:6.1f} us"))
+    rows.append((res[VA] * cnt, f"{c0:4d}+{c1:<4d}->{cout:4d} @{r:3d}^2 x{cnt:<3d} {OPT}={VA} {res[VA]:7.1f} us {fl / res[VA] / 1e6:6.0f} TF | "
+                 f"{OPT}={VB} {res[VB]:7.1f} us {fl / res[VB] / 1e6:6.0f} TF | hbm floor {hbm:6.1f} us  mma floor {fl / 2.25e9:6.1f} us"))
 for _, line in sorted(rows, reverse=True):
     print(line)
-lib.pub_debug_option(b"conv_halo", 1)
-print(f"sum over one step: per-tap {tot[0] / 1e3:.3f} ms, halo {tot[2] / 1e3:.3f} ms")
+lib.pub_debug_option(OPT.encode(), 1)
+print(f"sum over one step: {OPT}={VA} {tot[VA] / 1e3:.3f} ms, {OPT}={VB} {tot[VB] / 1e3:.3f} ms")

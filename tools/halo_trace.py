@@ -27,9 +27,8 @@ cb = c0 // 32
 def rel(v): return [int(a) - t0 for a in v if a > 0]
 P, M, E = rel(t[0]), rel(t[1]), rel(t[2])
 print(f"shape {c0}->{cout}@{r}^2  K blocks per tile {cb}; cycles relative to first stamp")
-print("producer per item: [copies landed, published, next item issued]")
-for i in range(0, min(len(P), 3 * 14), 3):
-    print("  item", i // 3, P[i:i + 3])
+print("TMA producer, per K block: [stage free -> box issued]")
+print("  ", P[:24])
 print("mma: per tile [acc buffer free, then per K block: (A full, committed)]")
 per = 1 + 2 * cb
 for i in range(0, min(len(M), per * 8), per):
@@ -37,6 +36,5 @@ for i in range(0, min(len(M), per * 8), per):
 print("epilogue per tile: [acc full, stored]")
 for i in range(0, min(len(E), 2 * 8), 2):
     print("  tile", i // 2, E[i:i + 2])
-if len(P) >= 6:
-    n = len(P) // 3
-    print("producer period (cycles/item):", (P[3 * (n - 1) + 1] - P[1]) / max(1, n - 1), "items", n)
+if len(P) >= 3:
+    print("producer period (cycles/K block):", (P[-1] - P[1]) / max(1, len(P) - 2), "items", len(P))
