@@ -1,4 +1,5 @@
 // C-ABI entry points (include/probunet_b200.h) for the primitive ops + shared host helpers.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -13,6 +14,7 @@ unsigned long long g_launch_count = 0;
 int g_opt_conv_halo = -1;
 int g_opt_wgrad_box3 = 1;
 int g_opt_fcomb_fwd_mma = 1;
+int g_opt_wgrad_fused_bias = 1;
 long long* g_halo_trace = nullptr;
 
 void set_error(const char* fmt, ...) {
@@ -94,9 +96,30 @@ int pub_debug_option(const char* name, int value) {
   if (strcmp(name, "conv_halo") == 0) { g_opt_conv_halo = value; return 0; }
   if (strcmp(name, "wgrad_box3") == 0) { g_opt_wgrad_box3 = value; return 0; }
   if (strcmp(name, "fcomb_fwd_mma") == 0) { g_opt_fcomb_fwd_mma = value; return 0; }
+  if (strcmp(name, "wgrad_fused_bias") == 0) { g_opt_wgrad_fused_bias = value; return 0; }
   set_error("pub_debug_option: unknown option '%s'", name);
   return -1;
 }
+
+namespace {
+// PUB_OPTS="name=value,name=value": the same knobs from the environment (A/B runs of unmodified drivers, e.g. bench.py)
+struct EnvOpts {
+  EnvOpts() {
+    const char* e = getenv("PUB_OPTS");
+    if (!e) return;
+    std::string s(e);
+    size_t pos = 0;
+    while (pos < s.size()) {
+      size_t end = s.find(',', pos);
+      if (end == std::string::npos) end = s.size();
+      const std::string kv = s.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos) pub_debug_option(kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1));
+      pos = end + 1;
+    }
+  }
+} g_env_opts;
+}  // namespace
 
 int pub_debug_pointer(const char* name, void* p) {
   PUB_REQUIRE(name != nullptr, "pub_debug_pointer: null name");

@@ -16,6 +16,7 @@
 // tcgen05.commit releases stages and publishes the accumulator.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include <type_traits>
@@ -655,7 +656,8 @@ struct TcWgradArgs {
   int tiles_total, tiles_per_split;
   int stages;
   float* part;            // [split][tap][cout][cin] f32
-  int box3;               // 3x3, 8x8 patches: x as three (8+2) x 8 boxes, dx taps as row offsets (see wgrad_tc_kernel)
+  int box3;               // 3x3, 8x8 patches: x as one (8+2) x (8+2) halo box, taps as row offsets (see wgrad_tc_kernel)
+  float* bias_part;       // [split][cout] column sums of dy (bias gradient partials) or nullptr
 };
 
 constexpr int WG_P = 64;  // pixels (K) per stage
@@ -704,8 +706,11 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   const int t_beg = split * a.tiles_per_split;
   const int t_end = min(a.tiles_total, t_beg + a.tiles_per_split);
 
+  // bias gradient: the CTAs of the first ci block also sum the dy tiles they stage (the four epilogue warps are idle
+  // during the main loop); a stage is then released by the MMA commit AND those four warps
+  const bool do_bias = a.bias_part != nullptr && blockIdx.x == 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, do_bias ? 5 : 1); }
     mbar_init(accbar, 1);
     fence_barrier_init();
     prefetch_tmap(&tmX0);
@@ -805,6 +810,37 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
     const bool has_work = t_end > t_beg;
+    if (do_bias) {
+      // column sums of the staged dy tiles: thread = channel (group q, lane), 64 pixel rows per K tile; the smem image
+      // is the TMA swizzle (bf16: 16-byte chunk ^= (row >> 1) & 3; tf32: 32-byte chunk ^= row & 3)
+      float bsum = 0.f;
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t choff = ES == 2 ? (uint32_t)(lane & 7) * 2u : (uint32_t)(lane & 7) * 4u;
+      for (int t = t_beg; t < t_end; ++t) {
+        mbar_wait(full0 + 8 * stage, phase);
+        if (q < ngroups) {
+          const uint32_t sg = base + (uint32_t)stage * STAGE_BYTES + (uint32_t)q * WG_GROUP_BYTES;
+#pragma unroll 8
+          for (int r = 0; r < WG_P; ++r) {
+            if (ES == 2) {
+              const uint32_t ad = sg + (uint32_t)r * ROW + ((((uint32_t)lane >> 3) ^ (((uint32_t)r >> 1) & 3u)) << 4) + choff;
+              uint16_t v;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(ad));
+              bsum += __uint_as_float((uint32_t)v << 16);
+            } else {
+              const uint32_t ad = sg + (uint32_t)r * ROW + ((((uint32_t)lane >> 3) ^ ((uint32_t)r & 3u)) << 5) + choff;
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad));
+              bsum += v;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      if (co < a.cout) a.bias_part[(int64_t)split * a.cout + co] = bsum;
+    }
     mbar_wait(accbar, 0);
     tc_fence_after();
     for (int tap = 0; tap < a.taps; ++tap) {
@@ -1104,7 +1140,8 @@ size_t wgrad_tc_workspace(const WgradParams& p, int dtype) {
   if (!wgrad_plan(p, esize(dtype), pl)) return 0;
   const int64_t n = (int64_t)p.ks * p.ks * p.cout * (p.c0 + p.c1);
   const int64_t M = (int64_t)p.B * p.H * p.W;
-  return align_up((size_t)pl.nsplit * n * sizeof(float), 256) + align_up((size_t)cdiv(M, 1024) * p.cout * 4, 256);
+  return align_up((size_t)pl.nsplit * n * sizeof(float), 256) +
+         align_up((size_t)std::max(cdiv(M, 1024), pl.nsplit) * p.cout * 4, 256);
 }
 
 int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
@@ -1119,6 +1156,8 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
   a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages; a.box3 = pl.box3;
   a.part = (float*)ws;
+  float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * taps * p.cout * cin * sizeof(float), 256));
+  a.bias_part = (p.dbias && g_opt_wgrad_fused_bias) ? bpart : nullptr;
   const CUtensorMapSwizzle sw = es == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX0, tmX1, tmDY;
   const int xbw = pl.box3 ? pl.tw + 2 : pl.tw, xbh = pl.box3 ? pl.th + 2 : pl.th;   // box3: the patch plus its halo
@@ -1136,10 +1175,9 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   if (es == 2) wgrad_tc_kernel<2><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
   else wgrad_tc_kernel<4><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
   PUB_LAUNCH_CHECK();
-  const int64_t n = (int64_t)taps * p.cout * cin;
-  float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * n * sizeof(float), 256));
-  int nchunk = 0;
-  if (p.dbias) PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, nullptr, 0, s, &nchunk));
+  int nchunk = pl.nsplit;     // bias partials: one row per split (summed inside the wgrad kernel) ...
+  if (p.dbias && !a.bias_part)  // ... or per 1024-pixel chunk from the separate column-sum pass
+    PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, nullptr, 0, s, &nchunk));
   return wgrad_finish(a.part, p.dw, pl.nsplit, taps, p.cout, cin, bpart, nchunk, p.dbias, accumulate, s);
 }
 
