@@ -811,27 +811,36 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     const int co = co0 + q * 32 + lane;
     const bool has_work = t_end > t_beg;
     if (do_bias) {
-      // column sums of the staged dy tiles: thread = channel (group q, lane), 64 pixel rows per K tile; the smem image
-      // is the TMA swizzle (bf16: 16-byte chunk ^= (row >> 1) & 3; tf32: 32-byte chunk ^= row & 3)
-      float bsum = 0.f;
+      // column sums of the staged dy tiles (group q of this warp): a lane owns one LOGICAL 16-byte chunk of the row
+      // (8 bf16 / 4 f32 channels) and walks the rows; its physical position follows the TMA swizzle (bf16: 16-byte
+      // chunk ^= (row >> 1) & 3; tf32: 32-byte chunk ^= row & 3).  16-byte loads: half the shared-memory wavefronts
+      // of scalar loads -- they compete with the tensor core's operand reads.
+      constexpr int CPRW = ROW / 16;            // 16-byte chunks per row: 4 / 8
+      constexpr int RPI = 32 / CPRW;            // rows per warp instruction: 8 / 4
+      constexpr int NV = 16 / ES;               // channels per chunk: 8 / 4
+      const int c16 = lane % CPRW, r0 = lane / CPRW;
+      float bs[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) bs[j] = 0.f;
       int stage = 0; uint32_t phase = 0;
-      const uint32_t choff = ES == 2 ? (uint32_t)(lane & 7) * 2u : (uint32_t)(lane & 7) * 4u;
       for (int t = t_beg; t < t_end; ++t) {
         mbar_wait(full0 + 8 * stage, phase);
         if (q < ngroups) {
           const uint32_t sg = base + (uint32_t)stage * STAGE_BYTES + (uint32_t)q * WG_GROUP_BYTES;
-#pragma unroll 8
-          for (int r = 0; r < WG_P; ++r) {
+#pragma unroll
+          for (int k = 0; k < WG_P / RPI; ++k) {
+            const uint32_t r = (uint32_t)(r0 + k * RPI);
+            const uint32_t pos = ES == 2 ? (((uint32_t)c16 ^ ((r >> 1) & 3u)) << 4)
+                                         : (((((uint32_t)c16 >> 1) ^ (r & 3u)) << 5) | (((uint32_t)c16 & 1u) << 4));
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sg + r * ROW + pos));
             if (ES == 2) {
-              const uint32_t ad = sg + (uint32_t)r * ROW + ((((uint32_t)lane >> 3) ^ (((uint32_t)r >> 1) & 3u)) << 4) + choff;
-              uint16_t v;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(ad));
-              bsum += __uint_as_float((uint32_t)v << 16);
+              bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
+              bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
+              bs[4 % NV] += __uint_as_float(w2 << 16); bs[5 % NV] += __uint_as_float(w2 & 0xFFFF0000u);
+              bs[6 % NV] += __uint_as_float(w3 << 16); bs[7 % NV] += __uint_as_float(w3 & 0xFFFF0000u);
             } else {
-              const uint32_t ad = sg + (uint32_t)r * ROW + ((((uint32_t)lane >> 3) ^ ((uint32_t)r & 3u)) << 5) + choff;
-              float v;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad));
-              bsum += v;
+              bs[0] += __uint_as_float(w0); bs[1] += __uint_as_float(w1); bs[2] += __uint_as_float(w2); bs[3] += __uint_as_float(w3);
             }
           }
         }
@@ -839,7 +848,18 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
         if (lane == 0) mbar_arrive(empty0 + 8 * stage);
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
-      if (co < a.cout) a.bias_part[(int64_t)split * a.cout + co] = bsum;
+      // rows were dealt over lane / CPRW: fixed xor tree over those lane bits, then lanes 0 .. CPRW-1 write their chunk
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int o = CPRW; o < 32; o <<= 1) bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], o);
+      if (lane < CPRW) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int cc = co0 + q * 32 + c16 * NV + j;
+          if (cc < a.cout) a.bias_part[(int64_t)split * a.cout + cc] = bs[j];
+        }
+      }
     }
     mbar_wait(accbar, 0);
     tc_fence_after();

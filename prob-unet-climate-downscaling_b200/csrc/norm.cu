@@ -27,9 +27,19 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return r;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
-__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
-__device__ __forceinline__ float silu_grad_fast(float x) {
-  const float s = sigmoid_fast(x);
+// bf16 storage: one MUFU (tanh.approx, rel. error 2^-11 -- below the 2^-9 of the bf16 value it is multiplied into)
+// instead of ex2 + rcp + 2 FP32 ops; f32 storage keeps the exact-to-1e-6 form
+__device__ __forceinline__ float sigmoid_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x) {
+  return sizeof(T) == 2 ? sigmoid_tanh(x) : sigmoid_fast(x);
+}
+template <typename T> __device__ __forceinline__ float silu_t(float x) { return x * sigmoid_t<T>(x); }
+template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
+  const float s = sigmoid_t<T>(x);
   return fmaf(x * s, 1.f - s, s);
 }
 
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
+                const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
                 s1[j] += du;
                 s2[j] = fmaf(du, x[j], s2[j]);
               }
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
         load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
+          const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
           s1[j] += du;
           s2[j] = fmaf(du, x[j], s2[j]);
         }
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
         float x[8], o[8];
         xr[u].unpack(x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = silu_fast(fmaf(a[j], x[j], bb[j]));
+        for (int j = 0; j < 8; ++j) o[j] = silu_t<T>(fmaf(a[j], x[j], bb[j]));
         if (p.p_drop > 0.f) {
           bool keep[8];
           dropout_keep8(p.seed, p.subseq, pix * C + c, thresh, keep);
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
         float x[8];
         load_vec<T>(p, pix, v, x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += silu_fast(fmaf(a[j], x[j], bb[j]));
+        for (int j = 0; j < 8; ++j) o[j] += silu_t<T>(fmaf(a[j], x[j], bb[j]));
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
+          const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
           o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
         }
         if (ab) {
@@ -468,7 +478,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
     load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float du = g[j] * silu_grad_fast(fmaf(a[j], x[j], bb[j]));
+      const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
       o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
     }
     if (addend) {
