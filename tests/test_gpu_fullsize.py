@@ -1,0 +1,105 @@
+"""Size-independent properties at BASELINE.json's FULL sizes (B = 64, 128 x 128), where the CPU oracle would take
+minutes: two independent kernels for the same op must agree, linear ops must be linear, normalised outputs must be
+normalised, a training step must be deterministic.  Small-size parity against the oracle / golden vectors lives in
+test_gpu_conv.py and test_gpu_model.py."""
+import pytest
+import torch
+
+from helpers import canonical_model, rel_err
+
+pytestmark = pytest.mark.gpu
+B, R = 64, 128
+
+
+def _gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("cin,cout,res", [(32, 32, 128), (64, 64, 64), (96, 32, 128), (256, 256, 16)])
+def test_conv_two_kernels_agree_and_are_linear(cin, cout, res):
+    """conv_halo_kernel (one halo box per tile, taps as operand offsets) vs conv_tc_kernel (one TMA box per tap):
+    different data paths, same products -> equal up to f32 summation order; and conv(a + b) == conv(a) + conv(b)."""
+    import _native as N
+    g = _gen(1)
+    x = torch.randn(B, res, res, cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(9, cout, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g)
+    out = {}
+    try:
+        for opt in (0, 1):
+            N.lib().pub_debug_option(b"conv_halo", opt)
+            out[opt] = N.conv2d_nhwc(x, w, b, ksize=3).float()
+        torch.cuda.synchronize()
+    finally:
+        N.lib().pub_debug_option(b"conv_halo", 1)
+    assert rel_err(out[1], out[0]) < 4e-3          # both round the same f32 sums to bf16
+    x2 = torch.randn(B, res, res, cin, device="cuda", generator=g).bfloat16()
+    lhs = N.conv2d_nhwc((x.float() + x2.float()).bfloat16(), w, None, ksize=3).float()
+    rhs = N.conv2d_nhwc(x, w, None, ksize=3).float() + N.conv2d_nhwc(x2, w, None, ksize=3).float()
+    assert rel_err(lhs, rhs) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout,res", [(32, 32, 128), (64, 64, 64), (256, 256, 16)])
+def test_wgrad_two_producers_agree_and_bias_is_column_sum(cin, cout, res):
+    """box3 (one halo box, taps as row offsets) vs nine tap boxes; the bias gradient summed inside the kernel equals
+    the column sums of dy; deterministic (bit-identical) across two runs."""
+    import _native as N
+    g = _gen(2)
+    x = torch.randn(B, res, res, cin, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(B, res, res, cout, device="cuda", generator=g).bfloat16()
+    out = {}
+    try:
+        for opt in (0, 1):
+            N.lib().pub_debug_option(b"wgrad_box3", opt)
+            out[opt] = N.conv2d_wgrad_nhwc(x, dy, 3)
+        again = N.conv2d_wgrad_nhwc(x, dy, 3)
+        torch.cuda.synchronize()
+    finally:
+        N.lib().pub_debug_option(b"wgrad_box3", 1)
+    assert rel_err(out[1][0], out[0][0]) < 1e-4
+    assert rel_err(out[1][1], dy.float().sum(dim=(0, 1, 2))) < 1e-4
+    assert torch.equal(again[0], out[1][0]) and torch.equal(again[1], out[1][1])
+
+
+def test_full_size_training_step_is_deterministic_and_finite():
+    """BASELINE configs[2] shape: same seed -> bit-identical loss and gradients (no float atomics anywhere), dropout
+    keeps ~90 %, every one of the 391 gradients is finite."""
+    import _native as N
+    from climex_synth import make_fields
+    m = canonical_model(compute_dtype="bf16", device="cuda")
+    m.train()
+    f = make_fields(B, R, R, 16, seed=5)
+    x, y = f["inputs"].cuda(), f["targets"].cuda()
+    eps = torch.randn(15, B, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    runs = []
+    for _ in range(2):
+        N.manual_seed(77)
+        m.zero_grad(set_to_none=True)
+        total, recon, kl = m.elbo(x, y, None, M=15, eps=eps)
+        total.backward()
+        runs.append((float(total), [p.grad.clone() for p in m.parameters()]))
+    assert runs[0][0] == runs[1][0]
+    for g0, g1 in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(g0, g1) and bool(torch.isfinite(g0).all())
+    eng = m.unet.engine()
+    key = [k for k in eng.block_keys if not k.endswith("_conv")][0]
+    keep = eng.dropout_mask(key, B, R, R, 77).float().mean()
+    assert abs(float(keep) - 0.9) < 2e-3
+
+
+def test_full_size_ensemble_crps_properties():
+    """100 prior members per field: CRPS >= 0, CRPS of an ensemble whose members all equal the truth is 0, and the
+    CRPS kernel is invariant under a permutation of the members."""
+    import metrics
+    g = torch.Generator().manual_seed(8)
+    T, M = 8, 100
+    hr = torch.randn(T, 3, R, R, generator=g)
+    ens = hr.unsqueeze(1) + 0.3 * torch.randn(T, M, 3, R, R, generator=g)
+    means, arrays = metrics.crps_over_groundtruth(hr, ens)
+    assert all(v >= 0 for v in means.values())
+    perm = torch.randperm(M, generator=g)
+    means_p, _ = metrics.crps_over_groundtruth(hr, ens[:, perm])
+    for k in means:
+        assert abs(means[k] - means_p[k]) < 1e-6 * max(1.0, abs(means[k]))
+    zero, _ = metrics.crps_over_groundtruth(hr, hr.unsqueeze(1).expand(T, 4, 3, R, R).contiguous())
+    assert all(abs(v) < 1e-7 for v in zero.values())
