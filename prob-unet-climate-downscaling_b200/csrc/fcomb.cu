@@ -735,23 +735,30 @@ __global__ void fcomb_bwd_final_kernel(const float* __restrict__ part, int nx, i
     Stot[i] = (float)sum;
   }
 }
+// db0, dW0z: one WARP per output, lanes stride over the M*B (member, sample) pairs in double (fixed shuffle tree);
+// dz: one thread per element.  (A thread per output walking all pairs serially in double took 0.28 ms.)
 __global__ void fcomb_bwd_latent_kernel(const float* __restrict__ Stot, int B, int M, int L, const float* __restrict__ z,
                                         const float* __restrict__ w0, float* __restrict__ dz, float* __restrict__ dw0,
                                         float* __restrict__ db0) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int MB = M * B;
-  for (int i = tid; i < F; i += nth) {  // db0[j]
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int o = gw; o < F + F * L; o += nw) {
     double s = 0.0;
-    for (int mb = 0; mb < MB; ++mb) s += (double)Stot[mb * F + i];
-    db0[i] = (float)s;
-  }
-  for (int i = tid; i < F * L; i += nth) {  // dW0z[j][l] = sum_mb S[mb][j] z[mb][l]
-    const int j = i / L, l = i % L;
-    double s = 0.0;
-    for (int mb = 0; mb < MB; ++mb) s += (double)Stot[mb * F + j] * (double)z[(int64_t)mb * L + l];
-    dw0[j * (F + L) + F + l] = (float)s;
+    if (o < F) {                       // db0[j]
+      for (int mb = lane; mb < MB; mb += 32) s += (double)Stot[mb * F + o];
+    } else {                           // dW0z[j][l] = sum_mb S[mb][j] z[mb][l]
+      const int j = (o - F) / L, l = (o - F) % L;
+      for (int mb = lane; mb < MB; mb += 32) s += (double)Stot[mb * F + j] * (double)z[(int64_t)mb * L + l];
+    }
+    s = warp_sum_d(s);
+    if (lane == 0) {
+      if (o < F) db0[o] = (float)s;
+      else dw0[((o - F) / L) * (F + L) + F + (o - F) % L] = (float)s;
+    }
   }
   if (dz) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < MB * L; i += nth) {  // dz[mb][l] = sum_j W0z[j][l] S[mb][j]
       const int mb = i / L, l = i % L;
       float s = 0.f;
@@ -856,7 +863,7 @@ int pub_fcomb_backward(const pub_fcomb_args* a, const float* dout, void* dfeat, 
     PUB_LAUNCH_CHECK();
     fcomb_bwd_final_kernel<<<16, 256, 0, st>>>(part, gx, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0, dw1, db1, dw2, db2, Stot);
     PUB_LAUNCH_CHECK();
-    fcomb_bwd_latent_kernel<<<8, 256, 0, st>>>(Stot, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0);
+    fcomb_bwd_latent_kernel<<<132, 256, 0, st>>>(Stot, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0);
     PUB_LAUNCH_CHECK();
     return 0;
   }
@@ -870,7 +877,7 @@ int pub_fcomb_backward(const pub_fcomb_args* a, const float* dout, void* dfeat, 
   PUB_LAUNCH_CHECK();
   fcomb_bwd_final_kernel<<<16, 256, 0, st>>>(part, gx, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0, dw1, db1, dw2, db2, Stot);
   PUB_LAUNCH_CHECK();
-  fcomb_bwd_latent_kernel<<<8, 256, 0, st>>>(Stot, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0);
+  fcomb_bwd_latent_kernel<<<132, 256, 0, st>>>(Stot, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0);
   PUB_LAUNCH_CHECK();
   return 0;
 }
