@@ -1,6 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv` launch list:
 time (and DRAM traffic, when captured) per kernel name over ONE training step = the launches between two consecutive
-adamw_kernel launches (or the last N launches).  usage: summarize_launches.py launches.csv [--json out.json]"""
+adamw_kernel launches (or, with --per-step N, the N launches ending at the one adamw launch captured).
+usage: summarize_launches.py launches.csv [--per-step N] [--json out.json]"""
 import csv, sys, re, collections, json
 path = sys.argv[1]
 with open(path, newline="") as f:
@@ -20,6 +21,11 @@ rows = list(per.values())
 ad = [i for i, d in enumerate(rows) if "adamw_kernel" in d["name"]]
 if len(ad) >= 2:
     rows = rows[ad[-2] + 1: ad[-1] + 1]        # exactly one step
+elif len(ad) == 1 and "--per-step" in sys.argv:  # window ending at the optimizer launch
+    n = int(sys.argv[sys.argv.index("--per-step") + 1])
+    head = rows[ad[0] + 1:][:n]                     # the beginning of the NEXT step (steps are structurally identical)
+    need = n - len(head)                            # ... completed by the end of this one
+    rows = head + rows[max(0, ad[0] - need + 1): ad[0] + 1]
 def short(n):
     n = n.replace("pub::<unnamed>::", "").replace("pub::(anonymous namespace)::", "")
     return re.sub(r"\(.*", "", re.sub(r"^void ", "", n))
