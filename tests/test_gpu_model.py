@@ -354,3 +354,63 @@ def test_fcomb_forward_tensor_core_kernel_close_to_f32_kernel(golden):
     e_kernels = rel_err(out[1], out[0])
     assert e_kernels < 5e-5, e_kernels
     assert rel_err(out[1], ref) < TOL["bf16"], (rel_err(out[1], ref), rel_err(out[0], ref))
+
+
+def test_deterministic_unet_config2_forward_backward():
+    """BASELINE configs[1]: networks.UNet(img_resolution, in_channels=3, out_channels=3, label_dim=0) as built by
+    src/deterministic_unet_main.py:52 (model_channels 16, channel_mult [1,4,8,16]) trained with MSE
+    (src/trainmodel.py:158-160).  16- and 3-channel layers take the fp32-FMA conv path, the rest tcgen05."""
+    import networks
+    from helpers import dezero
+    torch.manual_seed(42)
+    net = networks.UNet(img_resolution=(64, 64), in_channels=3, out_channels=3, label_dim=0, use_diffuse=False)
+    dezero(net)
+    sd = {"unet." + k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = O.UNetCfg(in_channels=3, out_channels=3, model_channels=16, channel_mult=(1, 4, 8, 16), label_dim=0,
+                    img_resolution=(64, 64))
+    g = torch.Generator().manual_seed(6)
+    x, y = torch.randn(2, 3, 64, 64, generator=g), torch.randn(2, 3, 64, 64, generator=g)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "resample_filter" not in k}
+    full = dict(sd); full.update(leaves)
+    ref = O.unet_forward(full, x, cfg)
+    torch.nn.functional.mse_loss(ref, y).backward()
+    # per-tensor gradient rel-err (stricter than the norm comparison of the Prob U-Net tests): bf16 rounding of the
+    # activations shows up as ~8 % on the smallest GroupNorm / FiLM gradients
+    for name, tol, gtol in (("fp32", 1e-4, 2e-3), ("bf16", 2e-2, 1.2e-1)):
+        net.compute_dtype = name
+        m = net.cuda().eval()
+        m.zero_grad(set_to_none=True)
+        out = m(x.cuda(), class_labels=None)            # the keyword train_step passes (src/trainmodel.py:158)
+        assert out.shape == (2, 3, 64, 64)
+        assert rel_err(out, ref) < tol, (name, rel_err(out, ref))
+        torch.nn.functional.mse_loss(out, y.cuda()).backward()
+        bad = []
+        for k, p in m.named_parameters():
+            r = leaves["unet." + k].grad
+            if r is None:                                # map_label is absent / affine.weight sees a zero input
+                assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
+                continue
+            if float(r.norm()) > 1e-7 and rel_err(p.grad, r) > gtol:
+                bad.append((k, rel_err(p.grad, r)))
+        assert not bad, (name, bad[:6])
+
+
+def test_posterior_latent_sweep_shapes_at_256():
+    """BASELINE configs[4] (src/latent_exploration_posterior.py): 256 x 256 grids, posterior means, one U-Net pass and
+    a grid of fcomb decodes on an expanded (non-contiguous) feature view -- against the oracle."""
+    m = canonical_model(latent_dim=8, compute_dtype="fp32", device="cuda")
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    cfg = O.ProbUNetCfg(latent_dim=8)
+    g = torch.Generator().manual_seed(10)
+    x, y = torch.randn(1, 3, 256, 256, generator=g), torch.randn(1, 3, 256, 256, generator=g)
+    with torch.no_grad():
+        q = m.posterior(x.cuda(), y.cuda())
+        feat = m.unet(x.cuda())
+        zs = q.base_dist.loc + q.base_dist.scale * torch.linspace(-3, 3, 4, device="cuda").unsqueeze(1)   # [4, L]
+        dec = m.fcomb(feat.expand(4, -1, -1, -1), zs)
+        mu_r, sig_r = O.gaussian_encoder(sd, "posterior", x, y, cfg.num_filters)
+        feat_r = O.unet_forward(sd, x, cfg.unet())
+        dec_r = O.fcomb(sd, feat_r.expand(4, -1, -1, -1), zs.cpu())
+    assert rel_err(q.base_dist.loc, mu_r) < 1e-4 and rel_err(q.base_dist.scale, sig_r) < 1e-4
+    assert feat.shape == (1, 32, 256, 256) and rel_err(feat, feat_r) < 1e-4
+    assert dec.shape == (4, 3, 256, 256) and rel_err(dec, dec_r) < 1e-4
