@@ -414,6 +414,25 @@ def run_b200(args):
                                 "includes": "unet+prior once per field, fcomb x M, residual_to_hr+CRPS+MAE kernel"}
         except Exception as ex:
             line["ensemble"] = {"error": repr(ex)}
+        # ---- auxiliary: GPU-side dataset transform (__getitem__ math, src/climex_utils.py:197-225)
+        try:
+            from climex_gpu import ClimexBatchTransform
+            hr_all = torch.randn(4 * B, 3, R, R, device="cuda") * 4 + 280
+            tr = ClimexBatchTransform(lowres_scale=16 if R >= 128 else 8)
+            tr.compute_stats(hr_all)
+            for _ in range(3):
+                tr(hr_all[:B])
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(20):
+                tr(hr_all[(i % 4) * B:(i % 4 + 1) * B])
+            f1.record(); torch.cuda.synchronize()
+            dt_f = f0.elapsed_time(f1) * 1e-3 / 20
+            line["feeder"] = {"samples_per_s": B / dt_f, "gb_per_s": B * 3 * R * R * 4 * 4 / dt_f / 1e9,
+                              "what": "climex_transform_kernel: hr [B,3,H,W] in HBM -> inputs, targets, lrinterp, lr "
+                                      "(reads 1x, writes 3x; the reference does this per sample on the host)"}
+        except Exception as ex:
+            line["feeder"] = {"error": repr(ex)}
         # ---- CPU baseline: the oracle on the host cores, bounded sample
         try:
             torch.cuda.synchronize()

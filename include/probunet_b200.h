@@ -208,6 +208,19 @@ int pub_wmse_msssim_loss(const float* pred, const float* target, int B, int C, i
 int pub_scale_by_device_scalar(float* y, const float* scale, int64_t n, pub_stream_t s);
 
 /* ------------------------------------------------------------------------------------
+ * Dataset transform on the GPU: climex2torch.__getitem__ for type "lrinterp_to_residuals"
+ * (src/climex_utils.py:197-225) and compute_stats (:255-264), batched.  All tensors f32 NCHW.
+ *   pub_climex_stats:     hr [T,C,H,W] -> mean_lr, std_lr [C,H/s,W/s] (unbiased std over T of the s x s cell means)
+ *   pub_climex_transform: hr [B,C,H,W] -> inputs, targets, lrinterp [B,C,H,W], lr [B,C,H/s,W/s]
+ *                         (lrinterp / lr optional, may be NULL); eps = 1e-10 in the reference (:86)
+ * ---------------------------------------------------------------------------------- */
+int pub_climex_stats(const float* hr, int T, int C, int H, int W, int lowres_scale, float* mean_lr, float* std_lr,
+                     pub_stream_t s);
+int pub_climex_transform(const float* hr, const float* mean_lr, const float* std_lr, int B, int C, int H, int W,
+                         int lowres_scale, float eps, float* inputs, float* targets, float* lrinterp, float* lr,
+                         pub_stream_t s);
+
+/* ------------------------------------------------------------------------------------
  * Ensemble metrics: metrics.crps_over_groundtruth / compute_mae (src/metrics.py:11-71) with
  * residual_to_hr + inverse transforms fused (src/climex_utils.py:277-285,42-46).
  * preds [T,M,3,HW] f32; transform=1: preds are standardised residuals, converted with

@@ -417,3 +417,28 @@ def residual_to_real(residual: Tensor, lrinterp: Tensor, std_hr: Tensor) -> Tens
     tmin = hr[..., 1, :, :] - 273.15
     tmax = softplus_ref(hr[..., 2, :, :], c=0.0) + hr[..., 1, :, :] - 273.15
     return torch.stack([pr, tmin, tmax], dim=-3)
+
+
+# --------------------------------------------------------------------------------------
+# dataset transform  (src/climex_utils.py:197-225, 255-264, 277-285)
+# --------------------------------------------------------------------------------------
+def climex_compute_stats(hr_all: Tensor, s: int):
+    """compute_stats (src/climex_utils.py:255-264): statistics of the coarsened fields over time, and their
+    block-constant expansion to the HR grid."""
+    lr = F.avg_pool2d(hr_all, s)
+    mean, std = lr.mean(dim=0), lr.std(dim=0)
+    up = lambda t: t.repeat_interleave(s, dim=1).repeat_interleave(s, dim=2)
+    return (mean, std), (up(mean), up(std))
+
+
+def climex_getitem(hr: Tensor, stats, s: int, eps: float = 1e-10) -> Dict[str, Tensor]:
+    """__getitem__ for type "lrinterp_to_residuals" (src/climex_utils.py:197-225), one field [C,H,W] or a batch."""
+    batched = hr.dim() == 4
+    h = hr if batched else hr.unsqueeze(0)
+    lr = F.avg_pool2d(h, s)
+    lrinterp = F.interpolate(lr, scale_factor=s)
+    mean_hr, std_hr = stats[1]
+    lrinterp_stand = (lrinterp - mean_hr) / (std_hr + eps)
+    hr_stand = (h - mean_hr) / (std_hr + eps)
+    out = {"inputs": lrinterp_stand, "targets": hr_stand - lrinterp_stand, "hr": h, "lr": lr, "lrinterp": lrinterp}
+    return out if batched else {k: v.squeeze(0) for k, v in out.items()}

@@ -76,7 +76,7 @@ EXPORTS = [
     "pub_unet_dropout_mask", "pub_encoder_create", "pub_encoder_destroy", "pub_encoder_num_params",
     "pub_encoder_workspace_bytes", "pub_encoder_forward", "pub_encoder_backward", "pub_rsample_forward",
     "pub_rsample_backward", "pub_kl_normal_forward", "pub_kl_normal_backward", "pub_fcomb_forward_workspace", "pub_fcomb_forward",
-    "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss", "pub_msssim_workspace", "pub_wmse_msssim_loss",
+    "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss", "pub_msssim_workspace", "pub_wmse_msssim_loss", "pub_climex_stats", "pub_climex_transform",
     "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
 ]
 

@@ -129,3 +129,20 @@ def test_metrics_restatement_consistency():
     ref = torch.stack([O.crps_empirical(preds[t], hr[t]).mean(dim=(1, 2)) for t in range(3)]).numpy()
     np.testing.assert_allclose(c, ref, rtol=1e-5, atol=1e-6)
     assert O.compute_mae(hr, preds).shape == (3, 3)
+
+
+def test_climex_transform_oracle_matches_the_real_dataset_class():
+    """oracle.climex_compute_stats / climex_getitem against fixtures produced by the REAL climex2torch class
+    (tests/golden/make_climex_golden.py: __getitem__ "lrinterp_to_residuals", compute_stats, residual_to_hr)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "climex_golden.npz"))
+    hr, s = torch.from_numpy(g["hr"]), int(g["scale"])
+    stats = O.climex_compute_stats(hr, s)
+    assert rel_err(stats[0][0], g["mean_lr"]) < 1e-6 and rel_err(stats[0][1], g["std_lr"]) < 1e-6
+    assert rel_err(stats[1][0], g["mean_hr"]) < 1e-6 and rel_err(stats[1][1], g["std_hr"]) < 1e-6
+    for n, i in enumerate(g["idx"]):
+        it = O.climex_getitem(hr[int(i)], stats, s)
+        for k in ("inputs", "targets", "lr", "lrinterp"):
+            assert rel_err(it[k], g[k][n]) < 1e-6, (k, rel_err(it[k], g[k][n]))
+    batch = O.climex_getitem(hr[torch.from_numpy(g["idx"])], stats, s)
+    assert rel_err(batch["targets"], g["targets"]) < 1e-6
