@@ -37,6 +37,9 @@ class FusedAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        sync = N.grad_ready_callback
+        if sync is not None and hasattr(sync, "wait_all"):
+            sync.wait_all()           # gradient all-reduces overlapped with the rest of backward end here
         for gi, group in enumerate(self.param_groups):
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:

@@ -5,8 +5,10 @@ The reference is single-process.  The hot path shards two ways:
 * training -- pure data parallel: every rank runs the full model on its slice of the batch and
   gradients are SUM-all-reduced (``GradSynchronizer``); the 1/world factor is folded into
   FusedAdamW's ``grad_scale``.  Each engine (fcomb, U-Net, posterior, prior) hands its flat
-  gradient buffer to the synchronizer as soon as its backward kernels are enqueued, so the
-  collective of one sub-network is in flight on NCCL's stream while the host enqueues the next.
+  gradient buffer to the synchronizer as soon as its backward kernels are enqueued; the collective
+  runs on NCCL's stream while the NEXT sub-network's backward kernels run on the compute stream --
+  the compute stream only waits for the collectives in ``wait_all()``, which FusedAdamW.step()
+  (or the user, before any other use of the gradients) calls.
 * ensemble sampling -- fields are partitioned over ranks, no collective until the final gather
   of the [T,3] score arrays (``shard_range`` / ``gather_scores``).
 """
@@ -29,13 +31,21 @@ class GradSynchronizer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.calls = 0
         self.bytes = 0
+        self.pending = []          # (work handle, buffer kept alive until the wait)
 
     def __call__(self, flat):
         self.calls += 1
         self.bytes += flat.numel() * flat.element_size()
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            work.wait()       # stream-ordered for NCCL (no host block); blocking for gloo
+            self.pending.append((work, flat))
+
+    def wait_all(self):
+        """Makes the current stream wait for every collective issued since the last call (stream-ordered for
+        NCCL: no host block; blocking for gloo).  Must run before the gradients are consumed."""
+        for work, _ in self.pending:
+            work.wait()
+        self.pending.clear()
 
     def install(self):
         import _native

@@ -80,8 +80,14 @@ r = dist.get_rank()
 sync = GradSynchronizer().install()
 flat = torch.full((1000,), float(r + 1))
 _native._notify(flat)                      # what every engine backward calls with its flat gradient buffer
+flat2 = torch.full((10,), float(10 * (r + 1)))
+_native._notify(flat2)                     # a second sub-network: both collectives stay in flight ...
+assert len(sync.pending) == 2
+sync.wait_all()                            # ... until the optimizer (FusedAdamW.step) asks for the gradients
+assert not sync.pending
 assert torch.allclose(flat, torch.full((1000,), 3.0)), flat[:4]
-assert sync.calls == 1 and sync.bytes == 4000 and sync.world == 2
+assert torch.allclose(flat2, torch.full((10,), 30.0)), flat2[:4]
+assert sync.calls == 2 and sync.bytes == 4040 and sync.world == 2
 b, e = shard_range(5, r, 2)
 local = torch.arange(b, e).float().reshape(-1, 1).repeat(1, 3)
 allv = gather_scores(local, [3, 2])
