@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--loss", default="afcrps", choices=["afcrps", "crps", "l1", "mse+ssim"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--latent", type=int, default=32)
+    ap.add_argument("--device-scalars", action="store_true",
+                    help="model.sync_scalars = False: elbo() returns its reconstruction terms as device tensors instead of "
+                         "Python floats (no host sync between forward and backward); default keeps the reference's floats")
     ap.add_argument("--no-aux", action="store_true", help="skip the roofline sweep / cpu baseline / ensemble aux")
     ap.add_argument("--cpu-batch", type=int, default=2)
     return ap.parse_args()
@@ -178,6 +181,7 @@ def workload_config(args):
             "reference_config": "BASELINE.json configs[2]: Prob U-Net training 128x128 batch 64 bf16, data-parallel",
             "per_gpu_batch": args.batch, "resolution": args.res, "elbo_members": M, "loss": args.loss,
             "latent_dim": args.latent, "optimizer": "AdamW lr 1e-4 (fused)", "dropout": 0.1,
+            "elbo_scalars": "device tensors" if getattr(args, "device_scalars", False) else "python floats (reference)",
             "l2_policy": "working set per step (saved activations, several GB) >> 126 MB L2; no explicit flush"}
 
 
@@ -294,6 +298,7 @@ def run_b200(args):
     M = args.members if args.loss in ("afcrps", "crps") else 1
     model = canonical_model(latent_dim=args.latent, loss_type=args.loss, compute_dtype=args.dtype, device="cuda")
     model.train()                                      # dropout on, as the reference trains
+    model.sync_scalars = not args.device_scalars
     N.manual_seed(1000 + rank)
     opt = FusedAdamW(model.parameters(), lr=1e-4, grad_scale=1.0 / world)
     sync = GradSynchronizer().install()

@@ -966,20 +966,6 @@ int set_smem_attr(K kernel, int bytes) {
 
 }  // namespace
 
-bool conv_tc_supported(const ConvParams& p, int dtype) {
-  if (dtype != PUB_BF16 && dtype != PUB_TF32) return false;
-  const int es = esize(dtype), al = 16 / es;
-  if (p.ks != 1 && p.ks != 3) return false;
-  const int cin = p.c0 + p.c1;
-  if (p.c0 % 32 || p.c1 % 32 || cin < 32 || pick_bn(p.cout) == 0) return false;
-  if (p.ld0 % al || (p.x1 && p.ld1 % al) || p.ldy % al) return false;
-  if (!aligned16(p.x0) || !aligned16(p.x1) || !aligned16(p.w) || !aligned16(p.y)) return false;
-  if ((p.res && (p.ld_res % al || !aligned16(p.res))) || (p.mask && (p.ld_mask % al || !aligned16(p.mask))))
-    return false;
-  int tw, th, tb;
-  return pick_patch(p.H, p.W, 128, tw, th, tb);
-}
-
 namespace {
 bool halo_enabled() {
   if (g_opt_conv_halo < 0) { const char* e = getenv("PUB_CONV_HALO"); g_opt_conv_halo = (e && e[0] == '0') ? 0 : 1; }
@@ -993,6 +979,24 @@ bool conv_halo_ok(const ConvParams& p, int dtype) {
   return halo_enabled() && p.ks == 3 && p.W % 8 == 0 && p.H % 16 == 0 && (dtype == PUB_BF16 || dtype == PUB_TF32);
 }
 
+}  // namespace
+
+bool conv_tc_supported(const ConvParams& p, int dtype) {
+  if (dtype != PUB_BF16 && dtype != PUB_TF32) return false;
+  const int es = esize(dtype), al = 16 / es;
+  if (p.ks != 1 && p.ks != 3) return false;
+  const int cin = p.c0 + p.c1;
+  if (p.c0 % 32 || p.c1 % 32 || cin < 32 || pick_bn(p.cout) == 0) return false;
+  if (p.ld0 % al || (p.x1 && p.ld1 % al) || p.ldy % al) return false;
+  if (!aligned16(p.x0) || !aligned16(p.x1) || !aligned16(p.w) || !aligned16(p.y)) return false;
+  if ((p.res && (p.ld_res % al || !aligned16(p.res))) || (p.mask && (p.ld_mask % al || !aligned16(p.mask))))
+    return false;
+  if (conv_halo_ok(p, dtype)) return true;      // 8 x 16 halo tiles: any W % 8 == 0, H % 16 == 0
+  int tw, th, tb;
+  return pick_patch(p.H, p.W, 128, tw, th, tb);
+}
+
+namespace {
 int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   const int cin = p.c0 + p.c1, es = esize(dtype);
   const int KC = es == 4 ? 32 : ((p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32);

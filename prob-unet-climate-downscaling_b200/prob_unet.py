@@ -136,6 +136,10 @@ class ProbabilisticUNet(nn.Module):
         self.fcomb = Fcomb(num_filters[0], latent_dim, num_classes).to(device)
         self.prior_latent_space = None
         self.posterior_latent_space = None
+        # The reference returns the reconstruction terms as Python floats (.item() / .tolist(): a host sync between
+        # forward and backward).  False keeps them as 0-dim device tensors so the whole step is enqueued without
+        # waiting for the GPU; the values are the same.
+        self.sync_scalars = True
 
     def set_compute_dtype(self, name):
         self.unet.compute_dtype = self.prior.compute_dtype = self.posterior.compute_dtype = name
@@ -180,17 +184,18 @@ class ProbabilisticUNet(nn.Module):
             l1, per_var = _native.l1_loss(out[:, 0], target)
             kl2 = _native.kl_normal(q.loc, q.scale, torch.zeros_like(q.loc), torch.ones_like(q.scale))
             total = self.beta_0 * l1 + self.beta_1 * torch.mean(kl_div) + self.beta_2 * torch.mean(kl2)
-            return total, per_var.detach().tolist(), kl_div, kl2
+            pv = per_var.detach()
+            return total, (pv.tolist() if self.sync_scalars else list(pv.unbind())), kl_div, kl2
         z = self.posterior_latent_space.rsample((M,), eps=eps)
         ens = _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)      # [B,M,C,H,W]
         if lt in ("afcrps", "crps"):
             crps = _native.ensemble_loss(ens, target, kind=lt, alpha=alpha)
             total = self.beta_0 * crps + self.beta_1 * kl_div.mean()
-            return total, [crps.item()], kl_div
+            return total, [crps.item() if self.sync_scalars else crps.detach()], kl_div
         if lt == "mse+ssim":
             recs = [_native.wmse_ms_ssim(ens[:, m], target, alpha_w, beta_w, lam_w, None) for m in range(M)]
             recon = torch.stack([r[0] for r in recs]).mean()
             total = self.beta_0 * recon + self.beta_1 * kl_div.mean()
-            return (total, [recon.detach().cpu().item()], kl_div,
-                    recs[-1][1].detach().cpu().item(), recs[-1][2].detach().cpu().item())
+            host = (lambda v: v.detach().cpu().item()) if self.sync_scalars else (lambda v: v.detach())
+            return total, [host(recon)], kl_div, host(recs[-1][1]), host(recs[-1][2])
         raise ValueError(f"unknown loss_type {lt!r}")

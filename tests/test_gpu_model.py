@@ -414,3 +414,33 @@ def test_posterior_latent_sweep_shapes_at_256():
     assert rel_err(q.base_dist.loc, mu_r) < 1e-4 and rel_err(q.base_dist.scale, sig_r) < 1e-4
     assert feat.shape == (1, 32, 256, 256) and rel_err(feat, feat_r) < 1e-4
     assert dec.shape == (4, 3, 256, 256) and rel_err(dec, dec_r) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["fp32", "bf16"])
+def test_elbo_on_a_non_square_grid_matches_the_oracle(name):
+    """96 x 64 fields (not a power of two, H != W): the pyramid is 96x64 / 48x32 / 24x16 / 12x8, so the halo conv
+    (H % 16 == 0), the per-tap conv and the FMA fallback (24x16, 12x8) are all on the path; loss and every
+    gradient norm against the oracle."""
+    m = canonical_model(compute_dtype=name, device="cuda")
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "resample_filter" not in k}
+    full = dict(sd); full.update(leaves)
+    g = torch.Generator().manual_seed(21)
+    x, y = torch.randn(2, 3, 96, 64, generator=g), torch.randn(2, 3, 96, 64, generator=g)
+    eps = torch.randn(3, 2, CFG.latent_dim, generator=g)
+    rt = O.elbo(full, CFG, x, y, eps, "afcrps")
+    rt[0].backward()
+    m.loss_type = "afcrps"
+    m.zero_grad(set_to_none=True)
+    total, recon, kl = m.elbo(x.cuda(), y.cuda(), None, M=3, eps=eps.cuda())
+    total.backward()
+    assert abs(float(total) - float(rt[0])) / abs(float(rt[0])) < 5 * TOL[name], (float(total), float(rt[0]))
+    bad = []
+    for n, p in m.named_parameters():
+        r = leaves[n].grad
+        if r is None or float(r.norm()) < 1e-7:
+            continue
+        gn, rn = float(p.grad.double().norm()), float(r.double().norm())
+        if abs(gn - rn) > GTOL[name] * rn + 1e-9:
+            bad.append((n, gn, rn))
+    assert not bad, bad[:6]
