@@ -15,6 +15,8 @@ int g_opt_conv_halo = -1;
 int g_opt_wgrad_box3 = 1;
 int g_opt_fcomb_fwd_mma = 1;
 int g_opt_wgrad_fused_bias = 1;
+int g_opt_pdl = 1;
+unsigned long long g_last_pack_launch = 0;
 long long* g_halo_trace = nullptr;
 
 void set_error(const char* fmt, ...) {
@@ -97,6 +99,7 @@ int pub_debug_option(const char* name, int value) {
   if (strcmp(name, "wgrad_box3") == 0) { g_opt_wgrad_box3 = value; return 0; }
   if (strcmp(name, "fcomb_fwd_mma") == 0) { g_opt_fcomb_fwd_mma = value; return 0; }
   if (strcmp(name, "wgrad_fused_bias") == 0) { g_opt_wgrad_fused_bias = value; return 0; }
+  if (strcmp(name, "pdl") == 0) { g_opt_pdl = value; return 0; }
   set_error("pub_debug_option: unknown option '%s'", name);
   return -1;
 }

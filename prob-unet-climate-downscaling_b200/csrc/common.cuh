@@ -43,6 +43,32 @@ extern unsigned long long g_launch_count;  // kernels enqueued by this library (
     PUB_CUDA(cudaGetLastError());   \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Kernels whose first global-memory access comes after pdl_wait() are launched through launch_pdl(): the next kernel
+// of the stream may be scheduled once every CTA of this one has passed its own pdl_wait() and called pdl_trigger(),
+// so its CTAs occupy SMs as ours drain and its prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// resident-weight TMA) overlaps our tail instead of following it.  Trigger-after-wait bounds the look-ahead to one
+// kernel: when a kernel starts, everything up to its predecessor's predecessor has completed and is visible.
+// Kernels launched the ordinary way (<<< >>>) in between keep full stream serialisation; in them, and with
+// g_opt_pdl = 0 (pub_debug_option("pdl", 0)), both instructions are no-ops.
+extern int g_opt_pdl;
+extern unsigned long long g_last_pack_launch;  // g_launch_count right after the last weight-pack launch
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_opt_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);   // errors surface in PUB_LAUNCH_CHECK
+}
+#endif
+
 #define PUB_TRY(expr)        \
   do {                       \
     int r__ = (expr);        \

@@ -23,6 +23,7 @@ __device__ __forceinline__ float load2src(const T* x0, const T* x1, int c0, int 
 
 template <typename T>
 __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvParams p) {
+  pdl_enter();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const T* x0 = (const T*)p.x0;
@@ -136,6 +137,7 @@ template <int CIN> struct PixLoad<bf16, CIN> {
 // warp instead of 72 + 72 shared loads of the lane-per-channel version it replaces (1.1 ms -> HBM-bound output write).
 template <typename T, int CIN>
 __global__ void __launch_bounds__(128) conv_smallc_kernel(ConvParams p) {
+  pdl_enter();
   __shared__ __align__(16) float ws[9 * CIN][32];  // [tap*CIN + ci][co]
   __shared__ float bs[32];
   const T* x0 = (const T*)p.x0;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(128) conv_smallc_kernel(ConvParams p) {
 template <typename T>
 __global__ void __launch_bounds__(NT) wgrad_simt_kernel(WgradParams p, float* __restrict__ part, int nsplit,
                                                         int pix_per_split) {
+  pdl_enter();
   __shared__ float As[BK][BM + 4];  // [pixel][co]
   __shared__ float Bs[BK][BN + 4];  // [pixel][ci]
   const T* x0 = (const T*)p.x0;
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(NT) wgrad_simt_kernel(WgradParams p, float* __
 // keeps 8 of them in flight while the additions stay in split order.
 __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw,
                                                            int nsplit, int taps, int cout, int cin, int accumulate) {
+  pdl_enter();
   const int64_t n = (int64_t)taps * cout * cin;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -319,6 +323,7 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
                                                            int nsplit, int taps, int cout, int cin, int nbw,
                                                            const float* __restrict__ bpart, int nchunk,
                                                            float* __restrict__ dbias, int accumulate) {
+  pdl_enter();
   if ((int)blockIdx.x < nbw) {
     const int64_t n = (int64_t)taps * cout * cin;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,6 +357,7 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
 // per iteration are in flight.  part[cta][tap][co][ci].
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, float* __restrict__ part, int pix_per_cta) {
+  pdl_enter();
   __shared__ float red[9 * CIN][32];
   const T* x0 = (const T*)p.x0;
   const T* dy = (const T*)p.dy;
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, flo
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int ld, int C, int64_t M,
                                                          int rows_per_chunk, float* __restrict__ part) {
+  pdl_enter();
   extern __shared__ float sm[];  // [RY][V][8]
   const int V = C / 8, RY = 256 / V;
   const int v = threadIdx.x % V, ry = threadIdx.x / V;
@@ -466,6 +473,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 template <typename T>
 __global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int C, int64_t M, int rows_per_chunk,
                                       float* __restrict__ part) {
+  pdl_enter();
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
@@ -475,6 +483,7 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, int ld, int C, in
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nchunk, int C, float* __restrict__ out,
                                     int accumulate) {
+  pdl_enter();
   // one warp per channel, lanes stride over the chunk partials, fixed shuffle tree
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -530,6 +539,7 @@ __global__ void pack_weights_batched_kernel(const __grid_constant__ PackTable t,
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0, const float* __restrict__ x1, int c1,
                                     T* __restrict__ y, int ldy, int B, int64_t HW) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * HW) return;
   const int64_t b = i / HW, p = i % HW;
@@ -541,6 +551,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x0, int c0, const 
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ld, int C, float* __restrict__ y, int B, int64_t HW,
                                     int accumulate) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * HW) return;
   const int64_t b = i / HW, p = i % HW;
@@ -559,7 +570,7 @@ int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
   if (p.c1 == 0 && p.c0 <= 8 && p.ld0 % 8 == 0 && (((uintptr_t)p.x0) & 31) == 0 && (p.ks == 1 || p.ks == 3)) {
     dim3 grid(cdiv(M, 128), cdiv(p.cout, 32));
     const int cc = p.c0 <= 3 ? 3 : (p.c0 <= 6 ? 6 : 8);
-#define PUB_SMALLC(TT, CC) conv_smallc_kernel<TT, CC><<<grid, 128, 0, s>>>(p)
+#define PUB_SMALLC(TT, CC) launch_pdl(conv_smallc_kernel<TT, CC>, grid, 128, 0, s, p)
     if (dtype == PUB_BF16) { if (cc == 3) PUB_SMALLC(bf16, 3); else if (cc == 6) PUB_SMALLC(bf16, 6); else PUB_SMALLC(bf16, 8); }
     else { if (cc == 3) PUB_SMALLC(float, 3); else if (cc == 6) PUB_SMALLC(float, 6); else PUB_SMALLC(float, 8); }
 #undef PUB_SMALLC
@@ -567,8 +578,8 @@ int conv_simt(const ConvParams& p, int dtype, cudaStream_t s) {
     return 0;
   }
   dim3 grid(cdiv(M, BM), cdiv(p.cout, BN));
-  if (dtype == PUB_BF16) conv_simt_kernel<bf16><<<grid, NT, 0, s>>>(p);
-  else conv_simt_kernel<float><<<grid, NT, 0, s>>>(p);
+  if (dtype == PUB_BF16) launch_pdl(conv_simt_kernel<bf16>, grid, NT, 0, s, p);
+  else launch_pdl(conv_simt_kernel<float>, grid, NT, 0, s, p);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -617,7 +628,7 @@ int wgrad_finish(const float* part, float* dw, int nsplit, int taps, int cout, i
                  float* dbias, int accumulate, cudaStream_t s) {
   const int64_t n = (int64_t)taps * cout * cin;
   const int nbw = cdiv(n, 128), nbb = dbias ? cdiv(cout, 4) : 0;
-  wgrad_finish_kernel<<<nbw + nbb, 128, 0, s>>>(part, dw, nsplit, taps, cout, cin, nbw, bpart, nchunk, dbias, accumulate);
+  launch_pdl(wgrad_finish_kernel, nbw + nbb, 128, 0, s, part, dw, nsplit, taps, cout, cin, nbw, bpart, nchunk, dbias, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -630,23 +641,23 @@ int colsum(const void* x, int ld, int C, int64_t M, int dtype, float* part, floa
   if (nchunk_out) *nchunk_out = nchunk;
   if (C % 8 == 0 && ld % 8 == 0 && C <= 2048 && (((uintptr_t)x) & 31) == 0) {
     const size_t smem = (size_t)(256 / (C / 8)) * (C / 8) * 8 * sizeof(float);
-    if (dtype == PUB_BF16) colsum_vec_kernel<bf16><<<nchunk, 256, smem, s>>>((const bf16*)x, ld, C, M, rows, part);
-    else colsum_vec_kernel<float><<<nchunk, 256, smem, s>>>((const float*)x, ld, C, M, rows, part);
+    if (dtype == PUB_BF16) launch_pdl(colsum_vec_kernel<bf16>, nchunk, 256, smem, s, (const bf16*)x, ld, C, M, rows, part);
+    else launch_pdl(colsum_vec_kernel<float>, nchunk, 256, smem, s, (const float*)x, ld, C, M, rows, part);
   } else {
     dim3 grid(nchunk, cdiv(C, 64));
-    if (dtype == PUB_BF16) colsum_partial_kernel<bf16><<<grid, 64, 0, s>>>((const bf16*)x, ld, C, M, rows, part);
-    else colsum_partial_kernel<float><<<grid, 64, 0, s>>>((const float*)x, ld, C, M, rows, part);
+    if (dtype == PUB_BF16) launch_pdl(colsum_partial_kernel<bf16>, grid, 64, 0, s, (const bf16*)x, ld, C, M, rows, part);
+    else launch_pdl(colsum_partial_kernel<float>, grid, 64, 0, s, (const float*)x, ld, C, M, rows, part);
   }
   PUB_LAUNCH_CHECK();
   if (!out) return 0;
-  colsum_final_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(part, nchunk, C, out, accumulate);
+  launch_pdl(colsum_final_kernel, cdiv((int64_t)C * 32, 256), 256, 0, s, part, nchunk, C, out, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
 }
 
 int wgrad_reduce(const float* part, float* dw, int nsplit, int taps, int cout, int cin, int accumulate, cudaStream_t s) {
   const int64_t n = (int64_t)taps * cout * cin;
-  wgrad_reduce_kernel<<<cdiv(n, 128), 128, 0, s>>>(part, dw, nsplit, taps, cout, cin, accumulate);
+  launch_pdl(wgrad_reduce_kernel, cdiv(n, 128), 128, 0, s, part, dw, nsplit, taps, cout, cin, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -663,15 +674,15 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
     smallc_plan(p, nctas, ppc);
     dim3 grid(nctas, cdiv(p.cout, 32));
     const int cc = p.c0 <= 3 ? 3 : (p.c0 <= 6 ? 6 : 8);
-#define PUB_SMALLC(TT, CC) wgrad_smallc_kernel<TT, CC><<<grid, 256, 0, s>>>(p, part, ppc)
+#define PUB_SMALLC(TT, CC) launch_pdl(wgrad_smallc_kernel<TT, CC>, grid, 256, 0, s, p, part, ppc)
     if (dtype == PUB_BF16) { if (cc == 3) PUB_SMALLC(bf16, 3); else if (cc == 6) PUB_SMALLC(bf16, 6); else PUB_SMALLC(bf16, 8); }
     else { if (cc == 3) PUB_SMALLC(float, 3); else if (cc == 6) PUB_SMALLC(float, 6); else PUB_SMALLC(float, 8); }
 #undef PUB_SMALLC
     nsplit = nctas;
   } else {
     dim3 grid(cdiv(cin, BN), cdiv(p.cout, BM), taps * nsplit);
-    if (dtype == PUB_BF16) wgrad_simt_kernel<bf16><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
-    else wgrad_simt_kernel<float><<<grid, NT, 0, s>>>(p, part, nsplit, pps);
+    if (dtype == PUB_BF16) launch_pdl(wgrad_simt_kernel<bf16>, grid, NT, 0, s, p, part, nsplit, pps);
+    else launch_pdl(wgrad_simt_kernel<float>, grid, NT, 0, s, p, part, nsplit, pps);
   }
   PUB_LAUNCH_CHECK();
   const int64_t n = (int64_t)taps * p.cout * cin;
@@ -686,6 +697,7 @@ int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype,
   if (dtype == PUB_BF16) pack_weight_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(w, (bf16*)out, cout, cin, ks, tflip, 0);
   else pack_weight_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(w, (float*)out, cout, cin, ks, tflip, dtype == PUB_TF32);
   PUB_LAUNCH_CHECK();
+  g_last_pack_launch = g_launch_count;
   return 0;
 }
 
@@ -704,6 +716,7 @@ int pack_weights_batched(const PackEntry* e, int n, int dtype, cudaStream_t s) {
     if (dtype == PUB_BF16) pack_weights_batched_kernel<bf16><<<blocks, 256, 0, s>>>(t, 0);
     else pack_weights_batched_kernel<float><<<blocks, 256, 0, s>>>(t, dtype == PUB_TF32);
     PUB_LAUNCH_CHECK();
+    g_last_pack_launch = g_launch_count;
   }
   return 0;
 }
@@ -712,9 +725,9 @@ int nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, int 
                  cudaStream_t s) {
   const int64_t n = (int64_t)B * H * W;
   if (dtype == PUB_BF16)
-    nchw_to_nhwc_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(x0, c0, x1, c1, (bf16*)y, ldy, B, (int64_t)H * W);
+    launch_pdl(nchw_to_nhwc_kernel<bf16>, cdiv(n, 256), 256, 0, s, x0, c0, x1, c1, (bf16*)y, ldy, B, (int64_t)H * W);
   else
-    nchw_to_nhwc_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(x0, c0, x1, c1, (float*)y, ldy, B, (int64_t)H * W);
+    launch_pdl(nchw_to_nhwc_kernel<float>, cdiv(n, 256), 256, 0, s, x0, c0, x1, c1, (float*)y, ldy, B, (int64_t)H * W);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -723,9 +736,9 @@ int nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, in
                  cudaStream_t s) {
   const int64_t n = (int64_t)B * H * W;
   if (dtype == PUB_BF16)
-    nhwc_to_nchw_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>((const bf16*)x, ld, C, y, B, (int64_t)H * W, accumulate);
+    launch_pdl(nhwc_to_nchw_kernel<bf16>, cdiv(n, 256), 256, 0, s, (const bf16*)x, ld, C, y, B, (int64_t)H * W, accumulate);
   else
-    nhwc_to_nchw_kernel<float><<<cdiv(n, 256), 256, 0, s>>>((const float*)x, ld, C, y, B, (int64_t)H * W, accumulate);
+    launch_pdl(nhwc_to_nchw_kernel<float>, cdiv(n, 256), 256, 0, s, (const float*)x, ld, C, y, B, (int64_t)H * W, accumulate);
   PUB_LAUNCH_CHECK();
   return 0;
 }

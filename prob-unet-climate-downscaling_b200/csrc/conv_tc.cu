@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_enter();   // everything above overlapped the previous kernel's tail; no global memory touched yet
 
   if (warp == 0) {
     if (lane == 0) {
@@ -415,6 +416,7 @@ struct HaloArgs {
   int tiles_x, tiles_y, m_tiles;
   int BN, cout;
   int astages, bstages, resident;
+  int w_early;        // weights were packed >= 2 launches ago: safe to load before the grid-dependency wait
   const float* bias;
   const void* res; int ld_res;
   const void* mask; int ld_mask;
@@ -480,15 +482,22 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // Resident weights are requested BEFORE the grid-dependency wait when the host knows they were packed at least two
+  // launches ago (a.w_early; see launch_pdl in common.cuh): the up-to-147 KB slab then lands while the previous
+  // kernel is still draining.  Everything else -- activations, residual, mask, the output -- is touched after it.
+  auto load_resident = [&]() {
+    mbar_expect_tx(wbar, (uint32_t)(cblk * 9) * B_BYTES);
+    for (int cb = 0; cb < cblk; ++cb)
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_3d(wbase + (uint32_t)(cb * 9 + tap) * B_BYTES, &tmW, wbar, cb * KC, n0, tap);
+  };
+  if (threadIdx.x == 0 && a.resident && a.w_early) load_resident();
+  pdl_enter();
+
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- resident weights once, then one halo box per (tile, K block)
-      if (a.resident) {
-        mbar_expect_tx(wbar, (uint32_t)(cblk * 9) * B_BYTES);
-        for (int cb = 0; cb < cblk; ++cb)
-          for (int tap = 0; tap < 9; ++tap)
-            tma_load_3d(wbase + (uint32_t)(cb * 9 + tap) * B_BYTES, &tmW, wbar, cb * KC, n0, tap);
-      }
+      if (a.resident && !a.w_early) load_resident();
       int stage = 0; uint32_t phase = 0;
       int trn = 0;
       for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x) {
@@ -722,6 +731,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_enter();   // prologue overlapped the previous kernel's tail; no global memory touched yet
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1010,6 +1020,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.mask = p.mask; a.ld_mask = p.ld_mask;
   a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
   a.trace = g_halo_trace;
+  a.w_early = p.w_settled && g_opt_pdl && g_launch_count - g_last_pack_launch >= 2;
   const int n_tiles = p.cout / a.BN;
   const int cblk = cin / KC;
   const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);
@@ -1049,9 +1060,9 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
     attr = true;
   }
   dim3 grid(gx, n_tiles);
-  if (es == 4) conv_halo_kernel<128, 4><<<grid, HTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
-  else if (rowb == 128) conv_halo_kernel<128, 2><<<grid, HTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
-  else conv_halo_kernel<64, 2><<<grid, HTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  if (es == 4) launch_pdl(conv_halo_kernel<128, 4>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  else if (rowb == 128) launch_pdl(conv_halo_kernel<128, 2>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  else launch_pdl(conv_halo_kernel<64, 2>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -1110,9 +1121,9 @@ int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
     PUB_TRY(set_smem_attr(conv_tc_kernel<128, 4>, 201 * 1024));
     attr = true;
   }
-  if (es == 4) conv_tc_kernel<128, 4><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
-  else if (rowb == 128) conv_tc_kernel<128, 2><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
-  else conv_tc_kernel<64, 2><<<grid, NTHREADS, smem, s>>>(tmA0, tmA1, tmW, a);
+  if (es == 4) launch_pdl(conv_tc_kernel<128, 4>, grid, NTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  else if (rowb == 128) launch_pdl(conv_tc_kernel<128, 2>, grid, NTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  else launch_pdl(conv_tc_kernel<64, 2>, grid, NTHREADS, smem, s, tmA0, tmA1, tmW, a);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -1196,8 +1207,8 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
     attr = true;
   }
   dim3 grid(cin / 32, cdiv(p.cout, 128), pl.nsplit);
-  if (es == 2) wgrad_tc_kernel<2><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
-  else wgrad_tc_kernel<4><<<grid, NTHREADS, pl.smem, s>>>(tmX0, tmX1, tmDY, a);
+  if (es == 2) launch_pdl(wgrad_tc_kernel<2>, grid, NTHREADS, pl.smem, s, tmX0, tmX1, tmDY, a);
+  else launch_pdl(wgrad_tc_kernel<4>, grid, NTHREADS, pl.smem, s, tmX0, tmX1, tmDY, a);
   PUB_LAUNCH_CHECK();
   int nchunk = pl.nsplit;     // bias partials: one row per split (summed inside the wgrad kernel) ...
   if (p.dbias && !a.bias_part)  // ... or per 1024-pixel chunk from the separate column-sum pass

@@ -19,6 +19,7 @@ inline int grid_for(int64_t n) {
 template <typename T>
 __global__ void resample_kernel(const T* __restrict__ x, int ld, int C, T* __restrict__ y, int B, int H, int W,
                                 int mode) {
+  pdl_enter();
   const int V = C / 8;
   const int Ho = mode == 1 ? H / 2 : H * 2, Wo = mode == 1 ? W / 2 : W * 2;
   const int64_t total = (int64_t)B * Ho * Wo * V;
@@ -50,6 +51,7 @@ __global__ void resample_kernel(const T* __restrict__ x, int ld, int C, T* __res
 template <typename T>
 __global__ void resample_bwd_kernel(const T* __restrict__ dy, int ld, int C, T* __restrict__ dx, int B, int H, int W,
                                     int mode) {
+  pdl_enter();
   const int V = C / 8;
   const int64_t total = (int64_t)B * H * W * V;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -79,6 +81,7 @@ __global__ void resample_bwd_kernel(const T* __restrict__ dy, int ld, int C, T* 
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, int lda, const T* __restrict__ b, int ldb, T* __restrict__ y,
                            int ldy, int C, int64_t M) {
+  pdl_enter();
   const int V = C / 8;
   const int64_t total = M * V;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -95,6 +98,7 @@ __global__ void add_kernel(const T* __restrict__ a, int lda, const T* __restrict
 
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ x, int C, T* __restrict__ y, int B, int H, int W) {
+  pdl_enter();
   const int V = C / 8, Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)B * Ho * Wo * V;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -118,6 +122,7 @@ __global__ void maxpool_kernel(const T* __restrict__ x, int C, T* __restrict__ y
 template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int C,
                                    int B, int H, int W) {
+  pdl_enter();
   const int V = C / 8, Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)B * Ho * Wo * V;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -151,6 +156,7 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
 
 template <typename T>
 __global__ void relu_mask_kernel(T* __restrict__ dy, const T* __restrict__ y, int64_t nvec) {
+  pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * NT) {
     float g[8], a[8];
     Vec8<T>::load(dy + i * 8, g);
@@ -164,6 +170,7 @@ __global__ void relu_mask_kernel(T* __restrict__ dy, const T* __restrict__ y, in
 // out[b][c] = mean over HW of x[b][p][c]; one thread per (b, c), fixed order
 template <typename T>
 __global__ void global_mean_kernel(const T* __restrict__ x, int C, int64_t HW, float* __restrict__ out) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (c >= C) return;
   float s = 0.f;
@@ -176,6 +183,7 @@ __global__ void global_mean_kernel(const T* __restrict__ x, int C, int64_t HW, f
 template <typename T>
 __global__ void global_mean_bwd_kernel(const float* __restrict__ dmean, const T* __restrict__ mask, int C, int64_t HW,
                                        int64_t total_vec, T* __restrict__ dx) {
+  pdl_enter();
   const int V = C / 8;
   const float inv = 1.f / (float)HW;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * NT) {
@@ -194,16 +202,16 @@ __global__ void global_mean_bwd_kernel(const float* __restrict__ dmean, const T*
 
 #define DISPATCH_T(dtype, KERNEL, grid, ...)                                            \
   do {                                                                                  \
-    if ((dtype) == PUB_BF16) KERNEL<bf16><<<grid, NT, 0, s>>>(__VA_ARGS__);             \
-    else KERNEL<float><<<grid, NT, 0, s>>>(__VA_ARGS__);                                \
+    if ((dtype) == PUB_BF16) launch_pdl(KERNEL<bf16>, grid, NT, 0, s, __VA_ARGS__);             \
+    else launch_pdl(KERNEL<float>, grid, NT, 0, s, __VA_ARGS__);                                \
     PUB_LAUNCH_CHECK();                                                                 \
   } while (0)
 
 int resample2x(const void* x, int ld, int C, void* y, int B, int H, int W, int mode, int dtype, cudaStream_t s) {
   PUB_REQUIRE(C % 8 == 0 && ld % 8 == 0, "resample2x: C and ld must be multiples of 8");
   const int64_t n = (int64_t)B * H * W * (C / 8) * (mode == 1 ? 1 : 4) / (mode == 1 ? 4 : 1);
-  if (dtype == PUB_BF16) resample_kernel<bf16><<<grid_for(n), NT, 0, s>>>((const bf16*)x, ld, C, (bf16*)y, B, H, W, mode);
-  else resample_kernel<float><<<grid_for(n), NT, 0, s>>>((const float*)x, ld, C, (float*)y, B, H, W, mode);
+  if (dtype == PUB_BF16) launch_pdl(resample_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, ld, C, (bf16*)y, B, H, W, mode);
+  else launch_pdl(resample_kernel<float>, grid_for(n), NT, 0, s, (const float*)x, ld, C, (float*)y, B, H, W, mode);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -211,8 +219,8 @@ int resample2x(const void* x, int ld, int C, void* y, int B, int H, int W, int m
 int resample2x_bwd(const void* dy, int ld, int C, void* dx, int B, int H, int W, int mode, int dtype, cudaStream_t s) {
   PUB_REQUIRE(C % 8 == 0 && ld % 8 == 0, "resample2x_bwd: C and ld must be multiples of 8");
   const int64_t n = (int64_t)B * H * W * (C / 8);
-  if (dtype == PUB_BF16) resample_bwd_kernel<bf16><<<grid_for(n), NT, 0, s>>>((const bf16*)dy, ld, C, (bf16*)dx, B, H, W, mode);
-  else resample_bwd_kernel<float><<<grid_for(n), NT, 0, s>>>((const float*)dy, ld, C, (float*)dx, B, H, W, mode);
+  if (dtype == PUB_BF16) launch_pdl(resample_bwd_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)dy, ld, C, (bf16*)dx, B, H, W, mode);
+  else launch_pdl(resample_bwd_kernel<float>, grid_for(n), NT, 0, s, (const float*)dy, ld, C, (float*)dx, B, H, W, mode);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -221,8 +229,8 @@ int add_views(const void* a, int lda, const void* b, int ldb, void* y, int ldy, 
               cudaStream_t s) {
   PUB_REQUIRE(C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0, "add_views: strides must be multiples of 8");
   const int64_t n = M * (C / 8);
-  if (dtype == PUB_BF16) add_kernel<bf16><<<grid_for(n), NT, 0, s>>>((const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)y, ldy, C, M);
-  else add_kernel<float><<<grid_for(n), NT, 0, s>>>((const float*)a, lda, (const float*)b, ldb, (float*)y, ldy, C, M);
+  if (dtype == PUB_BF16) launch_pdl(add_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)y, ldy, C, M);
+  else launch_pdl(add_kernel<float>, grid_for(n), NT, 0, s, (const float*)a, lda, (const float*)b, ldb, (float*)y, ldy, C, M);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -230,8 +238,8 @@ int add_views(const void* a, int lda, const void* b, int ldb, void* y, int ldy, 
 int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cudaStream_t s) {
   PUB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: C %% 8 and even H, W required");
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
-  if (dtype == PUB_BF16) maxpool_kernel<bf16><<<grid_for(n), NT, 0, s>>>((const bf16*)x, C, (bf16*)y, B, H, W);
-  else maxpool_kernel<float><<<grid_for(n), NT, 0, s>>>((const float*)x, C, (float*)y, B, H, W);
+  if (dtype == PUB_BF16) launch_pdl(maxpool_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, C, (bf16*)y, B, H, W);
+  else launch_pdl(maxpool_kernel<float>, grid_for(n), NT, 0, s, (const float*)x, C, (float*)y, B, H, W);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -239,32 +247,32 @@ int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cuda
 int maxpool2_bwd(const void* x, const void* /*yp*/, const void* dy, void* dx, int C, int B, int H, int W, int dtype,
                  cudaStream_t s) {
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
-  if (dtype == PUB_BF16) maxpool_bwd_kernel<bf16><<<grid_for(n), NT, 0, s>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, C, B, H, W);
-  else maxpool_bwd_kernel<float><<<grid_for(n), NT, 0, s>>>((const float*)x, (const float*)dy, (float*)dx, C, B, H, W);
+  if (dtype == PUB_BF16) launch_pdl(maxpool_bwd_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, (const bf16*)dy, (bf16*)dx, C, B, H, W);
+  else launch_pdl(maxpool_bwd_kernel<float>, grid_for(n), NT, 0, s, (const float*)x, (const float*)dy, (float*)dx, C, B, H, W);
   PUB_LAUNCH_CHECK();
   return 0;
 }
 
 int relu_mask_inplace(void* dy, const void* y, int64_t n, int dtype, cudaStream_t s) {
   PUB_REQUIRE(n % 8 == 0, "relu_mask_inplace: n %% 8");
-  if (dtype == PUB_BF16) relu_mask_kernel<bf16><<<grid_for(n / 8), NT, 0, s>>>((bf16*)dy, (const bf16*)y, n / 8);
-  else relu_mask_kernel<float><<<grid_for(n / 8), NT, 0, s>>>((float*)dy, (const float*)y, n / 8);
+  if (dtype == PUB_BF16) launch_pdl(relu_mask_kernel<bf16>, grid_for(n / 8), NT, 0, s, (bf16*)dy, (const bf16*)y, n / 8);
+  else launch_pdl(relu_mask_kernel<float>, grid_for(n / 8), NT, 0, s, (float*)dy, (const float*)y, n / 8);
   PUB_LAUNCH_CHECK();
   return 0;
 }
 
 int global_mean(const void* x, int C, int B, int64_t HW, float* out, float* /*partial*/, int dtype, cudaStream_t s) {
   dim3 grid(cdiv(C, 128), B);
-  if (dtype == PUB_BF16) global_mean_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, C, HW, out);
-  else global_mean_kernel<float><<<grid, 128, 0, s>>>((const float*)x, C, HW, out);
+  if (dtype == PUB_BF16) launch_pdl(global_mean_kernel<bf16>, grid, 128, 0, s, (const bf16*)x, C, HW, out);
+  else launch_pdl(global_mean_kernel<float>, grid, 128, 0, s, (const float*)x, C, HW, out);
   PUB_LAUNCH_CHECK();
   return 0;
 }
 
 int global_mean_bwd(const float* dmean, const void* mask, int C, int B, int64_t HW, void* dx, int dtype, cudaStream_t s) {
   const int64_t n = (int64_t)B * HW * (C / 8);
-  if (dtype == PUB_BF16) global_mean_bwd_kernel<bf16><<<grid_for(n), NT, 0, s>>>(dmean, (const bf16*)mask, C, HW, n, (bf16*)dx);
-  else global_mean_bwd_kernel<float><<<grid_for(n), NT, 0, s>>>(dmean, (const float*)mask, C, HW, n, (float*)dx);
+  if (dtype == PUB_BF16) launch_pdl(global_mean_bwd_kernel<bf16>, grid_for(n), NT, 0, s, dmean, (const bf16*)mask, C, HW, n, (bf16*)dx);
+  else launch_pdl(global_mean_bwd_kernel<float>, grid_for(n), NT, 0, s, dmean, (const float*)mask, C, HW, n, (float*)dx);
   PUB_LAUNCH_CHECK();
   return 0;
 }

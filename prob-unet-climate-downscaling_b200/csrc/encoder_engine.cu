@@ -180,6 +180,7 @@ int pub_encoder_forward(pub_encoder* e, int B, int H, int W, const float* x_nchw
     ConvParams c{};
     c.x0 = cur; c.c0 = cin; c.ld0 = ld; c.w = pl.wp[k]; c.bias = P[2 * k + 1];
     c.y = pl.act[k]; c.ldy = f; c.B = B; c.H = h; c.W = w; c.cout = f; c.ks = 3; c.relu = 1;
+    c.w_settled = 1;
     PUB_TRY(conv_forward(c, dt, backend, s));
     cur = pl.act[k]; cin = f; ld = f;
   }
@@ -226,6 +227,7 @@ int pub_encoder_backward(pub_encoder* e, int B, int H, int W, const float* dmu, 
     if (k == 0) break;
     ConvParams c{};
     c.x0 = ga; c.c0 = f; c.ld0 = f; c.w = pl.wp[k]; c.y = gb; c.ldy = cin; c.B = B; c.H = h; c.W = w; c.cout = cin; c.ks = 3;
+    c.w_settled = 1;
     if (!pooled_in) { c.mask = pl.act[k - 1]; c.ld_mask = cin; }
     PUB_TRY(conv_forward(c, dt, backend, s));
     if (pooled_in) {

@@ -148,6 +148,7 @@ __device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__
 template <typename T, int MODE>
 __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(GnParams p, const T* __restrict__ dy,
                                                                                float* __restrict__ part) {
+  pdl_enter();
   extern __shared__ float sm[];  // [ppi][V][16]
   constexpr int UNR = MODE == 0 ? 4 : 2;
   const int C = p.c0 + p.c1, V = C / 8;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
 
 // one warp per (b, g): mean / rstd, then the per-channel affine  y = silu(a x + b)
 __global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, int nchunk) {
+  pdl_enter();
   const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= p.B * p.groups) return;
@@ -271,6 +273,7 @@ __global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, i
 // y = resample(dropout(silu(a x + b))); the chunk index runs over INPUT pixels (none / up) or OUTPUT pixels (down)
 template <typename T>
 __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __restrict__ y) {
+  pdl_enter();
   const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
   const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
   if (pr >= ppi) return;
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
 // partials hold P1 = sum du, P2 = sum du*(x - mean);  sum du*xhat = rstd * P2
 __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef,
                                     float* __restrict__ bsum) {
+  pdl_enter();
   const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= p.B * p.groups) return;
@@ -386,6 +390,7 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
 // channel walking the batch serially took 50 us per launch -- 3 ms of a training step).
 __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ bsum, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ dfilm) {
+  pdl_enter();
   const int C = p.c0 + p.c1;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -411,6 +416,7 @@ template <typename T>
 __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
                                                                 const float* __restrict__ bcoef, T* __restrict__ dx,
                                                                 const T* __restrict__ addend, int ld_add) {
+  pdl_enter();
   constexpr int UNR = 2;
   const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
   const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
@@ -518,14 +524,14 @@ int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
   const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
   const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
   dim3 grid(nc, p.B);
-  if (dtype == PUB_BF16) gn_partial_kernel<bf16, 0><<<grid, GN_NT, smem, s>>>(p, nullptr, p.partial);
-  else gn_partial_kernel<float, 0><<<grid, GN_NT, smem, s>>>(p, nullptr, p.partial);
+  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 0>, grid, GN_NT, smem, s, p, nullptr, p.partial);
+  else launch_pdl(gn_partial_kernel<float, 0>, grid, GN_NT, smem, s, p, nullptr, p.partial);
   PUB_LAUNCH_CHECK();
-  gn_finalize_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc);
+  launch_pdl(gn_finalize_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.partial, nc);
   PUB_LAUNCH_CHECK();
   dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), gn_rows(p.H * p.W)), p.B);
-  if (dtype == PUB_BF16) gn_apply_kernel<bf16><<<agrid, GN_NT, 0, s>>>(p, (bf16*)y);
-  else gn_apply_kernel<float><<<agrid, GN_NT, 0, s>>>(p, (float*)y);
+  if (dtype == PUB_BF16) launch_pdl(gn_apply_kernel<bf16>, agrid, GN_NT, 0, s, p, (bf16*)y);
+  else launch_pdl(gn_apply_kernel<float>, agrid, GN_NT, 0, s, p, (float*)y);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -537,19 +543,19 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
   float* bcoef = p.partial + align_up((size_t)p.B * nc * C * 2, 4);  // 16-byte aligned rows of 4 floats
   dim3 grid(nc, p.B);
-  if (dtype == PUB_BF16) gn_partial_kernel<bf16, 1><<<grid, GN_NT, smem, s>>>(p, (const bf16*)dy, p.partial);
-  else gn_partial_kernel<float, 1><<<grid, GN_NT, smem, s>>>(p, (const float*)dy, p.partial);
+  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 1>, grid, GN_NT, smem, s, p, (const bf16*)dy, p.partial);
+  else launch_pdl(gn_partial_kernel<float, 1>, grid, GN_NT, smem, s, p, (const float*)dy, p.partial);
   PUB_LAUNCH_CHECK();
   float* bsum = bcoef + (size_t)p.B * C * 2;
-  gn_bwd_group_kernel<<<cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s>>>(p, p.partial, nc, bcoef, bsum);
+  launch_pdl(gn_bwd_group_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.partial, nc, bcoef, bsum);
   PUB_LAUNCH_CHECK();
-  gn_bwd_param_kernel<<<cdiv((int64_t)C * 32, 256), 256, 0, s>>>(p, bsum, dgamma, dbeta, dfilm);
+  launch_pdl(gn_bwd_param_kernel, cdiv((int64_t)C * 32, 256), 256, 0, s, p, bsum, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   if (dx) {
     if (dtype == PUB_BF16)
-      gn_bwd_apply_kernel<bf16><<<grid, GN_NT, 0, s>>>(p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
+      launch_pdl(gn_bwd_apply_kernel<bf16>, grid, GN_NT, 0, s, p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
     else
-      gn_bwd_apply_kernel<float><<<grid, GN_NT, 0, s>>>(p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
+      launch_pdl(gn_bwd_apply_kernel<float>, grid, GN_NT, 0, s, p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
     PUB_LAUNCH_CHECK();
   }
   return 0;

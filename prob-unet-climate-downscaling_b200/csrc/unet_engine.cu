@@ -185,6 +185,7 @@ ConvParams conv_params(const void* x0, int c0, int ld0, const void* x1, int c1, 
   c.x0 = x0; c.x1 = x1; c.c0 = c0; c.c1 = c1; c.ld0 = ld0; c.ld1 = ld1; c.w = w; c.bias = bias;
   c.res = res; c.ld_res = ld_res; c.mask = nullptr; c.ld_mask = 0; c.y = y; c.ldy = ldy;
   c.B = B; c.H = H; c.W = W; c.cout = cout; c.ks = ks; c.relu = 0;
+  c.w_settled = 1;   // packed by pack_all() at the start of the pass
   return c;
 }
 
