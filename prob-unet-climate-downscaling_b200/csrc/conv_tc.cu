@@ -1148,7 +1148,9 @@ bool wgrad_plan(const WgradParams& p, int es, WgPlan& pl) {
   pl.stages = (int)((212 * 1024) / stage);
   if (pl.stages > 6) pl.stages = 6;
   pl.smem = pl.stages * stage + 1024;
-  int want = cdiv(num_sms(), ctas);
+  // one CTA per SM: the split count is rounded DOWN so that ctas * nsplit <= SMs -- rounding up (e.g. 16 x 10 = 160
+  // CTAs on 148 SMs) leaves a second wave of a few CTAs that doubles the kernel time
+  int want = num_sms() / ctas;
   if (want < 1) want = 1;
   int max_split = pl.tiles_total / 4;  // at least 4 K tiles per CTA
   if (max_split < 1) max_split = 1;
