@@ -318,26 +318,43 @@ __global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restri
 }
 
 // split-K reduction of dW AND the final reduction of the bias-gradient column sums in one launch
-// (blocks [0, nbw): wgrad_reduce_kernel's work; blocks [nbw, ...): colsum_final_kernel's, one warp per channel)
+// (blocks [0, nbw): the dW sums; blocks [nbw, ...): colsum_final_kernel's work, one warp per channel).
+// KL = 1: a thread owns one dW element and walks all splits (8 loads in flight).  KL = 4 (many splits, few outputs:
+// e.g. 148 splits of a 32 -> 32 layer, where 72 blocks of serial 148-term sums took ~12 us): the four warps of a block
+// share 32 consecutive elements, warp w sums splits w, w+4, ..., and warp 0 adds the four partials in fixed order.
+template <int KL>
 __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ part, float* __restrict__ dw,
                                                            int nsplit, int taps, int cout, int cin, int nbw,
                                                            const float* __restrict__ bpart, int nchunk,
                                                            float* __restrict__ dbias, int accumulate) {
   pdl_enter();
+  __shared__ float red[KL][32];
   if ((int)blockIdx.x < nbw) {
     const int64_t n = (int64_t)taps * cout * cin;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int kl = KL == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const int64_t i = KL == 1 ? (int64_t)blockIdx.x * blockDim.x + threadIdx.x
+                              : (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
     float s = 0.f;
-    int k = 0;
-    for (; k + 8 <= nsplit; k += 8) {
-      float v[8];
+    if (i < n) {
+      int k = kl;
+      for (; k + 7 * KL < nsplit; k += 8 * KL) {
+        float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __ldg(part + (int64_t)(k + j) * n + i);
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(part + (int64_t)(k + j * KL) * n + i);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[j];
+        for (int j = 0; j < 8; ++j) s += v[j];
+      }
+      for (; k < nsplit; k += KL) s += __ldg(part + (int64_t)k * n + i);
     }
-    for (; k < nsplit; ++k) s += __ldg(part + (int64_t)k * n + i);
+    if (KL > 1) {
+      red[kl][threadIdx.x & 31] = s;
+      __syncthreads();
+      if (kl != 0) return;
+      s = red[0][threadIdx.x];
+#pragma unroll
+      for (int w = 1; w < KL; ++w) s += red[w][threadIdx.x];
+    }
+    if (i >= n) return;
     const int ci = (int)(i % cin), co = (int)((i / cin) % cout), tap = (int)(i / ((int64_t)cin * cout));
     const int64_t o = ((int64_t)co * cin + ci) * taps + tap;  // OIHW with (ky,kx) == tap
     dw[o] = accumulate ? dw[o] + s : s;
@@ -627,8 +644,14 @@ size_t wgrad_simt_workspace(const WgradParams& p) {
 int wgrad_finish(const float* part, float* dw, int nsplit, int taps, int cout, int cin, const float* bpart, int nchunk,
                  float* dbias, int accumulate, cudaStream_t s) {
   const int64_t n = (int64_t)taps * cout * cin;
-  const int nbw = cdiv(n, 128), nbb = dbias ? cdiv(cout, 4) : 0;
-  launch_pdl(wgrad_finish_kernel, nbw + nbb, 128, 0, s, part, dw, nsplit, taps, cout, cin, nbw, bpart, nchunk, dbias, accumulate);
+  const int nbb = dbias ? cdiv(cout, 4) : 0;
+  if (nsplit >= 32 && n <= 128 * 1024) {
+    const int nbw = cdiv(n, 32);
+    launch_pdl(wgrad_finish_kernel<4>, nbw + nbb, 128, 0, s, part, dw, nsplit, taps, cout, cin, nbw, bpart, nchunk, dbias, accumulate);
+  } else {
+    const int nbw = cdiv(n, 128);
+    launch_pdl(wgrad_finish_kernel<1>, nbw + nbb, 128, 0, s, part, dw, nsplit, taps, cout, cin, nbw, bpart, nchunk, dbias, accumulate);
+  }
   PUB_LAUNCH_CHECK();
   return 0;
 }

@@ -67,6 +67,7 @@ struct GnParams {
   float* stats;                                           // [B][G][2] mean, rstd   (saved for backward)
   float* coef;                                            // [B][C][2] scratch: per-(b,c) affine a,b
   float* partial;                                         // scratch for the two-stage reductions
+  int rows;                                               // pixels per CTA chunk: filled in by gn_forward / gn_backward
 };
 size_t gn_partial_floats(int B, int C, int H, int W);
 // y [B,H',W',C] NHWC dt (contiguous, ld = C)

@@ -15,9 +15,26 @@ namespace pub {
 namespace {
 
 constexpr int GN_NT = 256;
-// pixels per chunk (one CTA): small feature maps get small chunks so that the low-resolution layers still fill the GPU
-// (longer per-thread loops amortise the per-channel constant set-up; >= 4 CTAs per SM remain at B = 64)
-__host__ __device__ inline int gn_rows(int HW) { return HW >= 16384 ? 512 : (HW >= 4096 ? 256 : (HW >= 1024 ? 128 : 64)); }
+// Pixels per chunk (one CTA), GnParams::rows, picked by gn_pick_rows() on the host.  These kernels are bound by the
+// latency chain of a CTA's few load -> compute -> store iterations, not by HBM or issue rate, and a partly filled
+// wave takes as long as a full one (ncu, B = 64: 256 CTAs 23 us, 512 CTAs = 1.15 waves 41 us).  So the chunk count per
+// image is the largest that keeps B * chunks within ONE wave of resident CTAs (3 per SM); beyond one wave (large
+// batches) the old rule -- about 8 vectors per thread -- applies.
+inline int gn_pick_rows(int B, int HW, int C) {
+  const int V = C / 8;
+  const int slots = 3 * num_sms();
+  int n = slots / (B > 0 ? B : 1);                       // chunks per image that still fit one wave
+  const int min_rows = std::max(8, 2 * GN_NT / V);       // >= 2 vectors per thread
+  if (n >= 1) {
+    int rows = (HW + n - 1) / n;
+    if (rows < min_rows) rows = min_rows;
+    // large maps: several waves of the classic 8-vectors-per-thread chunks beat one wave of very long CTAs only
+    // when the tail is small; one wave wins or ties in every case measured, so keep it
+    return rows < HW ? rows : HW;
+  }
+  const int rows = 8 * GN_NT / V;
+  return rows < HW ? rows : HW;
+}
 
 // MUFU-only sigmoid (ex2 + rcp, no IEEE-division subroutine): rel. error ~1e-6, far inside the 1e-4 parity budget.
 // The kernels below are otherwise issue-bound on the division slow path rather than HBM-bound.
@@ -82,6 +99,50 @@ __device__ __forceinline__ const T* vec_ptr(const GnParams& p, int64_t pix, int 
   return c < p.c0 ? (const T*)p.x0 + pix * p.ld0 + c : (const T*)p.x1 + pix * p.ld1 + (c - p.c0);
 }
 constexpr int GN_UNROLL = 4;
+
+// ---- per-thread prefetch ring in shared memory (cp.async, 16-byte granules)
+// A thread's rows r, r + ppi, ... are requested RING_D - 1 iterations ahead into slots only that thread reads back,
+// so there is no block-level synchronisation: cp.async.wait_group orders a thread's own copies.  The loads of the next
+// rows are in flight while the current row is being computed, at no register cost (raw-vector registers held the
+// look-ahead before and capped it at two rows).
+template <typename T> struct RingCfg {
+  static constexpr int HV = sizeof(T) / 2;                  // 16-byte halves per 8-channel vector
+  static constexpr int D = sizeof(T) == 2 ? 4 : 3;          // stages
+};
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// slot of (stage, tensor) for thread t: planes of GN_NT 16-byte cells -> conflict-free 128-bit accesses
+template <typename T, int NTEN>
+__device__ __forceinline__ uint32_t ring_slot(uint32_t ring, int stage, int ten, int half, int t) {
+  return ring + (uint32_t)((((stage * NTEN + ten) * RingCfg<T>::HV + half) * GN_NT + t) << 4);
+}
+template <typename T, int NTEN>
+__device__ __forceinline__ void ring_issue(uint32_t ring, int stage, int ten, int t, const T* src) {
+#pragma unroll
+  for (int h = 0; h < RingCfg<T>::HV; ++h)
+    cp_async16(ring_slot<T, NTEN>(ring, stage, ten, h, t), reinterpret_cast<const char*>(src) + 16 * h);
+}
+template <typename T, int NTEN>
+__device__ __forceinline__ void ring_read(uint32_t ring, int stage, int ten, int t, float (&v)[8]) {
+  uint32_t w[4 * RingCfg<T>::HV];
+#pragma unroll
+  for (int h = 0; h < RingCfg<T>::HV; ++h)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[4 * h]), "=r"(w[4 * h + 1]), "=r"(w[4 * h + 2]), "=r"(w[4 * h + 3])
+                 : "r"(ring_slot<T, NTEN>(ring, stage, ten, h, t)));
+  if (sizeof(T) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(w[i % (4 * RingCfg<T>::HV)]);
+  }
+}
+template <typename T, int NTEN> constexpr size_t ring_bytes() { return (size_t)RingCfg<T>::D * NTEN * RingCfg<T>::HV * GN_NT * 16; }
 
 // coef[b][c][2] -> a[8], bb[8] for channels v*8 .. v*8+7
 __device__ __forceinline__ void load_affine(const float* coef, int b, int C, int v, float (&a)[8], float (&bb)[8]) {
@@ -149,13 +210,12 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(GnParams p, const T* __restrict__ dy,
                                                                                float* __restrict__ part) {
   pdl_enter();
-  extern __shared__ float sm[];  // [ppi][V][16]
-  constexpr int UNR = MODE == 0 ? 4 : 2;
+  extern __shared__ __align__(16) float sm[];  // [ppi][V][16] reduction buffer, then the prefetch ring
   const int C = p.c0 + p.c1, V = C / 8;
   const int ppi = GN_NT / V;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int HW = p.H * p.W;
-  const int rows = gn_rows(HW);
+  const int rows = p.rows;
   const int r0 = chunk * rows, r1 = min(HW, r0 + rows);
   const int t = threadIdx.x;
   const int v = t % V, pr = t / V;
@@ -174,43 +234,46 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
                              : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
       const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
       const T* gb = MODE == 1 ? dy + (int64_t)b * HW * C + c : nullptr;
-      for (int rb = r0 + pr; rb < r1; rb += UNR * ppi) {
-        Raw8<T> xr[UNR], gr[UNR];
+      constexpr int D = RingCfg<T>::D, NTEN = MODE == 0 ? 1 : 2;
+      const uint32_t ring = smem_addr(sm) + (uint32_t)(GN_NT * 16 * sizeof(float));   // behind the reduction buffer
+      const int K = r0 + pr < r1 ? (r1 - r0 - pr + ppi - 1) / ppi : 0;               // rows of this thread
+      auto issue = [&](int k, int stage) {
+        if (k < K) {
+          const int r = r0 + pr + k * ppi;
+          ring_issue<T, NTEN>(ring, stage, 0, t, xb + r * ldx);
+          if (MODE == 1) ring_issue<T, NTEN>(ring, stage, 1, t, gb + (int64_t)r * C);
+        }
+        cp_async_commit();
+      };
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int r = rb + u * ppi;
-          if (r < r1) {
-            xr[u].load(xb + r * ldx);
-            if (MODE == 1) gr[u].load(gb + (int64_t)r * C);
+      for (int k = 0; k < D - 1; ++k) issue(k, k);
+      int stage = 0;
+      for (int k = 0; k < K; ++k) {
+        issue(k + D - 1, stage == 0 ? D - 1 : stage - 1);
+        cp_async_wait<D - 1>();
+        float x[8];
+        ring_read<T, NTEN>(ring, stage, 0, t, x);
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
+        } else {
+          const int r = r0 + pr + k * ppi;
+          float g[8];
+          ring_read<T, NTEN>(ring, stage, 1, t, g);
+          if (p.p_drop > 0.f) {
+            bool keep[8];
+            dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
+            s1[j] += du;
+            s2[j] = fmaf(du, x[j], s2[j]);
           }
         }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int r = rb + u * ppi;
-          if (r < r1) {
-            float x[8];
-            xr[u].unpack(x);
-            if (MODE == 0) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
-            } else {
-              float g[8];
-              gr[u].unpack(g);
-              if (p.p_drop > 0.f) {
-                bool keep[8];
-                dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
-                s1[j] += du;
-                s2[j] = fmaf(du, x[j], s2[j]);
-              }
-            }
-          }
-        }
+        if (++stage == D) stage = 0;
       }
     } else {
       for (int r = r0 + pr; r < r1; r += ppi) {
@@ -283,49 +346,53 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
   if (p.resample != 1) {
     const uint32_t thresh = drop_thresh(p.p_drop);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
-    const int rows = gn_rows(HW);
+    const int rows = p.rows;
     const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
     const int c = v * 8;
     const T* xb = c < p.c0 ? (const T*)p.x0 + (int64_t)b * HW * p.ld0 + c
                            : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
     const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
-    for (int rb = r0 + pr; rb < r1; rb += GN_UNROLL * ppi) {
-      Raw8<T> xr[GN_UNROLL];
+    extern __shared__ __align__(16) uint8_t gn_ring_raw[];
+    const uint32_t ring = smem_addr(gn_ring_raw);
+    constexpr int D = RingCfg<T>::D;
+    const int K = r0 + pr < r1 ? (r1 - r0 - pr + ppi - 1) / ppi : 0;    // rows of this thread
+    auto issue = [&](int k, int stage) {
+      if (k < K) ring_issue<T, 1>(ring, stage, 0, t, xb + (r0 + pr + k * ppi) * ldx);
+      cp_async_commit();
+    };
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
-        const int r = rb + u * ppi;
-        if (r < r1) xr[u].load(xb + r * ldx);
+    for (int k = 0; k < D - 1; ++k) issue(k, k);
+    int stage = 0;
+    for (int k = 0; k < K; ++k) {
+      issue(k + D - 1, stage == 0 ? D - 1 : stage - 1);
+      cp_async_wait<D - 1>();
+      const int r = r0 + pr + k * ppi;
+      const int64_t pix = (int64_t)b * HW + r;
+      float x[8], o[8];
+      ring_read<T, 1>(ring, stage, 0, t, x);
+      if (++stage == D) stage = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = silu_t<T>(fmaf(a[j], x[j], bb[j]));
+      if (p.p_drop > 0.f) {
+        bool keep[8];
+        dropout_keep8(p.seed, p.subseq, pix * C + c, thresh, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
       }
+      if (p.resample == 0) {
+        Vec8<T>::store(y + pix * C + c, o);
+      } else {  // nearest 2x upsample: write the 2x2 children
+        const int yy = r / p.W, xx = r % p.W;
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
-        const int r = rb + u * ppi;
-        if (r >= r1) continue;
-        const int64_t pix = (int64_t)b * HW + r;
-        float x[8], o[8];
-        xr[u].unpack(x);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = silu_t<T>(fmaf(a[j], x[j], bb[j]));
-        if (p.p_drop > 0.f) {
-          bool keep[8];
-          dropout_keep8(p.seed, p.subseq, pix * C + c, thresh, keep);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
-        }
-        if (p.resample == 0) {
-          Vec8<T>::store(y + pix * C + c, o);
-        } else {  // nearest 2x upsample: write the 2x2 children
-          const int yy = r / p.W, xx = r % p.W;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
-            Vec8<T>::store(y + q * C + c, o);
-          }
+        for (int d = 0; d < 4; ++d) {
+          const int64_t q = ((int64_t)b * (p.H * 2) + yy * 2 + (d >> 1)) * (p.W * 2) + xx * 2 + (d & 1);
+          Vec8<T>::store(y + q * C + c, o);
         }
       }
     }
   } else {  // 2x2 mean of the activated values
     const int Ho = p.H / 2, Wo = p.W / 2, HWo = Ho * Wo;
-    const int rows = gn_rows(HW);
+    const int rows = p.rows;
     const int r0 = blockIdx.x * rows, r1 = min(HWo, r0 + rows);
     for (int r = r0 + pr; r < r1; r += ppi) {
       const int yo = r / Wo, xo = r % Wo;
@@ -417,7 +484,6 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
                                                                 const float* __restrict__ bcoef, T* __restrict__ dx,
                                                                 const T* __restrict__ addend, int ld_add) {
   pdl_enter();
-  constexpr int UNR = 2;
   const int C = p.c0 + p.c1, V = C / 8, ppi = GN_NT / V;
   const int b = blockIdx.y, t = threadIdx.x, v = t % V, pr = t / V;
   if (pr >= ppi) return;
@@ -427,7 +493,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
   const uint32_t thresh = drop_thresh(p.p_drop);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const int HW = p.H * p.W;
-  const int rows = gn_rows(HW);
+  const int rows = p.rows;
   const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
   const int c = v * 8;
   if (p.resample == 0) {
@@ -437,43 +503,48 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
     const T* gb = dy + (int64_t)b * HW * C + c;
     const T* ab = addend ? addend + (int64_t)b * HW * ld_add + c : nullptr;
     T* ob = dx + (int64_t)b * HW * C + c;
-    for (int rb = r0 + pr; rb < r1; rb += UNR * ppi) {
-      Raw8<T> xr[UNR], gr[UNR], ar[UNR];
+    extern __shared__ __align__(16) uint8_t gn_ring_raw[];
+    const uint32_t ring = smem_addr(gn_ring_raw);
+    constexpr int D = RingCfg<T>::D;
+    const int K = r0 + pr < r1 ? (r1 - r0 - pr + ppi - 1) / ppi : 0;    // rows of this thread
+    auto issue = [&](int k, int stage) {
+      if (k < K) {
+        const int r = r0 + pr + k * ppi;
+        ring_issue<T, 3>(ring, stage, 0, t, xb + r * ldx);
+        ring_issue<T, 3>(ring, stage, 1, t, gb + (int64_t)r * C);
+        if (ab) ring_issue<T, 3>(ring, stage, 2, t, ab + (int64_t)r * ld_add);
+      }
+      cp_async_commit();
+    };
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int r = rb + u * ppi;
-        if (r < r1) {
-          xr[u].load(xb + r * ldx);
-          gr[u].load(gb + (int64_t)r * C);
-          if (ab) ar[u].load(ab + (int64_t)r * ld_add);
-        }
+    for (int k = 0; k < D - 1; ++k) issue(k, k);
+    int stage = 0;
+    for (int k = 0; k < K; ++k) {
+      issue(k + D - 1, stage == 0 ? D - 1 : stage - 1);
+      cp_async_wait<D - 1>();
+      const int r = r0 + pr + k * ppi;
+      float x[8], g[8], o[8];
+      ring_read<T, 3>(ring, stage, 0, t, x);
+      ring_read<T, 3>(ring, stage, 1, t, g);
+      if (p.p_drop > 0.f) {
+        bool keep[8];
+        dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int r = rb + u * ppi;
-        if (r >= r1) continue;
-        float x[8], g[8], o[8];
-        xr[u].unpack(x);
-        gr[u].unpack(g);
-        if (p.p_drop > 0.f) {
-          bool keep[8];
-          dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
-          o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
-        }
-        if (ab) {
-          float ad[8];
-          ar[u].unpack(ad);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += ad[j];
-        }
-        Vec8<T>::store(ob + (int64_t)r * C, o);
+      for (int j = 0; j < 8; ++j) {
+        const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
+        o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
       }
+      if (ab) {
+        float ad[8];
+        ring_read<T, 3>(ring, stage, 2, t, ad);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += ad[j];
+      }
+      Vec8<T>::store(ob + (int64_t)r * C, o);
+      if (++stage == D) stage = 0;
     }
     return;
   }
@@ -506,7 +577,7 @@ int check(const GnParams& p) {
   return 0;
 }
 
-inline int nchunks(const GnParams& p) { return cdiv((int64_t)p.H * p.W, gn_rows(p.H * p.W)); }
+inline int nchunks(const GnParams& p) { return cdiv((int64_t)p.H * p.W, p.rows); }
 inline int grid_for(int64_t n) {
   int64_t g = (n + GN_NT - 1) / GN_NT;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -516,35 +587,45 @@ inline int grid_for(int64_t n) {
 }  // namespace
 
 size_t gn_partial_floats(int B, int C, int H, int W) {
-  return (size_t)B * cdiv((int64_t)H * W, gn_rows(H * W)) * C * 2 + (size_t)B * C * 6 + 64;
+  return (size_t)B * cdiv((int64_t)H * W, gn_pick_rows(B, H * W, C)) * C * 2 + (size_t)B * C * 6 + 64;
 }
 
-int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s) {
-  PUB_TRY(check(p));
+int gn_forward(const GnParams& p_, void* y, int dtype, cudaStream_t s) {
+  PUB_TRY(check(p_));
+  GnParams p = p_;
+  p.rows = gn_pick_rows(p.B, p.H * p.W, p.c0 + p.c1);
   const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
-  const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
+  const size_t red = (size_t)GN_NT * 16 * sizeof(float);
   dim3 grid(nc, p.B);
-  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 0>, grid, GN_NT, smem, s, p, nullptr, p.partial);
-  else launch_pdl(gn_partial_kernel<float, 0>, grid, GN_NT, smem, s, p, nullptr, p.partial);
+  static bool attr = false;
+  if (!attr) {
+    PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(red + ring_bytes<float, 1>())));
+    PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(red + ring_bytes<float, 2>())));
+    attr = true;
+  }
+  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 0>, grid, GN_NT, red + ring_bytes<bf16, 1>(), s, p, nullptr, p.partial);
+  else launch_pdl(gn_partial_kernel<float, 0>, grid, GN_NT, red + ring_bytes<float, 1>(), s, p, nullptr, p.partial);
   PUB_LAUNCH_CHECK();
   launch_pdl(gn_finalize_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.partial, nc);
   PUB_LAUNCH_CHECK();
-  dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), gn_rows(p.H * p.W)), p.B);
-  if (dtype == PUB_BF16) launch_pdl(gn_apply_kernel<bf16>, agrid, GN_NT, 0, s, p, (bf16*)y);
-  else launch_pdl(gn_apply_kernel<float>, agrid, GN_NT, 0, s, p, (float*)y);
+  dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), p.rows), p.B);
+  if (dtype == PUB_BF16) launch_pdl(gn_apply_kernel<bf16>, agrid, GN_NT, ring_bytes<bf16, 1>(), s, p, (bf16*)y);
+  else launch_pdl(gn_apply_kernel<float>, agrid, GN_NT, ring_bytes<float, 1>(), s, p, (float*)y);
   PUB_LAUNCH_CHECK();
   return 0;
 }
 
-int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend, int ld_add, float* dgamma,
+int gn_backward(const GnParams& p_, const void* dy, void* dx, const void* addend, int ld_add, float* dgamma,
                 float* dbeta, float* dfilm, int dtype, cudaStream_t s) {
-  PUB_TRY(check(p));
+  PUB_TRY(check(p_));
+  GnParams p = p_;
+  p.rows = gn_pick_rows(p.B, p.H * p.W, p.c0 + p.c1);
   const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
-  const size_t smem = (size_t)(GN_NT / V) * V * 16 * sizeof(float);
+  const size_t red = (size_t)GN_NT * 16 * sizeof(float);
   float* bcoef = p.partial + align_up((size_t)p.B * nc * C * 2, 4);  // 16-byte aligned rows of 4 floats
   dim3 grid(nc, p.B);
-  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 1>, grid, GN_NT, smem, s, p, (const bf16*)dy, p.partial);
-  else launch_pdl(gn_partial_kernel<float, 1>, grid, GN_NT, smem, s, p, (const float*)dy, p.partial);
+  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 1>, grid, GN_NT, red + ring_bytes<bf16, 2>(), s, p, (const bf16*)dy, p.partial);
+  else launch_pdl(gn_partial_kernel<float, 1>, grid, GN_NT, red + ring_bytes<float, 2>(), s, p, (const float*)dy, p.partial);
   PUB_LAUNCH_CHECK();
   float* bsum = bcoef + (size_t)p.B * C * 2;
   launch_pdl(gn_bwd_group_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.partial, nc, bcoef, bsum);
@@ -552,10 +633,16 @@ int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend,
   launch_pdl(gn_bwd_param_kernel, cdiv((int64_t)C * 32, 256), 256, 0, s, p, bsum, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   if (dx) {
+    static bool attr = false;
+    if (!attr) {
+      PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes<bf16, 3>()));
+      PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes<float, 3>()));
+      attr = true;
+    }
     if (dtype == PUB_BF16)
-      launch_pdl(gn_bwd_apply_kernel<bf16>, grid, GN_NT, 0, s, p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
+      launch_pdl(gn_bwd_apply_kernel<bf16>, grid, GN_NT, ring_bytes<bf16, 3>(), s, p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
     else
-      launch_pdl(gn_bwd_apply_kernel<float>, grid, GN_NT, 0, s, p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
+      launch_pdl(gn_bwd_apply_kernel<float>, grid, GN_NT, ring_bytes<float, 3>(), s, p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
     PUB_LAUNCH_CHECK();
   }
   return 0;
