@@ -384,11 +384,11 @@ def run_b200(args):
             roof, detail = conv_roofline(model, B, R, pk, pk_kind)
             roof["share_of_step"] = roof["conv_time_per_step_ms"] / line["ms_per_step"]
             # DRAM traffic of the same kernel family over one step, from the committed ncu launch list
-            # (profiles/r01c_launches_step.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed)
+            # (profiles/r01d_launches_step.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed)
             try:
-                fam = json.load(open(os.path.join(ROOT, "profiles", "r01c_launches_step_family.json")))["conv_family"]
+                fam = json.load(open(os.path.join(ROOT, "profiles", "r01d_launches_step_family.json")))["conv_family"]
                 roof["traffic"] = fam["dram_bytes"]
-                roof["traffic_source"] = ("profiles/r01c_launches_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                roof["traffic_source"] = ("profiles/r01d_launches_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
                                           f"{fam['launches']} conv-family launches of one step; ncu share of step {fam['share_of_step']:.3f})")
             except Exception:
                 pass
