@@ -63,7 +63,7 @@ template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
 // Every heavy kernel uses the same decomposition: grid = (pixel chunks, batch); inside a CTA thread t owns the
 // 8-channel vector v = t % V for the rows pr, pr + ppi, ... of the chunk (ppi = 256 / V).  The per-channel
 // constants of that vector (affine a/b, backward c1/c2/c3) are loaded ONCE into registers, so the inner loop is
-// 16/32-byte loads + ~10 FLOP per element -- the only way these passes get near the HBM roofline.
+// 16/32-byte vector traffic (through the cp.async prefetch ring below) + ~10 FLOP per element.
 
 template <typename T>
 __device__ __forceinline__ void load_vec(const GnParams& p, int64_t pix, int v, float (&f)[8]) {
@@ -72,34 +72,11 @@ __device__ __forceinline__ void load_vec(const GnParams& p, int64_t pix, int v, 
   else Vec8<T>::load((const T*)p.x1 + pix * p.ld1 + (c - p.c0), f);
 }
 
-// Raw (still packed) 8-channel vectors: 4 registers for bf16, 8 for f32.  The hot kernels issue the loads of
-// GN_UNROLL rows back to back as raw vectors (memory-level parallelism) and unpack them only when consumed.
-template <typename T> struct Raw8;
-template <> struct Raw8<bf16> {
-  uint4 u;
-  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
-  __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-  }
-};
-template <> struct Raw8<float> {
-  float4 a, b;
-  __device__ __forceinline__ void load(const float* p) {
-    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
-  }
-  __device__ __forceinline__ void unpack(float (&v)[8]) const {
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-};
 template <typename T>
 __device__ __forceinline__ const T* vec_ptr(const GnParams& p, int64_t pix, int v) {
   const int c = v * 8;
   return c < p.c0 ? (const T*)p.x0 + pix * p.ld0 + c : (const T*)p.x1 + pix * p.ld1 + (c - p.c0);
 }
-constexpr int GN_UNROLL = 4;
-
 // ---- per-thread prefetch ring in shared memory (cp.async, 16-byte granules)
 // A thread's rows r, r + ppi, ... are requested RING_D - 1 iterations ahead into slots only that thread reads back,
 // so there is no block-level synchronisation: cp.async.wait_group orders a thread's own copies.  The loads of the next
@@ -204,8 +181,8 @@ __device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__
 // MODE 1: (du, du * (x - mean_g))  -- backward; du = g_y * silu'(a x + b); sum du*xhat = rstd * second sum
 //         (accumulated as sum du*x and corrected by -mean * sum du when the partial is written: 8 fewer live
 //         registers and one fewer FLOP per element in the hot loop)
-// UNROLL rows are loaded back to back as raw vectors before any is consumed; with <= 64 (MODE 0) / <= 80 (MODE 1)
-// registers three to four CTAs share an SM, so one CTA's loads overlap another's arithmetic.
+// Rows arrive through the per-thread cp.async ring (three rows ahead); with <= 64 (MODE 0) / <= 80 (MODE 1)
+// registers three to four CTAs share an SM.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(GnParams p, const T* __restrict__ dy,
                                                                                float* __restrict__ part) {
@@ -478,7 +455,7 @@ __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ bsum, 
 }
 
 // dx = a*du + c2*x + c3 (+ addend);  a = rstd*gamma*(1+scale) is the forward coefficient, (c2, c3) come from the
-// group sums (bcoef[b][c] = (c2, c3)).  Two rows in flight per thread and <= 80 registers (three CTAs per SM).
+// group sums (bcoef[b][c] = (c2, c3)).  x, dy and the addend arrive through the cp.async ring; <= 80 registers.
 template <typename T>
 __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
                                                                 const float* __restrict__ bcoef, T* __restrict__ dx,

@@ -87,6 +87,38 @@ def test_full_size_training_step_is_deterministic_and_finite():
     assert abs(float(keep) - 0.9) < 2e-3
 
 
+def test_programmatic_dependent_launch_changes_nothing_but_timing():
+    """Every conv / GroupNorm / elementwise kernel is launched with programmatic stream serialisation (its prologue and,
+    in the halo conv, the resident-weight TMA run before the previous kernel has finished).  A kernel reading data
+    before its producer has written it would show up here: the full-size training step with the attribute on must be
+    BIT-identical (loss and all 391 gradients) to the same step with ordinary stream serialisation."""
+    import _native as N
+    from climex_synth import make_fields
+    m = canonical_model(compute_dtype="bf16", device="cuda")
+    m.train()
+    f = make_fields(B, R, R, 16, seed=6)
+    x, y = f["inputs"].cuda(), f["targets"].cuda()
+    eps = torch.randn(15, B, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    runs = {}
+    try:
+        for pdl in (0, 1, 1):
+            N.lib().pub_debug_option(b"pdl", pdl)
+            N.manual_seed(91)
+            m.zero_grad(set_to_none=True)
+            total, recon, kl = m.elbo(x, y, None, M=15, eps=eps)
+            total.backward()
+            torch.cuda.synchronize()
+            cur = (float(total.detach()), [p.grad.clone() for p in m.parameters()])
+            if pdl in runs:
+                assert cur[0] == runs[pdl][0]
+            runs[pdl] = cur
+    finally:
+        N.lib().pub_debug_option(b"pdl", 1)
+    assert runs[0][0] == runs[1][0]
+    for g0, g1 in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(g0, g1)
+
+
 def test_full_size_ensemble_crps_properties():
     """100 prior members per field: CRPS >= 0, CRPS of an ensemble whose members all equal the truth is 0, and the
     CRPS kernel is invariant under a permutation of the members."""
