@@ -376,20 +376,21 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
 // taps and channels >= Cout are zero-filled by cp.async (src-size 0), so the inner loop is 9 x CIN plain FMAs.
 // The previous version (direct global loads, one or two pixels in flight per warp) sat on load latency at
 // IPC ~0.17: 0.55 / 0.42 / 0.37 ms for the three first layers of a training step.  part[cta][tap][co][ci].
-template <typename T, int CIN>
+template <typename T, int CIN, int KS>
 __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, float* __restrict__ part, int pix_per_cta) {
   pdl_enter();
   constexpr int ES = sizeof(T), EPC = 16 / ES;   // elements per 16-byte chunk
   constexpr int CPT = 8 / EPC;                   // chunks per padded input pixel: 1 (bf16) / 2 (f32)
   constexpr int NXC = 9 * CPT, NDC = 32 / EPC;   // x / dy chunks per pixel
   constexpr int SLOT = (NXC + NDC) * 16;         // 208 / 416 bytes
-  constexpr int D = 8;                           // pixels in flight per warp
+  constexpr int D = 8;                           // pixels in flight per warp (16 measured no faster)
+  constexpr int TAPS = KS * KS;
   __shared__ __align__(16) uint8_t ring_raw[8 * D * SLOT];
   __shared__ float red[9 * CIN][32];
   const T* x0 = (const T*)p.x0;
   const T* dy = (const T*)p.dy;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cin = p.c0, taps = p.ks * p.ks;
+  const int cin = p.c0, taps = TAPS;
   const int64_t M = (int64_t)p.B * p.H * p.W;
   const int64_t pbeg = (int64_t)blockIdx.x * pix_per_cta, pend = min(M, pbeg + pix_per_cta);
   float acc[9][CIN];
@@ -400,43 +401,49 @@ __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, flo
   // each warp owns a contiguous pixel range
   const int64_t per_warp = (pend - pbeg + 7) / 8;
   const int64_t wbeg = min(pend, pbeg + warp * per_warp), wend = min(pend, wbeg + per_warp);
-  // this lane's chunk of every slot
+  // This lane's chunk of every slot.  NHWC pixels are contiguous, so the source of the chunk for the next pixel is the
+  // previous one plus a constant stride; only the border test needs the (x, y) of the pixel (warp-uniform counters).
   const bool is_x = lane < NXC, is_d = lane >= NXC && lane < NXC + NDC;
   const int tap = is_x ? lane / CPT : 0, hf = lane % CPT;
-  const int ty = p.ks == 3 ? tap / 3 - 1 : 0, tx = p.ks == 3 ? tap % 3 - 1 : 0;   // ks = 1: tap 0 is the centre
-  const bool x_live = is_x && tap < taps;
-  const int x_off = (ty * p.W + tx) * p.ld0 + hf * EPC;                            // elements from the centre pixel
-  const int d_el = blockIdx.y * 32 + (lane - NXC) * EPC;                           // first dy channel of the chunk
-  const bool d_live = is_d && d_el < p.cout;                                       // cout % 8 == 0 (smallc_ok)
+  const int ty = KS == 3 ? tap / 3 - 1 : 0, tx = KS == 3 ? tap % 3 - 1 : 0;   // KS = 1: tap 0 is the centre
+  const bool x_live = is_x && tap < TAPS;
+  const int d_el = blockIdx.y * 32 + (lane - NXC) * EPC;                       // first dy channel of the chunk
+  const bool d_live = is_d && d_el < p.cout;                                   // cout % 8 == 0 (smallc_ok)
+  const bool active = x_live || is_d;
+  const bool nt = x_live && ty < 0, nb = x_live && ty > 0, nl = x_live && tx < 0, nr = x_live && tx > 0;
+  const bool never = is_d && !d_live;                                          // always zero-filled
+  const char* src = is_x ? (const char*)(x0 + wbeg * p.ld0 + ((ty * p.W + tx) * p.ld0 + hf * EPC))
+                         : (const char*)(dy + wbeg * p.ld_dy + (d_live ? d_el : 0));
+  const int64_t step = (int64_t)(is_x ? p.ld0 : p.ld_dy) * ES;
+  const char* safe = is_x ? (const char*)x0 : (const char*)dy;                 // valid address for zero-size copies
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_raw) + (uint32_t)(warp * D * SLOT);
-  // issue stream: pixel mi and its (x, y, b), advanced incrementally (no divisions in the loop)
-  int64_t mi = wbeg;
-  int xi = (int)(wbeg % p.W), yi = (int)((wbeg / p.W) % p.H), bi = (int)(wbeg / ((int64_t)p.W * p.H));
-  auto issue = [&](int slot) {
+  const uint32_t lane_dst = ring + (uint32_t)(lane * 16);
+  int64_t mi = wbeg;                                                           // issue stream
+  int xi = (int)(wbeg % p.W), yi = (int)((wbeg / p.W) % p.H);
+  const int xl = p.W - 1, yl = p.H - 1;
+  uint32_t ioff = 0;                                                           // byte offset of the slot being filled
+  auto issue = [&]() {
     if (mi < wend) {
-      const uint32_t dst = ring + (uint32_t)(slot * SLOT + lane * 16);
-      if (x_live) {
-        const bool oob = (ty < 0 && yi == 0) || (ty > 0 && yi == p.H - 1) || (tx < 0 && xi == 0) || (tx > 0 && xi == p.W - 1);
-        const T* src = x0 + (((int64_t)bi * p.H + yi) * p.W + xi) * p.ld0 + (oob ? hf * EPC : x_off);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(oob ? 0 : 16) : "memory");
-      } else if (is_d) {
-        const T* src = dy + mi * p.ld_dy + (d_live ? d_el : 0);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(d_live ? 16 : 0) : "memory");
-      }
+      const bool oob = never || (nt && yi == 0) || (nb && yi == yl) || (nl && xi == 0) || (nr && xi == xl);
+      if (active)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(lane_dst + ioff), "l"(oob ? safe : src), "r"(oob ? 0 : 16) : "memory");
+      src += step;
       ++mi;
-      if (++xi == p.W) { xi = 0; if (++yi == p.H) { yi = 0; ++bi; } }
+      if (xi == xl) { xi = 0; yi = yi == yl ? 0 : yi + 1; } else ++xi;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    ioff = ioff == (uint32_t)((D - 1) * SLOT) ? 0u : ioff + SLOT;
   };
 #pragma unroll
-  for (int k = 0; k < D - 1; ++k) issue(k);
-  int slot = 0;
+  for (int k = 0; k < D - 1; ++k) issue();
+  uint32_t coff = 0;                                                           // byte offset of the slot being consumed
   for (int64_t m = wbeg; m < wend; ++m) {
     __syncwarp();                                   // every lane has read the slot that is refilled now
-    issue(slot == 0 ? D - 1 : slot - 1);
+    issue();
     asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
     __syncwarp();                                   // ... and every lane's chunk of pixel m has landed
-    const uint32_t sb = ring + (uint32_t)(slot * SLOT);
+    const uint32_t sb = ring + coff;
+    coff = coff == (uint32_t)((D - 1) * SLOT) ? 0u : coff + SLOT;
     float g;
     if (ES == 4) {
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(sb + NXC * 16 + lane * 4));
@@ -446,28 +453,25 @@ __global__ void __launch_bounds__(256, 2) wgrad_smallc_kernel(WgradParams p, flo
       g = __uint_as_float((uint32_t)h << 16);
     }
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (t < taps) {
-        float xv[8];
-        uint32_t w[4 * CPT];
+    for (int t = 0; t < TAPS; ++t) {
+      float xv[8];
+      uint32_t w[4 * CPT];
 #pragma unroll
-        for (int h2 = 0; h2 < CPT; ++h2)
-          if (h2 == 0 || CIN > 4)
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(w[4 * h2]), "=r"(w[4 * h2 + 1]), "=r"(w[4 * h2 + 2]), "=r"(w[4 * h2 + 3])
-                         : "r"(sb + (uint32_t)((t * CPT + h2) * 16)));
-        if (ES == 4) {
+      for (int h2 = 0; h2 < CPT; ++h2)
+        if (h2 == 0 || CIN > 4)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w[4 * h2]), "=r"(w[4 * h2 + 1]), "=r"(w[4 * h2 + 2]), "=r"(w[4 * h2 + 3])
+                       : "r"(sb + (uint32_t)((t * CPT + h2) * 16)));
+      if (ES == 4) {
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) xv[c] = __uint_as_float(w[c % (4 * CPT)]);
-        } else {
+        for (int c = 0; c < CIN; ++c) xv[c] = __uint_as_float(w[c % (4 * CPT)]);
+      } else {
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) xv[c] = __uint_as_float((c & 1) ? (w[(c >> 1) % (4 * CPT)] & 0xFFFF0000u) : (w[(c >> 1) % (4 * CPT)] << 16));
-        }
-#pragma unroll
-        for (int c = 0; c < CIN; ++c) acc[t][c] = fmaf(g, xv[c], acc[t][c]);
+        for (int c = 0; c < CIN; ++c) xv[c] = __uint_as_float((c & 1) ? (w[(c >> 1) % (4 * CPT)] & 0xFFFF0000u) : (w[(c >> 1) % (4 * CPT)] << 16));
       }
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) acc[t][c] = fmaf(g, xv[c], acc[t][c]);
     }
-    if (++slot == D) slot = 0;
   }
   // sum the 8 warps in a fixed order
   for (int w = 0; w < 8; ++w) {
@@ -738,7 +742,11 @@ int wgrad_simt(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int a
     smallc_plan(p, nctas, ppc);
     dim3 grid(nctas, cdiv(p.cout, 32));
     const int cc = p.c0 <= 3 ? 3 : (p.c0 <= 6 ? 6 : 8);
-#define PUB_SMALLC(TT, CC) launch_pdl(wgrad_smallc_kernel<TT, CC>, grid, 256, 0, s, p, part, ppc)
+#define PUB_SMALLC(TT, CC)                                                                   \
+  do {                                                                                       \
+    if (p.ks == 3) launch_pdl(wgrad_smallc_kernel<TT, CC, 3>, grid, 256, 0, s, p, part, ppc); \
+    else launch_pdl(wgrad_smallc_kernel<TT, CC, 1>, grid, 256, 0, s, p, part, ppc);           \
+  } while (0)
     if (dtype == PUB_BF16) { if (cc == 3) PUB_SMALLC(bf16, 3); else if (cc == 6) PUB_SMALLC(bf16, 6); else PUB_SMALLC(bf16, 8); }
     else { if (cc == 3) PUB_SMALLC(float, 3); else if (cc == 6) PUB_SMALLC(float, 6); else PUB_SMALLC(float, 8); }
 #undef PUB_SMALLC
