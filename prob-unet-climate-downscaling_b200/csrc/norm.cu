@@ -77,11 +77,16 @@ __device__ __forceinline__ const T* vec_ptr(const GnParams& p, int64_t pix, int 
   const int c = v * 8;
   return c < p.c0 ? (const T*)p.x0 + pix * p.ld0 + c : (const T*)p.x1 + pix * p.ld1 + (c - p.c0);
 }
-// ---- per-thread prefetch ring in shared memory (cp.async, 16-byte granules)
-// A thread's rows r, r + ppi, ... are requested RING_D - 1 iterations ahead into slots only that thread reads back,
-// so there is no block-level synchronisation: cp.async.wait_group orders a thread's own copies.  The loads of the next
+// ---- per-thread prefetch ring in shared memory (cp.async)
+// A thread's rows r, r + ppi, ... are requested D - 1 iterations ahead into cells only that thread reads back, so
+// there is no block-level synchronisation: cp.async.wait_group orders a thread's own copies.  The loads of the next
 // rows are in flight while the current row is being computed, at no register cost (raw-vector registers held the
-// look-ahead before and capped it at two rows).
+// look-ahead before and capped it at two rows).  Everything per row is incremental -- source pointers advance by a
+// constant byte stride, the stage offsets wrap -- because ncu showed these kernels as much issue-bound as
+// latency-bound.  A stage holds NTEN tensors as planes of GN_NT 16-byte cells (conflict-free 128-bit accesses; two
+// planes per tensor for f32).  (Tried on top of this: the forward pass storing the dropout keep bits, one byte per
+// vector, for the backward kernels to read through the ring instead of re-running Philox -- 108 of their ~300
+// instructions per vector.  Backward kernel times did not move, so they are not issue-bound any more; removed.)
 template <typename T> struct RingCfg {
   static constexpr int HV = sizeof(T) / 2;                  // 16-byte halves per 8-channel vector
   static constexpr int D = sizeof(T) == 2 ? 4 : 3;          // stages
@@ -92,34 +97,66 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// slot of (stage, tensor) for thread t: planes of GN_NT 16-byte cells -> conflict-free 128-bit accesses
-template <typename T, int NTEN>
-__device__ __forceinline__ uint32_t ring_slot(uint32_t ring, int stage, int ten, int half, int t) {
-  return ring + (uint32_t)((((stage * NTEN + ten) * RingCfg<T>::HV + half) * GN_NT + t) << 4);
-}
-template <typename T, int NTEN>
-__device__ __forceinline__ void ring_issue(uint32_t ring, int stage, int ten, int t, const T* src) {
+
+template <typename T, int NTEN> struct RowRing {
+  static constexpr int HV = RingCfg<T>::HV, D = RingCfg<T>::D;
+  static constexpr uint32_t PLANE = GN_NT * 16;
+  static constexpr uint32_t STAGE = NTEN * HV * PLANE;
+  static constexpr size_t BYTES = (size_t)D * STAGE;
+  uint32_t base16;               // this thread's cell in the planes of stage 0
+  uint32_t ioff, coff;           // byte offsets of the stage being filled / consumed
+  int left;                      // rows still to request
+  const char* src[NTEN];         // next row of each tensor (nullptr: tensor absent)
+  int step[NTEN];                // bytes between this thread's consecutive rows
+  __device__ __forceinline__ void init(uint32_t ring, int t, int rows) {
+    base16 = ring + (uint32_t)(t << 4);
+    ioff = coff = 0; left = rows;
 #pragma unroll
-  for (int h = 0; h < RingCfg<T>::HV; ++h)
-    cp_async16(ring_slot<T, NTEN>(ring, stage, ten, h, t), reinterpret_cast<const char*>(src) + 16 * h);
-}
-template <typename T, int NTEN>
-__device__ __forceinline__ void ring_read(uint32_t ring, int stage, int ten, int t, float (&v)[8]) {
-  uint32_t w[4 * RingCfg<T>::HV];
-#pragma unroll
-  for (int h = 0; h < RingCfg<T>::HV; ++h)
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(w[4 * h]), "=r"(w[4 * h + 1]), "=r"(w[4 * h + 2]), "=r"(w[4 * h + 3])
-                 : "r"(ring_slot<T, NTEN>(ring, stage, ten, h, t)));
-  if (sizeof(T) == 2) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(w[i % (4 * RingCfg<T>::HV)]);
+    for (int i = 0; i < NTEN; ++i) { src[i] = nullptr; step[i] = 0; }
   }
-}
-template <typename T, int NTEN> constexpr size_t ring_bytes() { return (size_t)RingCfg<T>::D * NTEN * RingCfg<T>::HV * GN_NT * 16; }
+  __device__ __forceinline__ void issue() {
+    if (left > 0) {
+#pragma unroll
+      for (int i = 0; i < NTEN; ++i)
+        if (src[i]) {
+#pragma unroll
+          for (int h = 0; h < HV; ++h) cp_async16(base16 + ioff + (uint32_t)((i * HV + h) * PLANE), src[i] + 16 * h);
+          src[i] += step[i];
+        }
+      --left;
+    }
+    cp_async_commit();
+    ioff = ioff == (D - 1) * STAGE ? 0u : ioff + STAGE;
+  }
+  __device__ __forceinline__ void prologue() {
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) issue();
+  }
+  // requests the row D - 1 ahead, waits for the current one and returns its stage offset
+  __device__ __forceinline__ uint32_t next() {
+    issue();
+    cp_async_wait<D - 1>();
+    const uint32_t c = coff;
+    coff = coff == (D - 1) * STAGE ? 0u : coff + STAGE;
+    return c;
+  }
+  __device__ __forceinline__ void read(uint32_t stage_off, int ten, float (&v)[8]) const {
+    uint32_t w[4 * HV];
+#pragma unroll
+    for (int h = 0; h < HV; ++h)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w[4 * h]), "=r"(w[4 * h + 1]), "=r"(w[4 * h + 2]), "=r"(w[4 * h + 3])
+                   : "r"(base16 + stage_off + (uint32_t)((ten * HV + h) * PLANE)));
+    if (sizeof(T) == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(w[i % (4 * HV)]);
+    }
+  }
+};
+template <typename T, int NTEN> constexpr size_t ring_bytes() { return RowRing<T, NTEN>::BYTES; }
 
 // coef[b][c][2] -> a[8], bb[8] for channels v*8 .. v*8+7
 __device__ __forceinline__ void load_affine(const float* coef, int b, int C, int v, float (&a)[8], float (&bb)[8]) {
@@ -211,35 +248,28 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
                              : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
       const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
       const T* gb = MODE == 1 ? dy + (int64_t)b * HW * C + c : nullptr;
-      constexpr int D = RingCfg<T>::D, NTEN = MODE == 0 ? 1 : 2;
-      const uint32_t ring = smem_addr(sm) + (uint32_t)(GN_NT * 16 * sizeof(float));   // behind the reduction buffer
+      constexpr int NTEN = MODE == 0 ? 1 : 2;
       const int K = r0 + pr < r1 ? (r1 - r0 - pr + ppi - 1) / ppi : 0;               // rows of this thread
-      auto issue = [&](int k, int stage) {
-        if (k < K) {
-          const int r = r0 + pr + k * ppi;
-          ring_issue<T, NTEN>(ring, stage, 0, t, xb + r * ldx);
-          if (MODE == 1) ring_issue<T, NTEN>(ring, stage, 1, t, gb + (int64_t)r * C);
-        }
-        cp_async_commit();
-      };
-#pragma unroll
-      for (int k = 0; k < D - 1; ++k) issue(k, k);
-      int stage = 0;
+      RowRing<T, NTEN> rr;
+      rr.init(smem_addr(sm) + (uint32_t)(GN_NT * 16 * sizeof(float)), t, K);          // behind the reduction buffer
+      rr.src[0] = (const char*)(xb + (r0 + pr) * ldx); rr.step[0] = (int)(ppi * ldx * (int64_t)sizeof(T));
+      int64_t e = ((int64_t)b * HW + r0 + pr) * C + c;                                // first element of the row vector
+      const int64_t estep = (int64_t)ppi * C;
+      if (MODE == 1) { rr.src[1] = (const char*)(gb + (int64_t)(r0 + pr) * C); rr.step[1] = (int)(estep * (int64_t)sizeof(T)); }
+      rr.prologue();
       for (int k = 0; k < K; ++k) {
-        issue(k + D - 1, stage == 0 ? D - 1 : stage - 1);
-        cp_async_wait<D - 1>();
+        const uint32_t st = rr.next();
         float x[8];
-        ring_read<T, NTEN>(ring, stage, 0, t, x);
+        rr.read(st, 0, x);
         if (MODE == 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
         } else {
-          const int r = r0 + pr + k * ppi;
           float g[8];
-          ring_read<T, NTEN>(ring, stage, 1, t, g);
+          rr.read(st, 1, g);
           if (p.p_drop > 0.f) {
             bool keep[8];
-            dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
+            dropout_keep8(p.seed, p.subseq, e, thresh, keep);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
           }
@@ -250,7 +280,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
             s2[j] = fmaf(du, x[j], s2[j]);
           }
         }
-        if (++stage == D) stage = 0;
+        e += estep;
       }
     } else {
       for (int r = r0 + pr; r < r1; r += ppi) {
@@ -330,34 +360,28 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
                            : (const T*)p.x1 + (int64_t)b * HW * p.ld1 + (c - p.c0);
     const int64_t ldx = c < p.c0 ? p.ld0 : p.ld1;
     extern __shared__ __align__(16) uint8_t gn_ring_raw[];
-    const uint32_t ring = smem_addr(gn_ring_raw);
-    constexpr int D = RingCfg<T>::D;
     const int K = r0 + pr < r1 ? (r1 - r0 - pr + ppi - 1) / ppi : 0;    // rows of this thread
-    auto issue = [&](int k, int stage) {
-      if (k < K) ring_issue<T, 1>(ring, stage, 0, t, xb + (r0 + pr + k * ppi) * ldx);
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int k = 0; k < D - 1; ++k) issue(k, k);
-    int stage = 0;
-    for (int k = 0; k < K; ++k) {
-      issue(k + D - 1, stage == 0 ? D - 1 : stage - 1);
-      cp_async_wait<D - 1>();
-      const int r = r0 + pr + k * ppi;
-      const int64_t pix = (int64_t)b * HW + r;
+    RowRing<T, 1> rr;
+    rr.init(smem_addr(gn_ring_raw), t, K);
+    rr.src[0] = (const char*)(xb + (r0 + pr) * ldx); rr.step[0] = (int)(ppi * ldx * (int64_t)sizeof(T));
+    rr.prologue();
+    int r = r0 + pr;
+    int64_t e = ((int64_t)b * HW + r) * C + c;                          // first element of the row vector
+    const int64_t estep = (int64_t)ppi * C;
+    for (int k = 0; k < K; ++k, r += ppi, e += estep) {
+      const uint32_t st = rr.next();
       float x[8], o[8];
-      ring_read<T, 1>(ring, stage, 0, t, x);
-      if (++stage == D) stage = 0;
+      rr.read(st, 0, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = silu_t<T>(fmaf(a[j], x[j], bb[j]));
       if (p.p_drop > 0.f) {
         bool keep[8];
-        dropout_keep8(p.seed, p.subseq, pix * C + c, thresh, keep);
+        dropout_keep8(p.seed, p.subseq, e, thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
       }
       if (p.resample == 0) {
-        Vec8<T>::store(y + pix * C + c, o);
+        Vec8<T>::store(y + e, o);
       } else {  // nearest 2x upsample: write the 2x2 children
         const int yy = r / p.W, xx = r % p.W;
 #pragma unroll
@@ -481,31 +505,24 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
     const T* ab = addend ? addend + (int64_t)b * HW * ld_add + c : nullptr;
     T* ob = dx + (int64_t)b * HW * C + c;
     extern __shared__ __align__(16) uint8_t gn_ring_raw[];
-    const uint32_t ring = smem_addr(gn_ring_raw);
-    constexpr int D = RingCfg<T>::D;
     const int K = r0 + pr < r1 ? (r1 - r0 - pr + ppi - 1) / ppi : 0;    // rows of this thread
-    auto issue = [&](int k, int stage) {
-      if (k < K) {
-        const int r = r0 + pr + k * ppi;
-        ring_issue<T, 3>(ring, stage, 0, t, xb + r * ldx);
-        ring_issue<T, 3>(ring, stage, 1, t, gb + (int64_t)r * C);
-        if (ab) ring_issue<T, 3>(ring, stage, 2, t, ab + (int64_t)r * ld_add);
-      }
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int k = 0; k < D - 1; ++k) issue(k, k);
-    int stage = 0;
-    for (int k = 0; k < K; ++k) {
-      issue(k + D - 1, stage == 0 ? D - 1 : stage - 1);
-      cp_async_wait<D - 1>();
-      const int r = r0 + pr + k * ppi;
+    int64_t e = ((int64_t)b * HW + r0 + pr) * C + c;                    // first element of the row vector
+    const int64_t estep = (int64_t)ppi * C;
+    RowRing<T, 3> rr;
+    rr.init(smem_addr(gn_ring_raw), t, K);
+    rr.src[0] = (const char*)(xb + (r0 + pr) * ldx); rr.step[0] = (int)(ppi * ldx * (int64_t)sizeof(T));
+    rr.src[1] = (const char*)(gb + (int64_t)(r0 + pr) * C); rr.step[1] = (int)(estep * (int64_t)sizeof(T));
+    if (ab) { rr.src[2] = (const char*)(ab + (int64_t)(r0 + pr) * ld_add); rr.step[2] = (int)((int64_t)ppi * ld_add * (int64_t)sizeof(T)); }
+    rr.prologue();
+    T* op = ob + (int64_t)(r0 + pr) * C;
+    for (int k = 0; k < K; ++k, e += estep, op += estep) {
+      const uint32_t st = rr.next();
       float x[8], g[8], o[8];
-      ring_read<T, 3>(ring, stage, 0, t, x);
-      ring_read<T, 3>(ring, stage, 1, t, g);
+      rr.read(st, 0, x);
+      rr.read(st, 1, g);
       if (p.p_drop > 0.f) {
         bool keep[8];
-        dropout_keep8(p.seed, p.subseq, ((int64_t)b * HW + r) * C + c, thresh, keep);
+        dropout_keep8(p.seed, p.subseq, e, thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
       }
@@ -516,12 +533,11 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
       }
       if (ab) {
         float ad[8];
-        ring_read<T, 3>(ring, stage, 2, t, ad);
+        rr.read(st, 2, ad);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += ad[j];
       }
-      Vec8<T>::store(ob + (int64_t)r * C, o);
-      if (++stage == D) stage = 0;
+      Vec8<T>::store(op, o);
     }
     return;
   }
@@ -563,6 +579,24 @@ inline int grid_for(int64_t n) {
 
 }  // namespace
 
+// dynamic shared memory of the ring kernels (reduction buffer + prefetch ring) goes past the 48 KB default
+static int set_gn_smem_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  const int red = GN_NT * 16 * (int)sizeof(float);
+  const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<bf16, 0>, at, red + (int)ring_bytes<bf16, 1>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 0>, at, red + (int)ring_bytes<float, 1>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<bf16, 1>, at, red + (int)ring_bytes<bf16, 2>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 1>, at, red + (int)ring_bytes<float, 2>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_apply_kernel<bf16>, at, (int)ring_bytes<bf16, 1>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_apply_kernel<float>, at, (int)ring_bytes<float, 1>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<bf16>, at, (int)ring_bytes<bf16, 3>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<float>, at, (int)ring_bytes<float, 3>()));
+  done = true;
+  return 0;
+}
+
 size_t gn_partial_floats(int B, int C, int H, int W) {
   return (size_t)B * cdiv((int64_t)H * W, gn_pick_rows(B, H * W, C)) * C * 2 + (size_t)B * C * 6 + 64;
 }
@@ -574,12 +608,7 @@ int gn_forward(const GnParams& p_, void* y, int dtype, cudaStream_t s) {
   const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
   const size_t red = (size_t)GN_NT * 16 * sizeof(float);
   dim3 grid(nc, p.B);
-  static bool attr = false;
-  if (!attr) {
-    PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(red + ring_bytes<float, 1>())));
-    PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(red + ring_bytes<float, 2>())));
-    attr = true;
-  }
+  PUB_TRY(set_gn_smem_attrs());
   if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 0>, grid, GN_NT, red + ring_bytes<bf16, 1>(), s, p, nullptr, p.partial);
   else launch_pdl(gn_partial_kernel<float, 0>, grid, GN_NT, red + ring_bytes<float, 1>(), s, p, nullptr, p.partial);
   PUB_LAUNCH_CHECK();
@@ -597,6 +626,7 @@ int gn_backward(const GnParams& p_, const void* dy, void* dx, const void* addend
   PUB_TRY(check(p_));
   GnParams p = p_;
   p.rows = gn_pick_rows(p.B, p.H * p.W, p.c0 + p.c1);
+  PUB_TRY(set_gn_smem_attrs());
   const int C = p.c0 + p.c1, V = C / 8, nc = nchunks(p);
   const size_t red = (size_t)GN_NT * 16 * sizeof(float);
   float* bcoef = p.partial + align_up((size_t)p.B * nc * C * 2, 4);  // 16-byte aligned rows of 4 floats
@@ -610,12 +640,6 @@ int gn_backward(const GnParams& p_, const void* dy, void* dx, const void* addend
   launch_pdl(gn_bwd_param_kernel, cdiv((int64_t)C * 32, 256), 256, 0, s, p, bsum, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   if (dx) {
-    static bool attr = false;
-    if (!attr) {
-      PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes<bf16, 3>()));
-      PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes<float, 3>()));
-      attr = true;
-    }
     if (dtype == PUB_BF16)
       launch_pdl(gn_bwd_apply_kernel<bf16>, grid, GN_NT, ring_bytes<bf16, 3>(), s, p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
     else
