@@ -16,7 +16,8 @@ int g_opt_wgrad_box3 = 1;
 int g_opt_fcomb_fwd_mma = 1;
 int g_opt_wgrad_fused_bias = 1;
 int g_opt_pdl = 1;
-unsigned long long g_last_pack_launch = 0;
+cudaStream_t g_pack_stream = nullptr;
+unsigned long long g_since_pack = 0;
 long long* g_halo_trace = nullptr;
 
 void set_error(const char* fmt, ...) {

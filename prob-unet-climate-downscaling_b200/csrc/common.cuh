@@ -52,7 +52,15 @@ extern unsigned long long g_launch_count;  // kernels enqueued by this library (
 // Kernels launched the ordinary way (<<< >>>) in between keep full stream serialisation; in them, and with
 // g_opt_pdl = 0 (pub_debug_option("pdl", 0)), both instructions are no-ops.
 extern int g_opt_pdl;
-extern unsigned long long g_last_pack_launch;  // g_launch_count right after the last weight-pack launch
+// Which stream the last weight-pack kernel ran on and how many launch_pdl() launches followed it ON THAT STREAM
+// (ordinary <<< >>> launches are not counted: under-counting only delays the early weight loads).  The library is
+// driven from one host thread per process (one process per GPU); these are plain globals.
+extern cudaStream_t g_pack_stream;
+extern unsigned long long g_since_pack;
+inline void note_weight_pack(cudaStream_t s) { g_pack_stream = s; g_since_pack = 0; }
+// true when weights packed by this library are complete and visible to a kernel that is launched next on `s` even
+// BEFORE that kernel's grid-dependency wait: at least two trigger-after-wait kernels separate it from the pack
+inline bool weights_settled_on(cudaStream_t s) { return g_opt_pdl && s == g_pack_stream && g_since_pack >= 2; }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -66,6 +74,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = g_opt_pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);   // errors surface in PUB_LAUNCH_CHECK
+  if (s == g_pack_stream) ++g_since_pack;
 }
 #endif
 

@@ -769,7 +769,7 @@ int pack_weight(const float* w, void* out, int cout, int cin, int ks, int dtype,
   if (dtype == PUB_BF16) pack_weight_kernel<bf16><<<cdiv(n, 256), 256, 0, s>>>(w, (bf16*)out, cout, cin, ks, tflip, 0);
   else pack_weight_kernel<float><<<cdiv(n, 256), 256, 0, s>>>(w, (float*)out, cout, cin, ks, tflip, dtype == PUB_TF32);
   PUB_LAUNCH_CHECK();
-  g_last_pack_launch = g_launch_count;
+  note_weight_pack(s);
   return 0;
 }
 
@@ -788,7 +788,7 @@ int pack_weights_batched(const PackEntry* e, int n, int dtype, cudaStream_t s) {
     if (dtype == PUB_BF16) pack_weights_batched_kernel<bf16><<<blocks, 256, 0, s>>>(t, 0);
     else pack_weights_batched_kernel<float><<<blocks, 256, 0, s>>>(t, dtype == PUB_TF32);
     PUB_LAUNCH_CHECK();
-    g_last_pack_launch = g_launch_count;
+    note_weight_pack(s);
   }
   return 0;
 }

@@ -1020,7 +1020,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   a.bias = p.bias; a.res = p.res; a.ld_res = p.ld_res; a.mask = p.mask; a.ld_mask = p.ld_mask;
   a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
   a.trace = g_halo_trace;
-  a.w_early = p.w_settled && g_opt_pdl && g_launch_count - g_last_pack_launch >= 2;
+  a.w_early = p.w_settled && weights_settled_on(s);
   const int n_tiles = p.cout / a.BN;
   const int cblk = cin / KC;
   const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);

@@ -200,13 +200,6 @@ __global__ void global_mean_bwd_kernel(const float* __restrict__ dmean, const T*
 
 }  // namespace
 
-#define DISPATCH_T(dtype, KERNEL, grid, ...)                                            \
-  do {                                                                                  \
-    if ((dtype) == PUB_BF16) launch_pdl(KERNEL<bf16>, grid, NT, 0, s, __VA_ARGS__);             \
-    else launch_pdl(KERNEL<float>, grid, NT, 0, s, __VA_ARGS__);                                \
-    PUB_LAUNCH_CHECK();                                                                 \
-  } while (0)
-
 int resample2x(const void* x, int ld, int C, void* y, int B, int H, int W, int mode, int dtype, cudaStream_t s) {
   PUB_REQUIRE(C % 8 == 0 && ld % 8 == 0, "resample2x: C and ld must be multiples of 8");
   const int64_t n = (int64_t)B * H * W * (C / 8) * (mode == 1 ? 1 : 4) / (mode == 1 ? 4 : 1);

@@ -15,7 +15,7 @@ struct ConvParams {
   void* y; int ldy;
   int B, H, W, cout, ks, relu;
   int round_tf32;  // SIMT path only: round the stored output to tf32 (PUB_TF32 tensors feed kind::tf32 MMAs)
-  int w_settled;   // set by the engines: w was written by this library's pack kernels (g_last_pack_launch tracks them),
+  int w_settled;   // set by the engines: w was written by this library's pack kernels (note_weight_pack tracks them),
                    // so the halo kernel may request it before its grid-dependency wait; 0 for caller-supplied weights
 };
 

@@ -125,3 +125,28 @@ def test_custom_ops_are_registered_with_fake_kernels():
     assert loss.shape == () and dens.shape == (2, 5, 3, 8, 8)
     with pytest.raises(Exception):                       # no CPU kernel is registered
         torch.ops.probunet_b200.kl_normal(*[torch.zeros(2, 4) for _ in range(4)])
+
+
+def test_every_pdl_launched_kernel_waits_for_its_grid_dependency():
+    """Source-level guard: a kernel launched through launch_pdl() may start before its predecessor has finished, so
+    its body must reach pdl_enter() / pdl_wait() before touching global memory.  Every kernel name passed to
+    launch_pdl must therefore contain one of the two calls (the placement is reviewed by hand; its absence is a bug)."""
+    src = {}
+    csrc = os.path.join(PKG, "csrc")
+    for fn in os.listdir(csrc):
+        if fn.endswith((".cu", ".cuh")):
+            src[fn] = open(os.path.join(csrc, fn)).read()
+    launched = set()
+    for text in src.values():
+        launched |= set(re.findall(r"launch_pdl\(\s*([A-Za-z_][A-Za-z0-9_]*)", text))
+    launched -= {"void", "kernel"}                       # the helper's own declaration
+    assert len(launched) >= 20, launched
+    for name in sorted(launched):
+        bodies = []
+        for text in src.values():
+            for m in re.finditer(r"__global__[^;{]*\b" + name + r"\s*\(", text):
+                start = text.index("{", m.end())
+                bodies.append(text[start:start + 6000])
+        assert bodies, f"{name}: launched with launch_pdl but no __global__ definition found"
+        for body in bodies:
+            assert re.search(r"\bpdl_(enter|wait)\(\)", body), f"{name} is launched with launch_pdl() but never waits"
