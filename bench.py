@@ -396,6 +396,7 @@ def run_b200(args):
             line["roofline_detail_top"] = sorted(detail, key=lambda d: -d["us"] * d["count"])[:8]
         except Exception as ex:  # never lose the headline line
             line["roofline"] = {"error": repr(ex)}
+    if rank == 0 and not args.no_aux and world == 1:     # the remaining extras (and the CPU baseline) at N = 1 only
         # ---- auxiliary: ensemble members/s (BASELINE config 4 shape: M=100 prior members per field + CRPS/MAE)
         try:
             import metrics as MET
