@@ -91,27 +91,34 @@ __global__ void __launch_bounds__(NT) ens_loss_kernel(const float* __restrict__ 
     float x[MAXM];
 #pragma unroll
     for (int j = 0; j < MAXM; ++j) x[j] = j < M ? e[(int64_t)j * C * HW] : 0.f;
-    float s1 = 0.f, s2 = 0.f;
+    // pairwise terms once per unordered pair: sum_{j,k} |x_j - x_k| = 2 sum_{j<k} |d|, and sign(x_j - x_k) enters the
+    // gradient of member j with + and of member k with - (ties: sign 0, like torch.abs' backward)
+    float s1 = 0.f, s2 = 0.f, sg[MAXM];
 #pragma unroll
     for (int j = 0; j < MAXM; ++j) {
-      if (j < M) {
-        s1 += fabsf(x[j] - y);
-        float sj = 0.f, sg = 0.f;
+      sg[j] = 0.f;
+      if (j < M) s1 += fabsf(x[j] - y);
+    }
 #pragma unroll
-        for (int k = 0; k < MAXM; ++k) {
-          if (k < M) {
-            const float d = x[j] - x[k];
-            sj += fabsf(d);
-            sg += (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-          }
+    for (int j = 0; j < MAXM; ++j)
+#pragma unroll
+      for (int k = j + 1; k < MAXM; ++k)
+        if (k < M) {
+          const float d = x[j] - x[k];
+          s2 += fabsf(d);
+          const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+          sg[j] += sgn;
+          sg[k] -= sgn;
         }
-        s2 += sj;
-        if (dens) {
+    s2 *= 2.f;
+    if (dens) {
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j)
+        if (j < M) {
           const float dy = x[j] - y;
           const float sy = (dy > 0.f) ? 1.f : ((dy < 0.f) ? -1.f : 0.f);
-          dens[b * M * C * HW + (int64_t)j * C * HW + r] = (sy / M - 2.f * c_pair * sg) * inv_n;
+          dens[b * M * C * HW + (int64_t)j * C * HW + r] = (sy / M - 2.f * c_pair * sg[j]) * inv_n;
         }
-      }
     }
     acc += s1 / M - c_pair * s2;
   }
