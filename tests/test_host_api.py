@@ -150,3 +150,21 @@ def test_every_pdl_launched_kernel_waits_for_its_grid_dependency():
         assert bodies, f"{name}: launched with launch_pdl but no __global__ definition found"
         for body in bodies:
             assert re.search(r"\bpdl_(enter|wait)\(\)", body), f"{name} is launched with launch_pdl() but never waits"
+
+
+def test_reference_arm_of_bench_prints_the_contract_line():
+    """`bench.py --impl reference` runs the CPU oracle's training step on the host cores (no GPU, no CUDA library)
+    and prints ONE JSON line with the keys the driver reads."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_samples_per_s" and d["unit"] == "samples/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["config"]["workload"].startswith("probunet_train_128x128_b64pergpu_afcrps_M15")
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert abs(d["e2e"]["value"] - d["value"]) < 1e-9 * max(1.0, d["value"])
