@@ -146,3 +146,39 @@ def test_climex_transform_oracle_matches_the_real_dataset_class():
             assert rel_err(it[k], g[k][n]) < 1e-6, (k, rel_err(it[k], g[k][n]))
     batch = O.climex_getitem(hr[torch.from_numpy(g["idx"])], stats, s)
     assert rel_err(batch["targets"], g["targets"]) < 1e-6
+
+
+def test_deterministic_unet_architecture_matches_the_real_reference():
+    """BASELINE configs[1] network (model_channels 16, channel_mult [1,4,8,16]) against tests/golden/unet_golden.npz,
+    produced by the REAL src/networks.py (tests/golden/make_unet_golden.py; label_dim = 1 because the snapshot's
+    label_dim = 0 branch raises a shape error -- see the generator's docstring).  Pins: the host mirror's init
+    (bit-identical state_dict), the oracle's forward, the MSE loss and all gradient norms."""
+    import os
+    import networks
+    from helpers import dezero
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "unet_golden.npz"))
+    torch.set_num_threads(8)
+    torch.manual_seed(42)
+    net = networks.UNet(img_resolution=(64, 64), in_channels=3, out_channels=3, label_dim=1, use_diffuse=False)
+    sd0 = net.state_dict()
+    assert list(sd0.keys()) == list(g["sd_keys"]) and int(g["model_channels"]) == 16
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd0.values()]), g["sd_sum"])
+    dezero(net)
+    sd1 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd1.values()]), g["sd1_sum"])
+    np.testing.assert_array_equal(np.array([float(v.double().abs().sum()) for v in sd1.values()]), g["sd1_abssum"])
+    cfg = O.UNetCfg(in_channels=3, out_channels=3, model_channels=16, channel_mult=(1, 4, 8, 16), label_dim=1,
+                    img_resolution=(64, 64))
+    full = {"unet." + k: v for k, v in sd1.items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in full.items() if "resample_filter" not in k}
+    full.update(leaves)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    pred = O.unet_forward(full, x, cfg)
+    loss = torch.nn.functional.mse_loss(pred, y)
+    loss.backward()
+    assert rel_err(pred, g["pred"]) < 1e-5, rel_err(pred, g["pred"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-6 * float(g["loss"])
+    for name, ref in zip(g["grad_names"], g["grad_norm"]):
+        gr = leaves["unet." + str(name)].grad
+        got = 0.0 if gr is None else float(gr.double().norm())
+        assert abs(got - ref) <= 1e-4 * max(ref, 1e-8) + 1e-10, (name, got, ref)
