@@ -408,15 +408,20 @@ def softplus_ref(x: Tensor, threshold: float = 20.0, c: float = 1e-7) -> Tensor:
     return torch.where(x > threshold, x, torch.log(torch.exp(x) + 1.0) - c)
 
 
-def residual_to_real(residual: Tensor, lrinterp: Tensor, std_hr: Tensor) -> Tensor:
-    """residual_to_hr (src/climex_utils.py:277-285, epsilon 1e-10) followed by the inverse
-    variable transforms of results.ipynb cell 2: pr = 86400*softplus(x0),
-    tasmin = x1-273.15, tasmax = softplus(x2, c=0)+x1-273.15.  [..., 3, H, W]."""
-    hr = lrinterp + residual * (std_hr + 1e-10)
-    pr = 86400.0 * softplus_ref(hr[..., 0, :, :])
-    tmin = hr[..., 1, :, :] - 273.15
-    tmax = softplus_ref(hr[..., 2, :, :], c=0.0) + hr[..., 1, :, :] - 273.15
+def invert_transfo_3vars(x: Tensor) -> Tensor:
+    """results.ipynb cell 2 (the function cell 11 maps over every (t, member) before metrics.crps_over_groundtruth):
+    pr = kgm2sTommday(softplus(x0)) (src/climex_utils.py:32-33,42-46), tasmin = KToC(x1) (:49-50),
+    tasmax = KToC(softplus(x2) + x1) -- softplus with its default c = 1e-7 in both places.  [..., 3, H, W].
+    Pinned by tests/golden/climex_golden.npz (tf_stored -> tf_real, produced by the notebook's own source)."""
+    pr = softplus_ref(x[..., 0, :, :]) * 24 * 60 * 60          # kgm2sTommday multiplies in this order (fp32)
+    tmin = x[..., 1, :, :] - 273.15
+    tmax = (softplus_ref(x[..., 2, :, :]) + x[..., 1, :, :]) - 273.15
     return torch.stack([pr, tmin, tmax], dim=-3)
+
+
+def residual_to_real(residual: Tensor, lrinterp: Tensor, std_hr: Tensor) -> Tensor:
+    """residual_to_hr (src/climex_utils.py:277-285, epsilon 1e-10) followed by invert_transfo_3vars."""
+    return invert_transfo_3vars(lrinterp + residual * (std_hr + 1e-10))
 
 
 # --------------------------------------------------------------------------------------

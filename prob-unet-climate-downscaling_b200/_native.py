@@ -247,7 +247,17 @@ class _Rng:
     @classmethod
     def next(cls, n=1):
         if cls.seed is None:
-            cls.seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+            # default: torch's global seed, with the data-parallel rank folded in -- every rank usually calls the same
+            # torch.manual_seed (needed for identical initial weights), and identical dropout masks / eps on all
+            # ranks would correlate the shards of the global batch
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()
+            except Exception:
+                rank = 0
+            cls.seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
         o = cls.offset
         cls.offset += n
         return cls.seed, o
@@ -263,20 +273,33 @@ class _WorkspacePool:
     re-malloc huge blocks (measured: sporadic ~1 s stalls).  Buffers are checked out for forward..backward and
     returned afterwards, so a steady-state training step allocates nothing."""
 
+    MAX_FREE = 6          # buffers kept per device; beyond that the smallest ones are released to the allocator
+
     def __init__(self):
-        self.free = {}
+        self.free = {}    # device -> list of free buffers, most recently returned last
 
     def take(self, nbytes, device):
-        lst = self.free.get((nbytes, device))
-        if lst:
-            return lst.pop()
+        """Best fit: the smallest free buffer that is large enough (a ragged last batch or a validation batch reuses
+        the training step's workspace instead of pinning another multi-GB block)."""
+        lst = self.free.get(device, [])
+        best = None
+        for i, b in enumerate(lst):
+            if b.numel() >= nbytes and (best is None or b.numel() < lst[best].numel()):
+                best = i
+        if best is not None:
+            return lst.pop(best)
         return torch.empty(nbytes, device=device, dtype=torch.uint8)
 
     def give(self, ws):
-        if ws is not None:
-            self.free.setdefault((ws.numel(), ws.device), []).append(ws)
+        if ws is None:
+            return
+        lst = self.free.setdefault(ws.device, [])
+        lst.append(ws)
+        while len(lst) > self.MAX_FREE:
+            lst.pop(min(range(len(lst)), key=lambda i: lst[i].numel()))
 
     def clear(self):
+        """Releases every cached workspace (call when the batch shape changes for good, e.g. after training)."""
         self.free.clear()
 
 
@@ -300,9 +323,19 @@ def _flat_grads(params):
     return flat, views
 
 
-def _notify(flat):
+def _notify(flat, params=None, views=None):
     if grad_ready_callback is not None:
-        grad_ready_callback(flat)
+        grad_ready_callback(flat, params, views)
+
+
+def _consume_ws(ctx, what):
+    """The engines' backward passes consume the workspace saved by forward: a second backward through the same graph
+    (retain_graph=True, two losses sharing the features) would hand the kernels a recycled buffer."""
+    if ctx.ws is None:
+        raise NativeError(f"{what}: backward was already run for this forward (retain_graph / a second backward "
+                          "through the same engine call is not supported: the saved workspace is recycled)")
+    ws, ctx.ws = ctx.ws, None
+    return ws
 
 
 # ======================================================================================
@@ -348,12 +381,12 @@ class _UNetFn(torch.autograd.Function):
             flat[flat.numel() - nz:].zero_()       # map_label / affine weights: exactly-zero gradients
         dx = torch.empty(B, eng.in_ch, H, W, device=dout.device, dtype=torch.float32) if ctx.x_req else None
         dout = dout.contiguous()
+        ws = _consume_ws(ctx, "UNet")
         check(lib().pub_unet_backward(eng.handle, B, H, W, ptr(dout), int(not ctx.nhwc_out), _ptr_table(real),
-                                      _ptr_table(gviews[:len(real)]), ptr(dx), ptr(ctx.ws), C.c_size_t(ctx.nbytes),
+                                      _ptr_table(gviews[:len(real)]), ptr(dx), ptr(ws), C.c_size_t(ctx.nbytes),
                                       C.c_uint64(ctx.seed), int(ctx.training), _backend, stream()), "pub_unet_backward")
-        workspaces.give(ctx.ws)
-        ctx.ws = None
-        _notify(flat)
+        workspaces.give(ws)
+        _notify(flat, list(real) + list(zero), gviews)
         return (None, dx, None, None, None, None) + tuple(gviews)
 
 
@@ -469,12 +502,12 @@ class _EncoderFn(torch.autograd.Function):
         flat, gviews = _flat_grads(list(params))
         dmu = (dmu if dmu is not None else torch.zeros(B, eng.latent, device=flat.device)).contiguous()
         dsigma = (dsigma if dsigma is not None else torch.zeros(B, eng.latent, device=flat.device)).contiguous()
+        ws = _consume_ws(ctx, "AxisAlignedConvGaussian")
         check(lib().pub_encoder_backward(eng.handle, B, H, W, ptr(dmu), ptr(dsigma), _ptr_table(params),
-                                         _ptr_table(gviews), ptr(ctx.ws), C.c_size_t(ctx.nbytes), _backend, stream()),
+                                         _ptr_table(gviews), ptr(ws), C.c_size_t(ctx.nbytes), _backend, stream()),
               "pub_encoder_backward")
-        workspaces.give(ctx.ws)
-        ctx.ws = None
-        _notify(flat)
+        workspaces.give(ws)
+        _notify(flat, list(params), gviews)
         return (None, None, None) + tuple(gviews)
 
 
@@ -628,7 +661,7 @@ class _FcombFn(torch.autograd.Function):
         check(lib().pub_fcomb_backward(C.byref(a), ptr(dout.contiguous()), ptr(dfeat), ptr(dz), ptr(g[0]), ptr(g[1]),
                                        ptr(g[2]), ptr(g[3]), ptr(g[4]), ptr(g[5]), ptr(ws), C.c_size_t(nbytes), stream()),
               "pub_fcomb_backward")
-        _notify(flat)
+        _notify(flat, list(params), g)
         return (None, None, dfeat, dz) + tuple(g)
 
 
@@ -663,9 +696,12 @@ class _EnsLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dloss):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
         d, ctx.dens = ctx.dens, None
         if d is None:
-            return None, None, None, None
+            raise NativeError("ensemble_loss: second backward through the same loss node (its stored gradient is scaled "
+                              "in place and released; retain_graph is not supported)")
         check(lib().pub_scale_by_device_scalar(ptr(d), ptr(dloss.contiguous().float()), C.c_int64(d.numel()), stream()),
               "pub_scale_by_device_scalar")
         return d, None, None, None
@@ -695,9 +731,11 @@ class _L1Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dl, _dpv):
+        if not ctx.needs_input_grad[0]:
+            return None, None
         d, ctx.dout = ctx.dout, None
         if d is None:
-            return None, None
+            raise NativeError("l1_loss: second backward through the same loss node (retain_graph is not supported)")
         check(lib().pub_scale_by_device_scalar(ptr(d), ptr(dl.contiguous().float()), C.c_int64(d.numel()), stream()),
               "pub_scale_by_device_scalar")
         return d, None
@@ -730,9 +768,11 @@ class _MsSsimFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dl, _dw, _dm):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
         d, ctx.dpred = ctx.dpred, None
         if d is None:
-            return None, None, None, None, None
+            raise NativeError("wmse_ms_ssim: second backward through the same loss node (retain_graph is not supported)")
         check(lib().pub_scale_by_device_scalar(ptr(d), ptr(dl.contiguous().float()), C.c_int64(d.numel()), stream()),
               "pub_scale_by_device_scalar")
         return d, None, None, None, None

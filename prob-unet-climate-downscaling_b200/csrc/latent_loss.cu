@@ -196,11 +196,11 @@ __global__ void __launch_bounds__(128) metrics_kernel(const float* __restrict__ 
       if (transform) {
         const float* li = lrinterp + ((int64_t)t * C) * HW + p;
         v = li[(int64_t)c * HW] + v * (std_hr[c] + 1e-10f);
-        if (c == 0) v = 86400.f * softplus_ref(v, 1e-7f);
+        if (c == 0) v = softplus_ref(v, 1e-7f) * 24.f * 60.f * 60.f;   // kgm2sTommday's own multiplication order
         else if (c == 1) v = v - 273.15f;
         else {
           const float v1 = li[(int64_t)HW] + pj[(int64_t)HW] * (std_hr[1] + 1e-10f);
-          v = softplus_ref(v, 0.f) + v1 - 273.15f;
+          v = (softplus_ref(v, 1e-7f) + v1) - 273.15f;   // results.ipynb cell 2: softplus default c, KToC of the sum
         }
       }
       x[j] = v; mean += v; s1 += fabsf(v - y);

@@ -24,27 +24,56 @@ def shard_range(n_items, rank, world):
 
 
 class GradSynchronizer:
-    """Sums every flat gradient buffer the engines report across ranks."""
+    """Sums every flat gradient buffer the engines report across ranks.
+
+    Contract (checked, not assumed): the engines hand autograd VIEWS of the flat buffer as the parameter gradients; with
+    ``zero_grad(set_to_none=True)`` autograd stores those views as ``p.grad`` itself, so the in-place all-reduce of the
+    flat buffer IS the reduction of ``p.grad``.  ``wait_all()`` verifies that aliasing for every parameter and raises
+    if autograd accumulated into an older ``p.grad`` instead (``zero_grad(set_to_none=False)`` or gradient accumulation:
+    the reduced values would never reach ``p.grad`` and the ranks would silently diverge).  A new backward while the
+    previous step's collectives were never consumed through ``wait_all()`` (an optimizer that does not know about the
+    synchronizer) raises too.  ``FusedAdamW.step()`` calls ``wait_all()`` and folds 1/world into its update; for any
+    other optimizer call ``sync.wait_all(average=True)`` before ``optimizer.step()``."""
 
     def __init__(self, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.calls = 0
         self.bytes = 0
-        self.pending = []          # (work handle, buffer kept alive until the wait)
+        self.pending = []          # (work handle, flat buffer kept alive until the wait, params, views)
 
-    def __call__(self, flat):
+    def __call__(self, flat, params=None, views=None):
+        if params:
+            for _, _, old_params, _ in self.pending:
+                if old_params and old_params[0] is params[0]:      # the same sub-network reported twice
+                    self.pending.clear()
+                    raise RuntimeError("GradSynchronizer: a new backward started but the previous step's gradient "
+                                       "all-reduces were never consumed -- call sync.wait_all(average=True) before "
+                                       "optimizer.step() (FusedAdamW does it itself)")
         self.calls += 1
         self.bytes += flat.numel() * flat.element_size()
+        work = None
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self.pending.append((work, flat))
+        self.pending.append((work, flat, params, views))
 
-    def wait_all(self):
+    def wait_all(self, average=False):
         """Makes the current stream wait for every collective issued since the last call (stream-ordered for
-        NCCL: no host block; blocking for gloo).  Must run before the gradients are consumed."""
-        for work, _ in self.pending:
-            work.wait()
+        NCCL: no host block; blocking for gloo), checks that every reduced view is the parameter's ``.grad``, and
+        (``average=True``, for optimizers other than FusedAdamW) divides the sums by the world size."""
+        for work, flat, params, views in self.pending:
+            if work is not None:
+                work.wait()
+            if params is not None:
+                for p, v in zip(params, views):
+                    if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                        self.pending.clear()
+                        raise RuntimeError(
+                            "GradSynchronizer: a parameter's .grad is not the all-reduced buffer (autograd accumulated "
+                            "into an existing .grad).  Use optimizer.zero_grad(set_to_none=True) every step; gradient "
+                            "accumulation across backward passes is not supported with the synchronizer installed.")
+            if average and self.world > 1:
+                flat.div_(self.world)
         self.pending.clear()
 
     def install(self):

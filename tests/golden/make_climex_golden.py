@@ -1,7 +1,10 @@
 """Golden vectors of the reference's dataset transform, produced by the REAL climex2torch class
 (/root/reference/src/climex_utils.py) in this container: its module-level imports (dask, xarray, cartopy,
 matplotlib ...) are stubbed, the instance is created without __init__ (which would read NetCDF files) and given a
-synthetic `hr` tensor; __getitem__ / compute_stats / residual_to_hr then run unmodified.
+synthetic `hr` tensor; __getitem__ / compute_stats / residual_to_hr then run unmodified.  Also pinned here: the
+inverse variable transforms softplus / KToC / kgm2sTommday (src/climex_utils.py:32-50), their composition
+invert_transfo_3vars (results.ipynb cell 2, executed from the notebook's own source) and metrics.compute_mae
+(src/metrics.py:48-71).
 
     python tests/golden/make_climex_golden.py        # writes tests/golden/climex_golden.npz
 """
@@ -35,5 +38,36 @@ for k in ("inputs", "targets", "lr", "lrinterp"):
 res = torch.randn(3, 3, H, H, generator=g)
 out["residual"] = res.numpy()
 out["residual_to_hr"] = torch.stack([ds.residual_to_hr(res[i], items[i]["lrinterp"]) for i in range(3)]).numpy()
+
+# ---- inverse variable transforms (src/climex_utils.py:32-50) and their composition in results.ipynb cell 2
+# (invert_transfo_3vars, the function cell 11 maps over every (t, member) before metrics.crps_over_groundtruth)
+xs = torch.cat([torch.randn(4000, generator=g) * 6.0, torch.tensor([19.9999, 20.0, 20.0001, 25.0, 80.0, -30.0, 0.0])])
+out["tf_x"] = xs.numpy()
+out["tf_softplus"] = CU.softplus(xs.clone()).numpy()               # the real functions work in place: clone
+out["tf_softplus_c0"] = CU.softplus(xs.clone(), c=0).numpy()
+out["tf_ktoc"] = CU.KToC(xs.clone()).numpy()
+out["tf_mmday"] = CU.kgm2sTommday(xs.clone()).numpy()
+import json  # noqa: E402
+nb = json.load(open(os.environ.get("PROBUNET_REFERENCE", "/root/reference") + "/src/notebooks/results.ipynb"))
+cell2 = "".join(nb["cells"][2]["source"])
+assert "def invert_transfo_3vars" in cell2
+ns = {"torch": torch}
+exec(compile(cell2, "results.ipynb:cell2", "exec"), ns)
+stored = torch.randn(5, 3, 16, 16, generator=g) * torch.tensor([3.0, 9.0, 4.0]).view(1, 3, 1, 1) + torch.tensor([-1.0, 272.0, 3.0]).view(1, 3, 1, 1)
+out["tf_stored"] = stored.numpy()
+out["tf_real"] = ns["invert_transfo_3vars"](stored.clone()).numpy()
+
+# ---- metrics.compute_mae (src/metrics.py:48-71) run for real; only the module-level `import pysteps` is stubbed
+# (compute_mae never calls it).  crps_over_groundtruth needs pysteps itself and stays a restatement (oracle header).
+sys.modules["pysteps"] = types.ModuleType("pysteps")
+import metrics as RM  # noqa: E402
+gt = torch.randn(4, 3, 12, 12, generator=g) * 5
+pe = gt.unsqueeze(1) + torch.randn(4, 7, 3, 12, 12, generator=g)
+mm, ma = RM.compute_mae(gt, pe)
+md, mda = RM.compute_mae(gt, pe[:, 0])
+out["mae_gt"], out["mae_pred"] = gt.numpy(), pe.numpy()
+out["mae_ens"] = np.stack([ma[v] for v in ("pr", "tasmin", "tasmax")], axis=1)
+out["mae_det"] = np.stack([mda[v] for v in ("pr", "tasmin", "tasmax")], axis=1)
+out["mae_ens_means"] = np.array([mm[v] for v in ("pr", "tasmin", "tasmax")])
 np.savez_compressed(os.path.join(HERE, "climex_golden.npz"), **out)
 print("wrote", os.path.join(HERE, "climex_golden.npz"), {k: v.shape for k, v in out.items()})

@@ -90,6 +90,13 @@ def grads_summary(model):
     return names, np.array(norms)
 
 
+def grads_projection(model):
+    """Two signed projections per gradient tensor (helpers.grad_projection): unlike a norm they change when a
+    gradient is transposed, mirrored or permuted, so they pin every one of the 391 gradients element-wise."""
+    from helpers import grad_projection
+    return np.array([[0.0, 0.0] if p.grad is None else grad_projection(p.grad) for _, p in model.named_parameters()])
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     prob_unet, utils = import_reference()
@@ -158,6 +165,7 @@ def main():
     out["A_crps_loss"] = float(utils.crps_loss(ens.detach(), y))
     names, norms = grads_summary(model)
     out["grad_names"], out["A_afcrps_gradnorm"] = np.array(names), norms
+    out["A_afcrps_gradproj"] = grads_projection(model)
     gsd = dict(model.named_parameters())
     for k in ["fcomb.layers.0.weight", "fcomb.layers.4.bias", "posterior.conv_mu.weight",
               "prior.conv_log_sigma.bias", "unet.out_norm.weight", "unet.enc.64x64_block0.skip.weight",
@@ -169,6 +177,7 @@ def main():
     total.backward()
     out["A_l1_total"], out["A_l1_l1"] = float(total), float(l1)
     _, out["A_l1_gradnorm"] = grads_summary(model)
+    out["A_l1_gradproj"] = grads_projection(model)
 
     # ---- case A-drop: train-mode dropout with injected masks (L1 ELBO) ----
     model.train()
@@ -182,6 +191,7 @@ def main():
     out["A_drop_maskbits"] = np.concatenate([np.packbits(m.numpy().reshape(-1)) for m in di.masks])
     out["A_drop_maskshapes"] = np.array([list(m.shape) for m in di.masks])
     _, out["A_drop_l1_gradnorm"] = grads_summary(model)
+    out["A_drop_l1_gradproj"] = grads_projection(model)
 
     # ---- case B: active MS-SSIM ELBO (src/prob_unet.py:229-267) at 128x128, B=1 ----
     f = make_fields(1, 128, 128, lowres_scale=16, seed=1234 + 3)
@@ -195,6 +205,7 @@ def main():
     out["B_total"], out["B_recon"], out["B_kl"] = float(total), float(recon[0]), klb.detach().numpy()
     out["B_wmse"], out["B_msssim_loss"] = float(wmse), float(msl)
     _, out["B_gradnorm"] = grads_summary(model)
+    out["B_gradproj"] = grads_projection(model)
     with torch.no_grad():
         fb = model.unet(xb)
         out["B_unet_sum"], out["B_unet_abssum"] = float(fb.double().sum()), float(fb.double().abs().sum())

@@ -46,6 +46,20 @@ def rel_err(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
+def grad_projection(g):
+    """(g . r1, g . r2) in float64 with r1[k] = sin(1 + 0.7311 k), r2[k] = cos(0.1 + 2.399963 k) over the flattened
+    (reference OIHW / row-major) tensor: closed-form, box-independent signed checksums of a gradient."""
+    v = torch.as_tensor(g).detach().double().cpu().reshape(-1).numpy()
+    k = np.arange(v.size, dtype=np.float64)
+    return [float(np.dot(v, np.sin(1.0 + 0.7311 * k))), float(np.dot(v, np.cos(0.1 + 2.399963 * k)))]
+
+
+def proj_close(got, ref, norm, tol):
+    """|projection error| <= tol * ||g|| * sqrt(n/2)-free bound: a projection of a vector with relative error e has
+    absolute error <= e * ||g|| * ||r||/sqrt(n) on average; we compare against tol * ||g||."""
+    return abs(got[0] - ref[0]) <= tol * norm + 1e-12 and abs(got[1] - ref[1]) <= tol * norm + 1e-12
+
+
 def unpack_masks(golden, topology_keys):
     """Dropout keep-masks stored by make_golden (packed bits, reference call order) -> {block key: bool tensor}."""
     shapes = golden["A_drop_maskshapes"]

@@ -5,13 +5,26 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import canonical_model, rel_err, unpack_masks
+from helpers import canonical_model, grad_projection, proj_close, rel_err, unpack_masks
 from oracle import probunet_oracle as O
 
 pytestmark = pytest.mark.gpu
 CFG = O.ProbUNetCfg()
-TOL = {"fp32": 1e-4, "bf16": 1e-2}
-GTOL = {"fp32": 2e-3, "bf16": 6e-2}     # per-tensor gradient rel-err (391 tensors; tiny-norm tensors are noisier)
+TOL = {"fp32": 1e-4, "bf16": 1e-2}      # BASELINE.json north_star: outputs, losses, KL
+# Gradients are not covered by north_star's output tolerances; every one of the 391 tensors is compared ELEMENT-WISE
+# (||g - g_ref|| / ||g_ref||) with the live oracle, whose own gradients are pinned by signed projections of the real
+# reference's (tests/test_oracle_golden.py).  bf16 activations put ~1e-2 of rounding noise on every backward operand.
+GTOL = {"fp32": 2e-3, "bf16": 1.2e-1}
+GTOL_NORM = {"fp32": 2e-3, "bf16": 6e-2}
+
+
+def oracle_grads(sd, fn):
+    """Runs `fn(full_state_dict)` through the oracle with every parameter a leaf; -> (outputs, {name: grad})."""
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "resample_filter" not in k}
+    full = dict(sd); full.update(leaves)
+    out = fn(full)
+    out[0].backward()
+    return out, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
 
 
 @pytest.fixture(scope="module", params=["fp32", "bf16"])
@@ -45,7 +58,7 @@ def test_prior_posterior_heads_and_kl(setup, golden):
         assert rel_err(q.base_dist.loc, golden["A_post_mu"]) < TOL[name]
         assert rel_err(q.base_dist.scale, golden["A_post_sigma"]) < TOL[name]
         kl = N.kl_normal(q.base_dist.loc, q.base_dist.scale, p.base_dist.loc, p.base_dist.scale)
-        assert rel_err(kl, golden["A_kl"]) < 5 * TOL[name]
+        assert rel_err(kl, golden["A_kl"]) < TOL[name]
         # torch.distributions interop (latent-exploration scripts use kl_divergence / base_dist)
         kl_t = torch.distributions.kl.kl_divergence(q, p)
         assert rel_err(kl, kl_t) < 1e-5
@@ -78,15 +91,28 @@ def test_fcomb_public_call_with_expanded_features(setup, golden):
         assert rel_err(oe, ref) < 1e-4
 
 
-def _check_grads(m, names, ref_norms, tol, sd=None, ref_grads=None):
-    bad = []
-    for n, r in zip(names, ref_norms):
-        g = dict(m.named_parameters())[n].grad
+def _check_grads(m, names, ref_norms, tol, ref_grads=None, elem_tol=None, ref_proj=None):
+    """Every gradient against (a) the golden norm of the real reference, (b) ELEMENT-WISE the oracle's gradient,
+    (c) the golden signed projections (catch a transposed / mirrored / permuted gradient with the right norm)."""
+    bad, worst = [], (0.0, None)
+    params = dict(m.named_parameters())
+    for i, (n, r) in enumerate(zip(names, ref_norms)):
+        n = str(n)
+        g = params[n].grad
         assert g is not None, f"{n} has no gradient"
         gn = float(g.double().norm())
         if abs(gn - r) > tol * max(r, 1e-6) + 1e-9:
-            bad.append((n, gn, float(r)))
-    assert not bad, f"{len(bad)} gradient norms off: {bad[:8]}"
+            bad.append(("norm", n, gn, float(r)))
+        if ref_grads is not None and float(r) > 1e-7:
+            e = rel_err(g, ref_grads[n])
+            worst = max(worst, (e, n))
+            if e > elem_tol:
+                bad.append(("elem", n, e))
+        if ref_proj is not None and float(r) > 1e-7:
+            if not proj_close(grad_projection(g), ref_proj[i], float(r), 3 * (elem_tol or tol)):
+                bad.append(("proj", n, grad_projection(g), list(ref_proj[i]), float(r)))
+    assert not bad, f"{len(bad)} gradient checks failed (worst element-wise {worst}): {bad[:8]}"
+    return worst
 
 
 def test_elbo_afcrps_loss_and_all_gradients(setup, golden):
@@ -96,10 +122,12 @@ def test_elbo_afcrps_loss_and_all_gradients(setup, golden):
     m.zero_grad(set_to_none=True)
     total, recon, kl = m.elbo(x, y, None, M=3, eps=eps)
     total.backward()
-    assert abs(float(total) - float(golden["A_afcrps_total"])) / abs(float(golden["A_afcrps_total"])) < 5 * TOL[name]
+    assert abs(float(total) - float(golden["A_afcrps_total"])) / abs(float(golden["A_afcrps_total"])) < TOL[name]
     assert abs(recon[0] - float(golden["A_afcrps_crps"])) / float(golden["A_afcrps_crps"]) < 5e-3   # CRPS within 0.5 %
-    assert rel_err(kl, golden["A_kl"]) < 5 * TOL[name]
-    _check_grads(m, list(golden["grad_names"]), golden["A_afcrps_gradnorm"], GTOL[name])
+    assert rel_err(kl, golden["A_kl"]) < TOL[name]
+    _, ref = oracle_grads(sd, lambda s_: O.elbo(s_, CFG, x.cpu(), y.cpu(), eps.cpu(), "afcrps"))
+    _check_grads(m, list(golden["grad_names"]), golden["A_afcrps_gradnorm"], GTOL_NORM[name], ref, GTOL[name],
+                 golden["A_afcrps_gradproj"])
     for k in golden.files:
         if k.startswith("A_afcrps_grad::"):
             g = dict(m.named_parameters())[k.split("::")[1]].grad
@@ -116,9 +144,11 @@ def test_elbo_l1_loss_and_gradients(setup, golden):
     total, per_var, kl, kl2 = m.elbo(x, y, None, eps=eps[:1])
     total.backward()
     m.loss_type = "afcrps"
-    assert abs(float(total) - float(golden["A_l1_total"])) / abs(float(golden["A_l1_total"])) < 5 * TOL[name]
+    assert abs(float(total) - float(golden["A_l1_total"])) / abs(float(golden["A_l1_total"])) < TOL[name]
     assert len(per_var) == 3 and kl2.shape == (2,)
-    _check_grads(m, list(golden["grad_names"]), golden["A_l1_gradnorm"], GTOL[name])
+    _, ref = oracle_grads(sd, lambda s_: O.elbo(s_, CFG, x.cpu(), y.cpu(), eps[:1].cpu(), "l1"))
+    _check_grads(m, list(golden["grad_names"]), golden["A_l1_gradnorm"], GTOL_NORM[name], ref, GTOL[name],
+                 golden["A_l1_gradproj"])
 
 
 def test_train_mode_dropout_matches_oracle_with_exported_masks(setup, golden):
@@ -268,14 +298,14 @@ def test_elbo_msssim_variant_at_128(golden):
         total, recon, kl, wmse, ms = m.elbo(x, y, None, M=eps.shape[0], eps=eps)
         total.backward()
         assert isinstance(recon, list) and isinstance(wmse, float) and isinstance(ms, float)
-        assert abs(float(total) - float(golden["B_total"])) / abs(float(golden["B_total"])) < 5 * TOL[name]
-        assert rel_err(kl, golden["B_kl"]) < 5 * TOL[name]
-        assert abs(wmse - float(golden["B_wmse"])) / float(golden["B_wmse"]) < 5 * TOL[name]
+        assert abs(float(total) - float(golden["B_total"])) / abs(float(golden["B_total"])) < TOL[name]
+        assert rel_err(kl, golden["B_kl"]) < TOL[name]
+        assert abs(wmse - float(golden["B_wmse"])) / float(golden["B_wmse"]) < 2 * TOL[name]   # squares the output error
         assert abs(recon[0] - float(golden["B_recon"])) / abs(float(golden["B_recon"])) < 2e-2
         assert abs(ms - float(golden["B_msssim_loss"])) / float(golden["B_msssim_loss"]) < 2e-2
         names, norms = list(golden["grad_names"]), golden["B_gradnorm"]
         kl_driven = [i for i, n in enumerate(names) if n.startswith("prior.")]
-        _check_grads(m, [names[i] for i in kl_driven], [norms[i] for i in kl_driven], GTOL[name])
+        _check_grads(m, [names[i] for i in kl_driven], [norms[i] for i in kl_driven], GTOL_NORM[name])
         for n, p_ in m.named_parameters():
             assert p_.grad is not None and bool(torch.isfinite(p_.grad).all()), n
 
@@ -434,13 +464,13 @@ def test_elbo_on_a_non_square_grid_matches_the_oracle(name):
     m.zero_grad(set_to_none=True)
     total, recon, kl = m.elbo(x.cuda(), y.cuda(), None, M=3, eps=eps.cuda())
     total.backward()
-    assert abs(float(total) - float(rt[0])) / abs(float(rt[0])) < 5 * TOL[name], (float(total), float(rt[0]))
+    assert abs(float(total) - float(rt[0])) / abs(float(rt[0])) < TOL[name], (float(total), float(rt[0]))
     bad = []
     for n, p in m.named_parameters():
         r = leaves[n].grad
         if r is None or float(r.norm()) < 1e-7:
             continue
-        gn, rn = float(p.grad.double().norm()), float(r.double().norm())
-        if abs(gn - rn) > GTOL[name] * rn + 1e-9:
-            bad.append((n, gn, rn))
+        e = rel_err(p.grad, r)                      # element-wise, every tensor
+        if e > GTOL[name]:
+            bad.append((n, e))
     assert not bad, bad[:6]

@@ -70,6 +70,22 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_workspace_pool_reuses_the_best_fit_and_stays_bounded():
+    import _native
+    pool = _native._WorkspacePool()
+    dev = torch.device("cpu")
+    big, small = pool.take(1000, dev), pool.take(100, dev)
+    pool.give(big); pool.give(small)
+    assert pool.take(90, dev) is small                 # ragged last batch: the smallest buffer that is large enough
+    assert pool.take(500, dev) is big                  # a smaller request reuses the big block instead of pinning another
+    assert pool.take(2000, dev).numel() == 2000        # nothing fits: allocate
+    for n in range(10):
+        pool.give(torch.empty(10 + n, dtype=torch.uint8))
+    assert len(pool.free[dev]) == pool.MAX_FREE and min(b.numel() for b in pool.free[dev]) == 14
+    pool.clear()
+    assert not pool.free
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
@@ -88,6 +104,40 @@ assert not sync.pending
 assert torch.allclose(flat, torch.full((1000,), 3.0)), flat[:4]
 assert torch.allclose(flat2, torch.full((10,), 30.0)), flat2[:4]
 assert sync.calls == 2 and sync.bytes == 4040 and sync.world == 2
+# the reduced buffer must BE the parameters' .grad (what autograd does with zero_grad(set_to_none=True)) ...
+p1, p2 = torch.nn.Parameter(torch.zeros(6)), torch.nn.Parameter(torch.zeros(2, 2))
+flat3 = torch.arange(10.) * (r + 1)
+views = [flat3[:6].view(6), flat3[6:].view(2, 2)]
+p1.grad, p2.grad = views
+_native._notify(flat3, [p1, p2], views)
+sync.wait_all()
+assert torch.equal(p1.grad, torch.arange(6.) * 3) and torch.equal(p2.grad.reshape(-1), torch.arange(6., 10.) * 3)
+# ... averaged for optimizers that do not fold 1/world into their update
+flat4 = torch.arange(10.) * (r + 1)
+views = [flat4[:6].view(6), flat4[6:].view(2, 2)]
+p1.grad, p2.grad = views
+_native._notify(flat4, [p1, p2], views)
+sync.wait_all(average=True)
+assert torch.equal(p1.grad, torch.arange(6.) * 1.5)
+# ... and an accumulated (non-aliasing) .grad is an error, not a silent divergence of the ranks
+flat5 = torch.ones(10)
+views = [flat5[:6].view(6), flat5[6:].view(2, 2)]
+p1.grad, p2.grad = views[0].clone(), views[1]
+_native._notify(flat5, [p1, p2], views)
+try:
+    sync.wait_all()
+    raise SystemExit("non-aliasing .grad was not detected")
+except RuntimeError as ex:
+    assert "set_to_none=True" in str(ex)
+# a step whose collectives were never consumed (optimizer unaware of the synchronizer) is detected at the next backward
+flat6 = torch.ones(10); views = [flat6[:6].view(6), flat6[6:].view(2, 2)]
+_native._notify(flat6, [p1, p2], views)
+try:
+    _native._notify(torch.ones(10), [p1, p2], views)
+    raise SystemExit("unconsumed step was not detected")
+except RuntimeError as ex:
+    assert "wait_all" in str(ex)
+assert not sync.pending
 b, e = shard_range(5, r, 2)
 local = torch.arange(b, e).float().reshape(-1, 1).repeat(1, 3)
 allv = gather_scores(local, [3, 2])
