@@ -16,6 +16,7 @@ int g_opt_wgrad_box3 = 1;
 int g_opt_fcomb_fwd_mma = 1;
 int g_opt_wgrad_fused_bias = 1;
 int g_opt_pdl = 1;
+int g_opt_gn_fuse = 1;
 cudaStream_t g_pack_stream = nullptr;
 unsigned long long g_since_pack = 0;
 long long* g_halo_trace = nullptr;
@@ -46,6 +47,7 @@ int conv_forward(const ConvParams& p, int dtype, int backend, cudaStream_t s) {
     return conv_tc(p, dtype, s);
   }
   if (backend == PUB_BACKEND_AUTO && conv_tc_supported(p, dtype)) return conv_tc(p, dtype, s);
+  PUB_REQUIRE(p.stat_part == nullptr, "conv_forward: fused GroupNorm epilogue requested for a launch that takes the FMA path");
   ConvParams q = p;
   q.round_tf32 = dtype == PUB_TF32;
   return conv_simt(q, dtype, s);
@@ -101,6 +103,7 @@ int pub_debug_option(const char* name, int value) {
   if (strcmp(name, "fcomb_fwd_mma") == 0) { g_opt_fcomb_fwd_mma = value; return 0; }
   if (strcmp(name, "wgrad_fused_bias") == 0) { g_opt_wgrad_fused_bias = value; return 0; }
   if (strcmp(name, "pdl") == 0) { g_opt_pdl = value; return 0; }
+  if (strcmp(name, "gn_fuse") == 0) { g_opt_gn_fuse = value; return 0; }
   set_error("pub_debug_option: unknown option '%s'", name);
   return -1;
 }

@@ -35,6 +35,7 @@ extern int g_opt_conv_halo;   // -1: from PUB_CONV_HALO (default on); 0/1 forced
 extern int g_opt_wgrad_box3;  // 1 (default): 3x3 wgrad loads x as three (8+2) x 8 boxes; 0: nine tap boxes (A/B: pub_debug_option("wgrad_box3", v))
 extern int g_opt_fcomb_fwd_mma;  // fcomb forward in bf16 mode: 1 = tensor-core kernel (bf16 operands), 0 = f32 FMA kernel
 extern int g_opt_wgrad_fused_bias;  // 1 (default): bias gradients summed from the dy tiles staged by the wgrad kernel; 0: separate pass
+extern int g_opt_gn_fuse;  // 1 (default): GroupNorm statistics / backward prologue fused into the halo conv epilogues; 0: separate passes
 extern long long* g_halo_trace;  // device buffer for conv_halo_kernel event stamps (pub_debug_pointer("halo_trace", p)), else null
 extern unsigned long long g_launch_count;  // kernels enqueued by this library (bench.py's gpu_launches)
 #define PUB_LAUNCH_CHECK()          \
@@ -181,6 +182,46 @@ __device__ __forceinline__ float silu_grad_f(float x) {
   const float s = 1.f / (1.f + __expf(-x));
   return s * (1.f + x * (1.f - s));
 }
+
+// ---------------------------------------------------------------- GroupNorm / SiLU / dropout helpers
+// (shared by norm.cu and by the conv epilogues that fuse the GroupNorm statistics / backward prologue, conv_tc.cu)
+#ifdef __CUDACC__
+// MUFU-only sigmoid (ex2 + rcp, no IEEE-division subroutine): rel. error ~1e-6, far inside the 1e-4 parity budget.
+// The kernels below are otherwise issue-bound on the division slow path rather than HBM-bound.
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
+// bf16 storage: one MUFU (tanh.approx, rel. error 2^-11 -- below the 2^-9 of the bf16 value it is multiplied into)
+// instead of ex2 + rcp + 2 FP32 ops; f32 storage keeps the exact-to-1e-6 form
+__device__ __forceinline__ float sigmoid_tanh(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x) {
+  return sizeof(T) == 2 ? sigmoid_tanh(x) : sigmoid_fast(x);
+}
+template <typename T> __device__ __forceinline__ float silu_t(float x) { return x * sigmoid_t<T>(x); }
+template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
+  const float s = sigmoid_t<T>(x);
+  return fmaf(x * s, 1.f - s, s);
+}
+
+// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0): ONE Philox call,
+// 16 random bits per element, keep <=> u16 >= round(p * 65536)
+__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint64_t subseq, int64_t e, uint32_t thresh, bool (&keep)[8]) {
+  const uint4 r = Philox::gen(seed, subseq, (uint64_t)(e >> 3));
+  keep[0] = (r.x & 0xFFFFu) >= thresh; keep[1] = (r.x >> 16) >= thresh;
+  keep[2] = (r.y & 0xFFFFu) >= thresh; keep[3] = (r.y >> 16) >= thresh;
+  keep[4] = (r.z & 0xFFFFu) >= thresh; keep[5] = (r.z >> 16) >= thresh;
+  keep[6] = (r.w & 0xFFFFu) >= thresh; keep[7] = (r.w >> 16) >= thresh;
+}
+__device__ __forceinline__ uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
+
+#endif
 
 // ---------------------------------------------------------------- bump allocator over a caller workspace
 struct Arena {

@@ -423,7 +423,41 @@ struct HaloArgs {
   void* y; int ldy;
   int relu;
   long long* trace;   // optional event trace of CTA (0,0) (tools/halo_trace.py): [role][1024] clock64 stamps
+  // ---- fused GroupNorm work in the epilogue (template parameter EPI of conv_halo_kernel)
+  uint32_t epi_off;   // byte offset (from the aligned smem base) of the 4 x [32][33] f32 transposition buffers
+  // EPI_STATS: per-(tile, epilogue warp) per-channel (sum, sum of squares) of the values as STORED (rounded to the
+  // storage type): rows [(tile * 4 + warp)][cout][2] -- the forward statistics of the GroupNorm that reads y
+  float* stat_part;
+  // EPI_GNBWD (data-gradient launches): the conv result g = dL/d(activated GroupNorm output) is turned into
+  // du = g * keep / (1 - p) * silu'(a x + b) before it is stored, and (sum du, sum du * x) are emitted like above;
+  // x = the GroupNorm's input (virtual concat gx0 | gx1), (a, b) = its per-(sample, channel) affine table
+  const void* gx0; const void* gx1; int gc0, gld0, gld1;
+  const float* gcoef;          // [B][cout][2]
+  float p_drop; uint64_t seed, subseq;
 };
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_GNBWD = 2 };
+
+// per-channel sums over the 32 pixels (lanes) of a warp's 32 x 32 accumulator chunk: every lane writes its 32 values
+// as a column of a [32][33] f32 buffer (conflict-free both ways), then lane j adds up row j in a fixed order
+__device__ __forceinline__ float warp_colsum32(float* tsm, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tsm[j * 33 + lane] = v[j];
+  __syncwarp();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += tsm[lane * 33 + i];
+  __syncwarp();
+  return s;
+}
+__device__ __forceinline__ void warp_colsum32_sq(float* tsm, int lane, const float (&v)[32], float& s1, float& s2) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tsm[j * 33 + lane] = v[j];
+  __syncwarp();
+  s1 = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { const float x = tsm[lane * 33 + i]; s1 += x; s2 = fmaf(x, x, s2); }
+  __syncwarp();
+}
 
 // role r, event counter n: stamps clock64 into trace[r*1024 + n]
 #define HALO_TR(r, n)                                                                   \
@@ -431,7 +465,7 @@ struct HaloArgs {
     if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (n) < 1024) a.trace[(r) * 1024 + (n)++] = clock64(); \
   } while (0)
 
-template <int ROWB_, int ES>
+template <int ROWB_, int ES, int EPI>
 __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                              const __grid_constant__ CUtensorMap tmA1,
                                                              const __grid_constant__ CUtensorMap tmW, HaloArgs a) {
@@ -589,6 +623,10 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
     int it = 0;
     int trn = 0;
     const bool trw = warp == 2 && lane == 0;
+    float* tsm = nullptr;
+    if (EPI != EPI_PLAIN) tsm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + a.epi_off) + q * (32 * 33);
+    const uint32_t thresh = EPI == EPI_GNBWD ? drop_thresh(a.p_drop) : 0u;
+    const float inv_keep = (EPI == EPI_GNBWD && a.p_drop > 0.f) ? 1.f / (1.f - a.p_drop) : 1.f;
     for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
       int t = tile;
       const int tx = t % a.tiles_x; t /= a.tiles_x;
@@ -638,6 +676,31 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
             for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
           }
         }
+        float xs[EPI == EPI_GNBWD ? 32 : 1];
+        if (EPI == EPI_GNBWD) {
+          // v = dL/d(dropout(silu(a x + b)))  ->  du = v * keep / (1 - p) * silu'(a x + b)
+          const T* xp = n < a.gc0 ? (const T*)a.gx0 + pix * a.gld0 + n : (const T*)a.gx1 + pix * a.gld1 + (n - a.gc0);
+          const float4* cf = reinterpret_cast<const float4*>(a.gcoef + ((int64_t)t * a.cout + n) * 2);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
+            Vec8<T>::load(xp + g * 8, f);
+            if (a.p_drop > 0.f) {
+              bool keep[8];
+              dropout_keep8(a.seed, a.subseq, pix * a.cout + n + g * 8, thresh, keep);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] = keep[j] ? v[g * 8 + j] * inv_keep : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float4 c4 = __ldg(cf + (g * 8 + j) / 2);      // (a, b) of two channels
+              v[g * 8 + j] *= silu_grad_t<T>(fmaf(c4.x, f[j], c4.y));
+              v[g * 8 + j + 1] *= silu_grad_t<T>(fmaf(c4.z, f[j + 1], c4.w));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xs[g * 8 + j] = f[j];
+          }
+        }
         T* yp = (T*)a.y + pix * a.ldy + n;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -645,6 +708,21 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = ES == 4 ? round_tf32(v[g * 8 + j]) : v[g * 8 + j];
           Vec8<T>::store(yp + g * 8, f);
+        }
+        if (EPI != EPI_PLAIN) {
+          // statistics of the values as the consumer will read them (rounded to the storage type)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = to_f<T>(from_f<T>(v[j]));
+          float s1, s2;
+          if (EPI == EPI_STATS) {
+            warp_colsum32_sq(tsm, lane, v, s1, s2);
+          } else {
+            s1 = warp_colsum32(tsm, lane, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= xs[j];
+            s2 = warp_colsum32(tsm, lane, v);
+          }
+          *reinterpret_cast<float2*>(a.stat_part + ((int64_t)(tile * 4 + q) * a.cout + n + lane) * 2) = make_float2(s1, s2);
         }
       }
       if (trw) HALO_TR(2, trn);
@@ -1006,12 +1084,29 @@ bool conv_tc_supported(const ConvParams& p, int dtype) {
   return pick_patch(p.H, p.W, 128, tw, th, tb);
 }
 
+int conv_fused_rows(const ConvParams& p, int dtype, int backend) {
+  if (backend == PUB_BACKEND_SIMT || dtype != PUB_BF16 || g_opt_gn_fuse == 0) return 0;
+  if (!conv_tc_supported(p, dtype) || !conv_halo_ok(p, dtype)) return 0;
+  return 4 * (p.W / 8) * (p.H / 16);
+}
+
 namespace {
+template <int EPI>
+void launch_halo(int es, int rowb, dim3 grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
+                 const CUtensorMap& tmW, const HaloArgs& a) {
+  if (es == 4) launch_pdl(conv_halo_kernel<128, 4, EPI_PLAIN>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  else if (rowb == 128) launch_pdl(conv_halo_kernel<128, 2, EPI>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  else launch_pdl(conv_halo_kernel<64, 2, EPI>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
+}
+
 int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   const int cin = p.c0 + p.c1, es = esize(dtype);
   const int KC = es == 4 ? 32 : ((p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32);
   const int rowb = KC * es;
   const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const int epi = p.stat_part ? (p.gn_bwd ? EPI_GNBWD : EPI_STATS) : EPI_PLAIN;
+  PUB_REQUIRE(epi == EPI_PLAIN || es == 2, "conv_halo: the fused GroupNorm epilogue exists for bf16 only");
+  PUB_REQUIRE(epi != EPI_GNBWD || (p.gx0 && p.gcoef && p.gc0 % 32 == 0), "conv_halo: incomplete GroupNorm-backward epilogue arguments");
   HaloArgs a{};
   a.c0 = p.c0; a.c1 = p.c1;
   a.B = p.B; a.H = p.H; a.W = p.W;
@@ -1021,12 +1116,16 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   a.y = p.y; a.ldy = p.ldy; a.relu = p.relu;
   a.trace = g_halo_trace;
   a.w_early = p.w_settled && weights_settled_on(s);
+  a.stat_part = p.stat_part;
+  a.gx0 = p.gx0; a.gx1 = p.gx1; a.gc0 = p.gx1 ? p.gc0 : p.cout; a.gld0 = p.gld0; a.gld1 = p.gld1;
+  a.gcoef = p.gcoef; a.p_drop = p.p_drop; a.seed = p.seed; a.subseq = p.subseq;
   const int n_tiles = p.cout / a.BN;
   const int cblk = cin / KC;
   const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);
   const size_t wres_bytes = (size_t)cblk * 9 * b_bytes;
+  const size_t epi_bytes = epi == EPI_PLAIN ? 0 : (size_t)4 * 32 * 33 * sizeof(float);   // transposition buffers
   const bool small_tmem = 2 * a.BN <= 256;            // two CTAs per SM are possible
-  const size_t budget2 = 110 * 1024 - 2048, budget1 = 222 * 1024 - 2048;
+  const size_t budget2 = 110 * 1024 - 2048 - epi_bytes, budget1 = 222 * 1024 - 2048 - epi_bytes;
   const int min_a = 3;
   bool two;
   if (small_tmem && wres_bytes + min_a * a_stage <= budget2) {
@@ -1043,7 +1142,9 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
     PUB_REQUIRE(a.bstages >= 2, "conv_halo: weight ring does not fit");
   }
   if (a.astages > 6) a.astages = 6;
-  const size_t smem = 1024 + (a.resident ? wres_bytes : (size_t)a.bstages * b_bytes) + (size_t)a.astages * a_stage;
+  const size_t ring_bytes = (a.resident ? wres_bytes : (size_t)a.bstages * b_bytes) + (size_t)a.astages * a_stage;
+  a.epi_off = (uint32_t)ring_bytes;
+  const size_t smem = 1024 + ring_bytes + epi_bytes;
   int gx = (two ? 2 : 1) * num_sms() / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
@@ -1054,15 +1155,19 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   PUB_TRY(make_weight_map(&tmW, p.w, es, cin, p.cout, 9, KC, a.BN, sw));
   static bool attr = false;
   if (!attr) {
-    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 2>, 225 * 1024));
-    PUB_TRY(set_smem_attr(conv_halo_kernel<64, 2>, 225 * 1024));
-    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 4>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 2, EPI_PLAIN>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<64, 2, EPI_PLAIN>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 4, EPI_PLAIN>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 2, EPI_STATS>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<64, 2, EPI_STATS>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<128, 2, EPI_GNBWD>, 225 * 1024));
+    PUB_TRY(set_smem_attr(conv_halo_kernel<64, 2, EPI_GNBWD>, 225 * 1024));
     attr = true;
   }
   dim3 grid(gx, n_tiles);
-  if (es == 4) launch_pdl(conv_halo_kernel<128, 4>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
-  else if (rowb == 128) launch_pdl(conv_halo_kernel<128, 2>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
-  else launch_pdl(conv_halo_kernel<64, 2>, grid, HTHREADS, smem, s, tmA0, tmA1, tmW, a);
+  if (epi == EPI_STATS) launch_halo<EPI_STATS>(es, rowb, grid, smem, s, tmA0, tmA1, tmW, a);
+  else if (epi == EPI_GNBWD) launch_halo<EPI_GNBWD>(es, rowb, grid, smem, s, tmA0, tmA1, tmW, a);
+  else launch_halo<EPI_PLAIN>(es, rowb, grid, smem, s, tmA0, tmA1, tmW, a);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -1072,6 +1177,7 @@ int conv_tc(const ConvParams& p, int dtype, cudaStream_t s) {
   PUB_REQUIRE(conv_tc_supported(p, dtype), "conv_tc: unsupported shape (c0=%d c1=%d cout=%d H=%d W=%d ks=%d dtype=%d)",
               p.c0, p.c1, p.cout, p.H, p.W, p.ks, dtype);
   if (conv_halo_ok(p, dtype)) return conv_halo(p, dtype, s);
+  PUB_REQUIRE(p.stat_part == nullptr, "conv_tc: the fused GroupNorm epilogue needs the halo kernel (check conv_fused_rows first)");
   const int cin = p.c0 + p.c1, es = esize(dtype);
   // channels per K block: bf16 -> 64 (128 B rows) when both sources allow it, else 32 (64 B rows); tf32 -> 32 (128 B rows)
   const int KC = es == 4 ? 32 : ((p.c0 % 64 == 0 && p.c1 % 64 == 0) ? 64 : 32);

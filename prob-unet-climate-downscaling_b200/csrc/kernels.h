@@ -17,6 +17,16 @@ struct ConvParams {
   int round_tf32;  // SIMT path only: round the stored output to tf32 (PUB_TF32 tensors feed kind::tf32 MMAs)
   int w_settled;   // set by the engines: w was written by this library's pack kernels (note_weight_pack tracks them),
                    // so the halo kernel may request it before its grid-dependency wait; 0 for caller-supplied weights
+  // ---- GroupNorm work fused into the epilogue (tcgen05 halo kernel, bf16 only: conv_fused_rows() > 0)
+  // stat_part != nullptr, gn_bwd == 0: rows [B * conv_fused_rows()][cout][2] receive per-channel (sum, sum of squares)
+  //   of the stored output = the forward statistics partials of the GroupNorm that reads y (src/networks.py:105-107)
+  // gn_bwd == 1 (data-gradient launches): the result g is stored as du = g * keep/(1-p) * silu'(a x + b) -- x (gx0|gx1)
+  //   the GroupNorm's input, gcoef its [B][cout][2] affine table -- and the rows receive (sum du, sum du * x)
+  float* stat_part;
+  int gn_bwd;
+  const void* gx0; const void* gx1; int gc0, gld0, gld1;
+  const float* gcoef;
+  float p_drop; uint64_t seed, subseq;
 };
 
 struct WgradParams {
@@ -46,6 +56,9 @@ int nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, in
 
 // ---- conv_tc.cu (tcgen05 / TMEM / TMA)
 bool conv_tc_supported(const ConvParams& p, int dtype);
+// partial rows per image a launch with the fused GroupNorm epilogue writes (4 per 8 x 16 output tile), or 0 when this
+// launch would not go through the halo kernel in bf16 (the caller then runs the separate statistics pass)
+int conv_fused_rows(const ConvParams& p, int dtype, int backend);
 int conv_tc(const ConvParams& p, int dtype, cudaStream_t s);
 bool wgrad_tc_supported(const WgradParams& p, int dtype);
 size_t wgrad_tc_workspace(const WgradParams& p, int dtype);
@@ -68,6 +81,9 @@ struct GnParams {
   float* coef;                                            // [B][C][2] scratch: per-(b,c) affine a,b
   float* partial;                                         // scratch for the two-stage reductions
   int rows;                                               // pixels per CTA chunk: filled in by gn_forward / gn_backward
+  // statistics partials already emitted by the conv that PRODUCED x0 (and x1) -- ConvParams::stat_part --: pre_rows
+  // rows per image of [c0][2] / [c1][2] (sum, sum of squares).  gn_forward then skips its own pass over x.
+  const float* pre0; const float* pre1; int pre_rows;
 };
 size_t gn_partial_floats(int B, int C, int H, int W);
 // y [B,H',W',C] NHWC dt (contiguous, ld = C)
@@ -76,6 +92,12 @@ int gn_forward(const GnParams& p, void* y, int dtype, cudaStream_t s);
 // (optional, NHWC dt, ld_add) is added to dx.  dgamma/dbeta [C], dfilm [2C] overwritten.
 int gn_backward(const GnParams& p, const void* dy, void* dx, const void* addend, int ld_add, float* dgamma,
                 float* dbeta, float* dfilm, int dtype, cudaStream_t s);
+// same, when the data-gradient conv already produced du = dy * keep/(1-p) * silu'(a x + b) and its partial sums
+// (ConvParams::gn_bwd): du [B,H,W,C] contiguous, du_part = rows_per_image rows per image of [C][2] (sum du, sum du * x).
+// No resampling (the fused epilogue only exists for blocks whose conv runs at the GroupNorm's resolution).
+int gn_backward_from_du(const GnParams& p, const void* du, const float* du_part, int rows_per_image, void* dx,
+                        const void* addend, int ld_add, float* dgamma, float* dbeta, float* dfilm, int dtype,
+                        cudaStream_t s);
 
 // ---- elementwise.cu
 int resample2x(const void* x, int ld, int C, void* y, int B, int H, int W, int mode, int dtype, cudaStream_t s);

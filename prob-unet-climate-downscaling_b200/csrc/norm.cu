@@ -36,30 +36,6 @@ inline int gn_pick_rows(int B, int HW, int C) {
   return rows < HW ? rows : HW;
 }
 
-// MUFU-only sigmoid (ex2 + rcp, no IEEE-division subroutine): rel. error ~1e-6, far inside the 1e-4 parity budget.
-// The kernels below are otherwise issue-bound on the division slow path rather than HBM-bound.
-__device__ __forceinline__ float rcp_fast(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
-// bf16 storage: one MUFU (tanh.approx, rel. error 2^-11 -- below the 2^-9 of the bf16 value it is multiplied into)
-// instead of ex2 + rcp + 2 FP32 ops; f32 storage keeps the exact-to-1e-6 form
-__device__ __forceinline__ float sigmoid_tanh(float x) {
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  return fmaf(0.5f, t, 0.5f);
-}
-template <typename T> __device__ __forceinline__ float sigmoid_t(float x) {
-  return sizeof(T) == 2 ? sigmoid_tanh(x) : sigmoid_fast(x);
-}
-template <typename T> __device__ __forceinline__ float silu_t(float x) { return x * sigmoid_t<T>(x); }
-template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
-  const float s = sigmoid_t<T>(x);
-  return fmaf(x * s, 1.f - s, s);
-}
-
 // Every heavy kernel uses the same decomposition: grid = (pixel chunks, batch); inside a CTA thread t owns the
 // 8-channel vector v = t % V for the rows pr, pr + ppi, ... of the chunk (ppi = 256 / V).  The per-channel
 // constants of that vector (affine a/b, backward c1/c2/c3) are loaded ONCE into registers, so the inner loop is
@@ -167,17 +143,6 @@ __device__ __forceinline__ void load_affine(const float* coef, int b, int C, int
     a[2 * i] = t.x; bb[2 * i] = t.y; a[2 * i + 1] = t.z; bb[2 * i + 1] = t.w;
   }
 }
-
-// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0): ONE Philox call,
-// 16 random bits per element, keep <=> u16 >= round(p * 65536)
-__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint64_t subseq, int64_t e, uint32_t thresh, bool (&keep)[8]) {
-  const uint4 r = Philox::gen(seed, subseq, (uint64_t)(e >> 3));
-  keep[0] = (r.x & 0xFFFFu) >= thresh; keep[1] = (r.x >> 16) >= thresh;
-  keep[2] = (r.y & 0xFFFFu) >= thresh; keep[3] = (r.y >> 16) >= thresh;
-  keep[4] = (r.z & 0xFFFFu) >= thresh; keep[5] = (r.z >> 16) >= thresh;
-  keep[6] = (r.w & 0xFFFFu) >= thresh; keep[7] = (r.w >> 16) >= thresh;
-}
-__device__ __forceinline__ uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
 
 // gradient wrt the activated output at INPUT resolution, rebuilt from dy (output resolution) + dropout
 template <typename T>
@@ -311,7 +276,11 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
 }
 
 // one warp per (b, g): mean / rstd, then the per-channel affine  y = silu(a x + b)
-__global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, int nchunk) {
+// partial rows: part0 holds channels [0, w0) in rows of w0 channels, part1 (optional) channels [w0, C) in rows of C - w0
+// (one buffer of full-width rows from gn_partial_kernel, or one buffer per source of a virtual concat when the
+// producing convs emitted them)
+__global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part0, int w0, const float* __restrict__ part1,
+                                   int nchunk) {
   pdl_enter();
   const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -320,7 +289,9 @@ __global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part, i
   double s = 0.0, ss = 0.0;
   for (int i = lane; i < nchunk * cpg; i += 32) {
     const int k = i / cpg, c = g * cpg + i % cpg;
-    const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
+    const float* row = c < w0 ? part0 + (((int64_t)b * nchunk + k) * w0 + c) * 2
+                              : part1 + (((int64_t)b * nchunk + k) * (C - w0) + (c - w0)) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(row);
     s += (double)v.x; ss += (double)v.y;
   }
   s = warp_sum_d(s); ss = warp_sum_d(ss);
@@ -417,8 +388,9 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
 
 // backward finalize 1: per (b, g) -> bcoef[b][c] = (c2, c3):  dx = a*du + c2*x + c3  (a = forward coefficient)
 // partials hold P1 = sum du, P2 = sum du*(x - mean);  sum du*xhat = rstd * P2
-__global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, float* __restrict__ bcoef,
-                                    float* __restrict__ bsum) {
+// raw2 != 0: the second partial is sum du * x (conv epilogue, ConvParams::gn_bwd) and is centred here, row by row
+__global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, int nchunk, int raw2,
+                                    float* __restrict__ bcoef, float* __restrict__ bsum) {
   pdl_enter();
   const int C = p.c0 + p.c1, cpg = C / p.groups;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -427,13 +399,14 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
   // per channel: sum the chunk partials (lanes stride over chunks, fixed tree), keep (S1, rstd*S2) per (b, c)
   // for the parameter-gradient kernel, and fold them into the group sums
   const float rstd_g = p.stats[((int64_t)b * p.groups + g) * 2 + 1];
+  const float mean_g = raw2 ? p.stats[((int64_t)b * p.groups + g) * 2] : 0.f;
   double q1 = 0.0, q2 = 0.0;
   for (int ci = 0; ci < cpg; ++ci) {
     const int c = g * cpg + ci;
     float a1 = 0.f, a2 = 0.f;
     for (int k = lane; k < nchunk; k += 32) {
       const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
-      a1 += v.x; a2 += v.y;
+      a1 += v.x; a2 += fmaf(-mean_g, v.x, v.y);
     }
     a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { bsum[((int64_t)b * C + c) * 2] = a1; bsum[((int64_t)b * C + c) * 2 + 1] = rstd_g * a2; }
@@ -480,7 +453,7 @@ __global__ void gn_bwd_param_kernel(GnParams p, const float* __restrict__ bsum, 
 
 // dx = a*du + c2*x + c3 (+ addend);  a = rstd*gamma*(1+scale) is the forward coefficient, (c2, c3) come from the
 // group sums (bcoef[b][c] = (c2, c3)).  x, dy and the addend arrive through the cp.async ring; <= 80 registers.
-template <typename T>
+template <typename T, bool FROM_DU>
 __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, const T* __restrict__ dy,
                                                                 const float* __restrict__ bcoef, T* __restrict__ dx,
                                                                 const T* __restrict__ addend, int ld_add) {
@@ -520,7 +493,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
       float x[8], g[8], o[8];
       rr.read(st, 0, x);
       rr.read(st, 1, g);
-      if (p.p_drop > 0.f) {
+      if (!FROM_DU && p.p_drop > 0.f) {
         bool keep[8];
         dropout_keep8(p.seed, p.subseq, e, thresh, keep);
 #pragma unroll
@@ -528,7 +501,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
+        const float du = FROM_DU ? g[j] : g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
         o[j] = fmaf(a[j], du, fmaf(c2[j], x[j], c3[j]));
       }
       if (ab) {
@@ -591,8 +564,9 @@ static int set_gn_smem_attrs() {
   PUB_CUDA(cudaFuncSetAttribute(gn_partial_kernel<float, 1>, at, red + (int)ring_bytes<float, 2>()));
   PUB_CUDA(cudaFuncSetAttribute(gn_apply_kernel<bf16>, at, (int)ring_bytes<bf16, 1>()));
   PUB_CUDA(cudaFuncSetAttribute(gn_apply_kernel<float>, at, (int)ring_bytes<float, 1>()));
-  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<bf16>, at, (int)ring_bytes<bf16, 3>()));
-  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<float>, at, (int)ring_bytes<float, 3>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<bf16, false>, at, (int)ring_bytes<bf16, 3>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<float, false>, at, (int)ring_bytes<float, 3>()));
+  PUB_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<bf16, true>, at, (int)ring_bytes<bf16, 3>()));
   done = true;
   return 0;
 }
@@ -609,11 +583,18 @@ int gn_forward(const GnParams& p_, void* y, int dtype, cudaStream_t s) {
   const size_t red = (size_t)GN_NT * 16 * sizeof(float);
   dim3 grid(nc, p.B);
   PUB_TRY(set_gn_smem_attrs());
-  if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 0>, grid, GN_NT, red + ring_bytes<bf16, 1>(), s, p, nullptr, p.partial);
-  else launch_pdl(gn_partial_kernel<float, 0>, grid, GN_NT, red + ring_bytes<float, 1>(), s, p, nullptr, p.partial);
-  PUB_LAUNCH_CHECK();
-  launch_pdl(gn_finalize_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.partial, nc);
-  PUB_LAUNCH_CHECK();
+  if (p.pre0 && (p.c1 == 0 || p.pre1)) {
+    // the producing conv(s) already emitted the (sum, sum of squares) partials: no pass over x
+    launch_pdl(gn_finalize_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.pre0, p.c0, p.pre1, p.pre_rows);
+    PUB_LAUNCH_CHECK();
+  } else {
+    if (dtype == PUB_BF16) launch_pdl(gn_partial_kernel<bf16, 0>, grid, GN_NT, red + ring_bytes<bf16, 1>(), s, p, nullptr, p.partial);
+    else launch_pdl(gn_partial_kernel<float, 0>, grid, GN_NT, red + ring_bytes<float, 1>(), s, p, nullptr, p.partial);
+    PUB_LAUNCH_CHECK();
+    launch_pdl(gn_finalize_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, (const float*)p.partial, C,
+               (const float*)nullptr, nc);
+    PUB_LAUNCH_CHECK();
+  }
   dim3 agrid(cdiv((int64_t)p.H * p.W / (p.resample == 1 ? 4 : 1), p.rows), p.B);
   if (dtype == PUB_BF16) launch_pdl(gn_apply_kernel<bf16>, agrid, GN_NT, ring_bytes<bf16, 1>(), s, p, (bf16*)y);
   else launch_pdl(gn_apply_kernel<float>, agrid, GN_NT, ring_bytes<float, 1>(), s, p, (float*)y);
@@ -635,17 +616,40 @@ int gn_backward(const GnParams& p_, const void* dy, void* dx, const void* addend
   else launch_pdl(gn_partial_kernel<float, 1>, grid, GN_NT, red + ring_bytes<float, 2>(), s, p, (const float*)dy, p.partial);
   PUB_LAUNCH_CHECK();
   float* bsum = bcoef + (size_t)p.B * C * 2;
-  launch_pdl(gn_bwd_group_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, p.partial, nc, bcoef, bsum);
+  launch_pdl(gn_bwd_group_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, (const float*)p.partial, nc, 0, bcoef, bsum);
   PUB_LAUNCH_CHECK();
   launch_pdl(gn_bwd_param_kernel, cdiv((int64_t)C * 32, 256), 256, 0, s, p, bsum, dgamma, dbeta, dfilm);
   PUB_LAUNCH_CHECK();
   if (dx) {
     if (dtype == PUB_BF16)
-      launch_pdl(gn_bwd_apply_kernel<bf16>, grid, GN_NT, ring_bytes<bf16, 3>(), s, p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
+      launch_pdl(gn_bwd_apply_kernel<bf16, false>, grid, GN_NT, ring_bytes<bf16, 3>(), s, p, (const bf16*)dy, bcoef, (bf16*)dx, (const bf16*)addend, ld_add);
     else
-      launch_pdl(gn_bwd_apply_kernel<float>, grid, GN_NT, ring_bytes<float, 3>(), s, p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
+      launch_pdl(gn_bwd_apply_kernel<float, false>, grid, GN_NT, ring_bytes<float, 3>(), s, p, (const float*)dy, bcoef, (float*)dx, (const float*)addend, ld_add);
     PUB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int gn_backward_from_du(const GnParams& p_, const void* du, const float* du_part, int rows_per_image, void* dx,
+                        const void* addend, int ld_add, float* dgamma, float* dbeta, float* dfilm, int dtype,
+                        cudaStream_t s) {
+  PUB_TRY(check(p_));
+  PUB_REQUIRE(dtype == PUB_BF16 && p_.resample == 0 && du && du_part && dx, "gn_backward_from_du: bf16, no resampling");
+  GnParams p = p_;
+  p.rows = gn_pick_rows(p.B, p.H * p.W, p.c0 + p.c1);
+  p.p_drop = 0.f;                                    // the dropout mask is already inside du
+  PUB_TRY(set_gn_smem_attrs());
+  const int C = p.c0 + p.c1, nc = nchunks(p);
+  float* bcoef = p.partial;                          // scratch: [B][C][2] coefficients, then [B][C][2] per-(b,c) sums
+  float* bsum = bcoef + (size_t)p.B * C * 2;
+  launch_pdl(gn_bwd_group_kernel, cdiv((int64_t)p.B * p.groups * 32, 128), 128, 0, s, p, du_part, rows_per_image, 1, bcoef, bsum);
+  PUB_LAUNCH_CHECK();
+  launch_pdl(gn_bwd_param_kernel, cdiv((int64_t)C * 32, 256), 256, 0, s, p, (const float*)bsum, dgamma, dbeta, dfilm);
+  PUB_LAUNCH_CHECK();
+  dim3 grid(nc, p.B);
+  launch_pdl(gn_bwd_apply_kernel<bf16, true>, grid, GN_NT, ring_bytes<bf16, 3>(), s, p, (const bf16*)du, (const float*)bcoef,
+             (bf16*)dx, (const bf16*)addend, ld_add);
+  PUB_LAUNCH_CHECK();
   return 0;
 }
 

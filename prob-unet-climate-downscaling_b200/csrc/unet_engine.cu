@@ -25,6 +25,7 @@ struct BlockPlan {
   void *a0, *h, *a1, *out, *dx;
   void *wp0, *wp1, *wps;    // packed weights of conv0 / conv1 / skip (plain conv: wp0), forward OR mirrored layout
   float *stats0, *coef0, *stats1, *coef1;
+  float *h_part, *out_part;  // GroupNorm statistics partials emitted by the epilogues of conv0 / conv1 (ConvParams::stat_part)
 };
 
 }  // namespace pub
@@ -56,6 +57,7 @@ struct Plan {
   // scratch
   void *wp_out;             // packed out_conv weights
   void *gn_scratch, *skipbuf, *s1, *s2, *sadd, *gsum, *wg_ws;
+  float *du_part;           // backward: (sum du, sum du*x) partials emitted by a data-gradient conv (ConvParams::gn_bwd)
   size_t wg_ws_bytes;
   size_t total;
 };
@@ -69,7 +71,11 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
   struct Out { int c, h, w, idx; };
   std::vector<Out> skips;
   int curC = u->in_ch, curH = H, curW = W, cur = -1;
-  size_t max_act = 0, max_w = 0, max_gn = 0, max_wg = 0;
+  size_t max_act = 0, max_w = 0, max_gn = 0, max_wg = 0, max_part = 0;
+  // rows of statistics partials a fused conv epilogue writes per image at (h, w): 4 per 8 x 16 output tile
+  auto part_floats = [&](int h, int w, int c) -> size_t {
+    return (h % 16 == 0 && w % 8 == 0) ? (size_t)B * 4 * (w / 8) * (h / 16) * c * 2 : 0;
+  };
   int pidx = 0;
   for (size_t i = 0; i < u->blocks.size(); ++i) {
     BlockPlan b{};
@@ -94,6 +100,7 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
       b.out = ar.take(n_out * b.d.cout * es);
       b.dx = nullptr;
       b.wp0 = ar.take((size_t)9 * b.d.cin * b.d.cout * es);
+      b.out_part = ar.take_n<float>(part_floats(b.Ho, b.Wo, b.d.cout));
     } else {
       PUB_REQUIRE(b.d.cin % 8 == 0 && b.d.cout % 8 == 0, "unet plan: block channels must be multiples of 8");
       pidx += 9 + (b.d.has_skip_conv ? 2 : 0);
@@ -109,6 +116,9 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
       b.coef0 = ar.take_n<float>((size_t)B * b.d.cin * 2);
       b.stats1 = ar.take_n<float>((size_t)B * groups_of(b.d.cout) * 2);
       b.coef1 = ar.take_n<float>((size_t)B * b.d.cout * 2);
+      b.h_part = ar.take_n<float>(part_floats(b.Ho, b.Wo, b.d.cout));
+      b.out_part = ar.take_n<float>(part_floats(b.Ho, b.Wo, b.d.cout));
+      max_part = std::max(max_part, part_floats(b.Ho, b.Wo, std::max(b.d.cin, b.d.cout)));
       max_gn = std::max(max_gn, gn_partial_floats(B, b.d.cin, b.Hi, b.Wi));
       max_gn = std::max(max_gn, gn_partial_floats(B, b.d.cout, b.Ho, b.Wo));
     }
@@ -153,6 +163,7 @@ int build_plan(const pub_unet* u, int B, int H, int W, void* base, size_t cap, P
   pl.gsum = ar.take(max_act);
   pl.wg_ws_bytes = max_wg;
   pl.wg_ws = ar.take(max_wg);
+  pl.du_part = ar.take_n<float>(std::max(max_part, part_floats(H, W, curC)));
   pl.total = ar.off + 1024;
   PUB_REQUIRE(ar.ok(), "unet workspace too small: need %zu bytes, have %zu", pl.total, cap);
   return 0;
@@ -270,6 +281,15 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
   const float pdrop = training ? u->dropout : 0.f;
   PUB_TRY(nchw_to_nhwc(x_nchw, u->in_ch, nullptr, 0, pl.x_in, 8, B, H, W, dt, s));
   PUB_TRY(pack_all(u, pl, P, 0, dt, s));
+  // GroupNorm statistics are produced by the epilogue of the conv that writes the tensor (conv_fused_rows() > 0: the
+  // tcgen05 halo kernel in bf16); out_rows[i] = partial rows per image that entry i's output carries (0: none, the
+  // consuming GroupNorm runs its own statistics pass)
+  std::vector<int> out_rows(pl.bp.size(), 0);
+  auto pre_of = [&](GnParams& g, int src0, int src1) {
+    if (src0 < 0 || out_rows[src0] == 0) return;
+    if (src1 >= 0 && out_rows[src1] != out_rows[src0]) return;
+    g.pre0 = pl.bp[src0].out_part; g.pre1 = src1 >= 0 ? pl.bp[src1].out_part : nullptr; g.pre_rows = out_rows[src0];
+  };
   for (size_t i = 0; i < pl.bp.size(); ++i) {
     BlockPlan& b = pl.bp[i];
     View v0 = src_view(pl, b.src0, 8);
@@ -278,18 +298,24 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
     const float* const* p = P + b.pidx;
     if (b.d.is_conv) {
       ConvParams c = conv_params(v0.p, b.c0, v0.ld, nullptr, 0, 0, b.wp0, p[1], nullptr, 0, b.out, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+      out_rows[i] = conv_fused_rows(c, dt, backend);
+      if (out_rows[i]) c.stat_part = b.out_part;
       PUB_TRY(conv_forward(c, dt, backend, s));
       continue;
     }
     const int mode = b.d.down ? 1 : (b.d.up ? 2 : 0);
     // a0 = resample(silu(norm0(x)))
     GnParams g0 = gn_params(pl, v0.p, b.c0, v0.ld, v1.p, b.c1, v1.ld, b.Hi, b.Wi, p[0], p[1], nullptr, mode, 0.f, 0, 0, b.stats0, b.coef0);
+    pre_of(g0, b.src0, b.src1);
     PUB_TRY(gn_forward(g0, b.a0, dt, s));
     // h = conv0(a0) + bias
     ConvParams c0 = conv_params(b.a0, b.d.cin, b.d.cin, nullptr, 0, 0, b.wp0, p[3], nullptr, 0, b.h, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+    const int h_rows = conv_fused_rows(c0, dt, backend);
+    if (h_rows) c0.stat_part = b.h_part;
     PUB_TRY(conv_forward(c0, dt, backend, s));
     // a1 = dropout(silu(shift + norm1(h) * (scale + 1)))
     GnParams g1 = gn_params(pl, b.h, b.d.cout, b.d.cout, nullptr, 0, 0, b.Ho, b.Wo, p[5], p[6], p[4], 0, pdrop, seed, (uint64_t)i, b.stats1, b.coef1);
+    if (h_rows) { g1.pre0 = b.h_part; g1.pre_rows = h_rows; }
     PUB_TRY(gn_forward(g1, b.a1, dt, s));
     // residual branch
     const void* res; int ld_res;
@@ -306,12 +332,15 @@ int pub_unet_forward(pub_unet* u, int B, int H, int W, const float* x_nchw, cons
     }
     // out = conv1(a1) + bias + residual
     ConvParams c1 = conv_params(b.a1, b.d.cout, b.d.cout, nullptr, 0, 0, b.wp1, p[8], res, ld_res, b.out, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+    out_rows[i] = conv_fused_rows(c1, dt, backend);
+    if (out_rows[i]) c1.stat_part = b.out_part;
     PUB_TRY(conv_forward(c1, dt, backend, s));
   }
   const BlockPlan& last = pl.bp.back();
   const float* const* p = P + (u->nparams - 4);
   const int fc = u->final_c;
   GnParams go = gn_params(pl, last.out, fc, fc, nullptr, 0, 0, H, W, p[0], p[1], nullptr, 0, 0.f, 0, 0, pl.stats_o, pl.coef_o);
+  pre_of(go, (int)pl.bp.size() - 1, -1);
   PUB_TRY(gn_forward(go, pl.a_out, dt, s));
   void* y = out_nchw ? pl.y_out : out;
   ConvParams co = conv_params(pl.a_out, fc, fc, nullptr, 0, 0, pl.wp_out, p[3], nullptr, 0, y, u->out_ch, B, H, W, u->out_ch, 3);
@@ -346,9 +375,13 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
     wp.B = B; wp.H = H; wp.W = W; wp.cout = u->out_ch; wp.ks = 3;
     PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
     ConvParams cd = conv_params(dy, u->out_ch, u->out_ch, nullptr, 0, 0, pl.wp_out, nullptr, nullptr, 0, pl.s1, fc, B, H, W, fc, 3);
-    PUB_TRY(conv_forward(cd, dt, backend, s));
     GnParams go = gn_params(pl, last.out, fc, fc, nullptr, 0, 0, H, W, p[0], p[1], nullptr, 0, 0.f, 0, 0, pl.stats_o, pl.coef_o);
-    PUB_TRY(gn_backward(go, pl.s1, pl.dx_last, nullptr, 0, g[0], g[1], nullptr, dt, s));
+    // the data-gradient conv stores du = g * silu'(a x + b) and its partial sums (GroupNorm-backward prologue fused)
+    const int rows = conv_fused_rows(cd, dt, backend);
+    if (rows) { cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = last.out; cd.gc0 = fc; cd.gld0 = fc; cd.gcoef = pl.coef_o; }
+    PUB_TRY(conv_forward(cd, dt, backend, s));
+    if (rows) PUB_TRY(gn_backward_from_du(go, pl.s1, pl.du_part, rows, pl.dx_last, nullptr, 0, g[0], g[1], nullptr, dt, s));
+    else PUB_TRY(gn_backward(go, pl.s1, pl.dx_last, nullptr, 0, g[0], g[1], nullptr, dt, s));
   }
   // gradient wrt the output of entry i, as a view: consumers are (a) the next entry in execution order
   // (slice [0, cout) of its dx) and (b) for encoder entries the decoder block that concatenated it.
@@ -403,17 +436,24 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       addp = gp; add_ld = gld;
     }
     // ---- conv1
+    int rows1 = 0, rows0 = 0;
     {
       WgradParams wp{};
       wp.x0 = b.a1; wp.c0 = b.d.cout; wp.ld0 = b.d.cout; wp.dy = gp; wp.ld_dy = gld; wp.dw = g[7]; wp.dbias = g[8];
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
       ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, b.wp1, nullptr, nullptr, 0, pl.s1, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
+      rows1 = conv_fused_rows(cd, dt, backend);
+      if (rows1) {
+        cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = b.h; cd.gc0 = b.d.cout; cd.gld0 = b.d.cout; cd.gcoef = b.coef1;
+        cd.p_drop = pdrop; cd.seed = seed; cd.subseq = (uint64_t)i;
+      }
       PUB_TRY(conv_forward(cd, dt, backend, s));
     }
     // ---- norm1 / FiLM / SiLU / dropout
     GnParams g1 = gn_params(pl, b.h, b.d.cout, b.d.cout, nullptr, 0, 0, b.Ho, b.Wo, p[5], p[6], p[4], 0, pdrop, seed, (uint64_t)i, b.stats1, b.coef1);
-    PUB_TRY(gn_backward(g1, pl.s1, pl.s2, nullptr, 0, g[5], g[6], g[4], dt, s));
+    if (rows1) PUB_TRY(gn_backward_from_du(g1, pl.s1, pl.du_part, rows1, pl.s2, nullptr, 0, g[5], g[6], g[4], dt, s));
+    else PUB_TRY(gn_backward(g1, pl.s1, pl.s2, nullptr, 0, g[5], g[6], g[4], dt, s));
     // ---- conv0
     {
       WgradParams wp{};
@@ -421,11 +461,17 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
       ConvParams cd = conv_params(pl.s2, b.d.cout, b.d.cout, nullptr, 0, 0, b.wp0, nullptr, nullptr, 0, pl.s1, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 3);
+      rows0 = mode == 0 ? conv_fused_rows(cd, dt, backend) : 0;     // resampling blocks: GroupNorm at another resolution
+      if (rows0) {
+        cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = v0.p; cd.gx1 = v1.p; cd.gc0 = b.c0; cd.gld0 = v0.ld; cd.gld1 = v1.ld;
+        cd.gcoef = b.coef0;
+      }
       PUB_TRY(conv_forward(cd, dt, backend, s));
     }
     // ---- norm0 / SiLU / resample  (+ residual-branch gradient)
     GnParams g0 = gn_params(pl, v0.p, b.c0, v0.ld, v1.p, b.c1, v1.ld, b.Hi, b.Wi, p[0], p[1], nullptr, mode, 0.f, 0, 0, b.stats0, b.coef0);
-    PUB_TRY(gn_backward(g0, pl.s1, b.dx, addp, add_ld, g[0], g[1], nullptr, dt, s));
+    if (rows0) PUB_TRY(gn_backward_from_du(g0, pl.s1, pl.du_part, rows0, b.dx, addp, add_ld, g[0], g[1], nullptr, dt, s));
+    else PUB_TRY(gn_backward(g0, pl.s1, b.dx, addp, add_ld, g[0], g[1], nullptr, dt, s));
   }
   return 0;
 }

@@ -186,3 +186,36 @@ def test_full_resolution_training_step_matches_the_oracle_on_the_gpu(name):
         if e > gtol:
             bad.append((n, e))
     assert not bad, (len(bad), worst, bad[:8])
+
+
+def test_fused_groupnorm_epilogues_match_the_separate_passes():
+    """GroupNorm statistics come from the epilogue of the conv that writes the tensor, and the GroupNorm-backward
+    prologue (du = g * keep/(1-p) * silu'(a x + b) and its two reductions) from the epilogue of the data-gradient conv
+    (pub_debug_option "gn_fuse" = 1, default).  Against the separate statistics / backward passes (gn_fuse = 0) on the
+    full-size training step: same loss to f32 summation-order noise, every gradient within bf16 rounding of du."""
+    import _native as N
+    from climex_synth import make_fields
+    m = canonical_model(compute_dtype="bf16", device="cuda")
+    m.train()
+    f = make_fields(B, R, R, 16, seed=13)
+    x, y = f["inputs"].cuda(), f["targets"].cuda()
+    eps = torch.randn(15, B, 32, generator=torch.Generator().manual_seed(14)).cuda()
+    runs, launches = {}, {}
+    try:
+        for opt in (0, 1):
+            N.lib().pub_debug_option(b"gn_fuse", opt)
+            N.manual_seed(123)
+            m.zero_grad(set_to_none=True)
+            l0 = N.lib().pub_launch_count()
+            total, recon, kl = m.elbo(x, y, None, M=15, eps=eps)
+            total.backward()
+            torch.cuda.synchronize()
+            launches[opt] = N.lib().pub_launch_count() - l0
+            runs[opt] = (float(total.detach()), {n: p.grad.clone() for n, p in m.named_parameters()})
+    finally:
+        N.lib().pub_debug_option(b"gn_fuse", 1)
+    assert launches[1] < launches[0] - 100, launches            # 57 statistics + 57 backward-reduction launches are gone
+    assert abs(runs[1][0] - runs[0][0]) < 1e-4 * abs(runs[0][0]), (runs[1][0], runs[0][0])
+    bad = [(n, rel_err(g, runs[0][1][n])) for n, g in runs[1][1].items()
+           if float(runs[0][1][n].norm()) > 1e-7 and rel_err(g, runs[0][1][n]) > 3e-2]
+    assert not bad, bad[:8]
