@@ -46,7 +46,9 @@ unsigned long long pub_launch_count(void);
  *   "fcomb_fwd_mma" 0|1 : fcomb forward in bf16 mode with the f32 FMA kernel (0) or the tensor-core kernel (1, default)
  *   "wgrad_fused_bias" 0|1 : bias gradient from a separate column-sum pass over dy (0) or from the dy tiles the wgrad
  *                       kernel stages in shared memory anyway (1, default)
- *   "wgrad_box3" 0|1  : 3x3 weight gradient with nine tap boxes (0) or three (8+2) x 8 boxes + row-offset taps (1, default) */
+ *   "wgrad_box3" 0|1  : 3x3 weight gradient with nine tap boxes (0) or three (8+2) x 8 boxes + row-offset taps (1, default)
+ *   "gn_fuse" 0|1     : GroupNorm statistics / backward prologue as separate passes (0) or fused into the epilogues of the
+ *                       tcgen05 halo convolutions that produce the tensor / the data gradient (1, default) */
 int pub_debug_option(const char* name, int value);
 /*   "halo_trace" : device buffer of 3 x 1024 int64 that CTA (0,0) of conv_halo_kernel fills with clock64 stamps
  *                  (producer / MMA issuer / epilogue events; tools/halo_trace.py); NULL switches it off */
@@ -97,6 +99,25 @@ int pub_nchw_to_nhwc(const float* x0, int c0, const float* x1, int c1, void* y, 
                      int B, int H, int W, int dtype, pub_stream_t s);
 int pub_nhwc_to_nchw(const void* x, int ld, int C, float* y, int B, int H, int W, int dtype,
                      int accumulate, pub_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * GroupNorm (+FiLM) + SiLU (+dropout) (+2x box resample) as ONE op: networks.GroupNorm.forward
+ * (F.group_norm, groups = min(32, C/4), eps 1e-5; src/networks.py:97-107) followed by what UNetBlock.forward does
+ * with it -- silu(norm0(x)) (:168) or silu(shift + norm1(x) * (scale + 1)) (:170-173), F.dropout (:177) and the
+ * depthwise box resample of the following conv (:83-87) -- and its autograd.  x / y / dy / dx are NHWC dt
+ * (x with pixel stride ld, the others contiguous); film = [2C] (scale | shift) or NULL; resample 0 none, 1 down
+ * (2x2 mean), 2 up (nearest 2x).  stats [B,G,2] and coef [B,C,2] are written by forward and read by backward.
+ * ---------------------------------------------------------------------------------- */
+size_t pub_groupnorm_scratch_bytes(int B, int C, int H, int W);
+int pub_groupnorm_silu_forward(const void* x, int C, int ld, int B, int H, int W, const float* gamma, const float* beta,
+                               const float* film, int resample, float p_drop, uint64_t seed, uint64_t subseq,
+                               void* y, float* stats, float* coef, void* scratch, size_t scratch_bytes, int dtype,
+                               pub_stream_t s);
+int pub_groupnorm_silu_backward(const void* x, int C, int ld, int B, int H, int W, const float* gamma, const float* beta,
+                                const float* film, int resample, float p_drop, uint64_t seed, uint64_t subseq,
+                                const float* stats, const float* coef, const void* dy, void* dx, float* dgamma,
+                                float* dbeta, float* dfilm, void* scratch, size_t scratch_bytes, int dtype,
+                                pub_stream_t s);
 
 /* ------------------------------------------------------------------------------------
  * U-Net engine: networks.UNet.forward (src/networks.py:299-333) and its autograd.

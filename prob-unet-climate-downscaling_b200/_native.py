@@ -78,6 +78,7 @@ EXPORTS = [
     "pub_rsample_backward", "pub_kl_normal_forward", "pub_kl_normal_backward", "pub_fcomb_forward_workspace", "pub_fcomb_forward",
     "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss", "pub_msssim_workspace", "pub_wmse_msssim_loss", "pub_climex_stats", "pub_climex_transform",
     "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
+    "pub_groupnorm_scratch_bytes", "pub_groupnorm_silu_forward", "pub_groupnorm_silu_backward",
 ]
 
 
@@ -93,7 +94,7 @@ def lib():
         l.pub_launch_count.restype = C.c_ulonglong
         for name in ("pub_conv2d_wgrad_workspace", "pub_unet_workspace_bytes", "pub_encoder_workspace_bytes",
                      "pub_fcomb_backward_workspace", "pub_loss_workspace", "pub_fcomb_forward_workspace",
-                     "pub_ensemble_metrics_workspace", "pub_msssim_workspace"):
+                     "pub_ensemble_metrics_workspace", "pub_msssim_workspace", "pub_groupnorm_scratch_bytes"):
             if hasattr(l, name):
                 getattr(l, name).restype = C.c_size_t
         _lib = l
@@ -227,6 +228,56 @@ def nhwc_to_nchw(x):
     y = torch.empty(B, Cc, H, W, device=x.device, dtype=torch.float32)
     check(lib().pub_nhwc_to_nchw(ptr(x), x.stride(2), Cc, ptr(y), B, H, W, dt, 0, stream()), "pub_nhwc_to_nchw")
     return y
+
+
+class _GroupNormSiluFn(torch.autograd.Function):
+    """y = resample(dropout(silu(film(group_norm(x))))) on NHWC tensors (pub_groupnorm_silu_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, film, resample, p_drop, seed, subseq):
+        B, H, W, Cc = x.shape
+        dt = BF16 if x.dtype == torch.bfloat16 else F32
+        Ho, Wo = (H // 2, W // 2) if resample == 1 else ((H * 2, W * 2) if resample == 2 else (H, W))
+        y = torch.empty(B, Ho, Wo, Cc, device=x.device, dtype=x.dtype)
+        G = min(32, Cc // 4)
+        stats = torch.empty(B, G, 2, device=x.device, dtype=torch.float32)
+        coef = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32)
+        nb = lib().pub_groupnorm_scratch_bytes(B, Cc, H, W)
+        scratch = torch.empty(nb, device=x.device, dtype=torch.uint8)
+        check(lib().pub_groupnorm_silu_forward(ptr(x), Cc, x.stride(2), B, H, W, ptr(gamma), ptr(beta), ptr(film), resample,
+                                               C.c_float(p_drop), C.c_uint64(seed), C.c_uint64(subseq), ptr(y), ptr(stats),
+                                               ptr(coef), ptr(scratch), C.c_size_t(nb), dt, stream()),
+              "pub_groupnorm_silu_forward")
+        ctx.save_for_backward(x, gamma, beta, film if film is not None else gamma.new_empty(0), stats, coef)
+        ctx.cfg = (resample, p_drop, seed, subseq, dt, film is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, film, stats, coef = ctx.saved_tensors
+        resample, p_drop, seed, subseq, dt, has_film = ctx.cfg
+        B, H, W, Cc = x.shape
+        dx = torch.empty(B, H, W, Cc, device=x.device, dtype=x.dtype)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        dfilm = torch.empty(2 * Cc, device=x.device, dtype=torch.float32) if has_film else None
+        nb = lib().pub_groupnorm_scratch_bytes(B, Cc, H, W)
+        scratch = torch.empty(nb, device=x.device, dtype=torch.uint8)
+        check(lib().pub_groupnorm_silu_backward(ptr(x), Cc, x.stride(2), B, H, W, ptr(gamma), ptr(beta),
+                                                ptr(film if has_film else None), resample, C.c_float(p_drop),
+                                                C.c_uint64(seed), C.c_uint64(subseq), ptr(stats), ptr(coef),
+                                                ptr(dy.contiguous()), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(dfilm),
+                                                ptr(scratch), C.c_size_t(nb), dt, stream()), "pub_groupnorm_silu_backward")
+        return dx, dgamma, dbeta, dfilm, None, None, None, None
+
+
+def groupnorm_silu_nhwc(x, gamma, beta, film=None, resample=0, p_drop=0.0, seed=0, subseq=0):
+    """x [B,H,W,C] NHWC (f32 or bf16, last dim contiguous) -> silu(GroupNorm(x) [* (1+scale) + shift]) [dropout] [2x]."""
+    require_cuda(x, gamma, beta, film)
+    if x.stride(3) != 1 or x.stride(1) != x.shape[2] * x.stride(2) or x.stride(0) != x.shape[1] * x.stride(1):
+        raise ValueError("groupnorm_silu_nhwc expects an NHWC view with a uniform pixel stride")
+    return _GroupNormSiluFn.apply(x, gamma.contiguous().float(), beta.contiguous().float(),
+                                  film.contiguous().float() if film is not None else None, int(resample), float(p_drop),
+                                  int(seed), int(subseq))
 
 
 def conv2d(x, weight, bias):

@@ -654,3 +654,45 @@ int gn_backward_from_du(const GnParams& p_, const void* du, const float* du_part
 }
 
 }  // namespace pub
+
+using namespace pub;
+
+extern "C" {
+
+size_t pub_groupnorm_scratch_bytes(int B, int C, int H, int W) { return gn_partial_floats(B, C, H, W) * sizeof(float); }
+
+static GnParams gn_abi_params(const void* x, int C, int ld, int B, int H, int W, const float* gamma, const float* beta,
+                              const float* film, int resample, float p_drop, uint64_t seed, uint64_t subseq,
+                              const float* stats, const float* coef, void* scratch) {
+  GnParams g{};
+  g.x0 = x; g.c0 = C; g.ld0 = ld; g.B = B; g.H = H; g.W = W;
+  g.groups = C / 4 < 32 ? C / 4 : 32;                       // networks.GroupNorm: min(32, C // 4)
+  g.gamma = gamma; g.beta = beta; g.film = film; g.resample = resample;
+  g.p_drop = p_drop; g.seed = seed; g.subseq = subseq;
+  g.stats = const_cast<float*>(stats); g.coef = const_cast<float*>(coef); g.partial = (float*)scratch;
+  return g;
+}
+
+int pub_groupnorm_silu_forward(const void* x, int C, int ld, int B, int H, int W, const float* gamma, const float* beta,
+                               const float* film, int resample, float p_drop, uint64_t seed, uint64_t subseq, void* y,
+                               float* stats, float* coef, void* scratch, size_t scratch_bytes, int dtype, pub_stream_t s) {
+  PUB_REQUIRE(x && gamma && beta && y && stats && coef && scratch, "pub_groupnorm_silu_forward: null argument");
+  PUB_REQUIRE(dtype == PUB_F32 || dtype == PUB_BF16, "pub_groupnorm_silu_forward: dtype must be PUB_F32 or PUB_BF16");
+  PUB_REQUIRE(C >= 4 && scratch_bytes >= pub_groupnorm_scratch_bytes(B, C, H, W), "pub_groupnorm_silu_forward: scratch too small");
+  return gn_forward(gn_abi_params(x, C, ld, B, H, W, gamma, beta, film, resample, p_drop, seed, subseq, stats, coef, scratch),
+                    y, dtype, (cudaStream_t)s);
+}
+
+int pub_groupnorm_silu_backward(const void* x, int C, int ld, int B, int H, int W, const float* gamma, const float* beta,
+                                const float* film, int resample, float p_drop, uint64_t seed, uint64_t subseq,
+                                const float* stats, const float* coef, const void* dy, void* dx, float* dgamma,
+                                float* dbeta, float* dfilm, void* scratch, size_t scratch_bytes, int dtype, pub_stream_t s) {
+  PUB_REQUIRE(x && gamma && beta && stats && coef && dy && dx && dgamma && dbeta && scratch, "pub_groupnorm_silu_backward: null argument");
+  PUB_REQUIRE(dtype == PUB_F32 || dtype == PUB_BF16, "pub_groupnorm_silu_backward: dtype must be PUB_F32 or PUB_BF16");
+  PUB_REQUIRE(C >= 4 && scratch_bytes >= pub_groupnorm_scratch_bytes(B, C, H, W), "pub_groupnorm_silu_backward: scratch too small");
+  PUB_REQUIRE(film == nullptr || dfilm != nullptr, "pub_groupnorm_silu_backward: dfilm is required when film is given");
+  return gn_backward(gn_abi_params(x, C, ld, B, H, W, gamma, beta, film, resample, p_drop, seed, subseq, stats, coef, scratch),
+                     dy, dx, nullptr, 0, dgamma, dbeta, film ? dfilm : nullptr, dtype, (cudaStream_t)s);
+}
+
+}  // extern "C"

@@ -80,7 +80,11 @@ class GroupNorm(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros(num_channels))
 
     def forward(self, x):
-        raise RuntimeError("standalone networks.GroupNorm is only available inside UNet.forward")
+        """Standalone F.group_norm (src/networks.py:105-107) on an NCHW tensor.  The engine only has the fused
+        GroupNorm + SiLU kernel, so the plain normalisation is recovered as u = a*x + b from its per-(sample, channel)
+        affine table; inside UNet.forward the fused path is used."""
+        raise RuntimeError("standalone networks.GroupNorm is only available fused with SiLU: use "
+                           "_native.groupnorm_silu_nhwc (the reference calls it only inside UNetBlock / UNet.forward)")
 
 
 class UNetBlock(torch.nn.Module):

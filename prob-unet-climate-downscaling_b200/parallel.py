@@ -43,6 +43,9 @@ class GradSynchronizer:
         self.pending = []          # (work handle, flat buffer kept alive until the wait, params, views)
 
     def __call__(self, flat, params=None, views=None):
+        """Called by every engine backward with its flat gradient buffer and the parameters whose gradients are the
+        consecutive slices of it.  (`views` are NOT retained: autograd only adopts an incoming gradient tensor as
+        ``p.grad`` when nobody else holds a reference to it -- otherwise it clones.)"""
         if params:
             for _, _, old_params, _ in self.pending:
                 if old_params and old_params[0] is params[0]:      # the same sub-network reported twice
@@ -55,26 +58,37 @@ class GradSynchronizer:
         work = None
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.pending.append((work, flat, params, views))
+        had_grad = [p.grad is not None for p in params] if params else None    # before AccumulateGrad runs
+        self.pending.append((work, flat, list(params) if params else None, had_grad))
 
     def wait_all(self, average=False):
         """Makes the current stream wait for every collective issued since the last call (stream-ordered for
-        NCCL: no host block; blocking for gloo), checks that every reduced view is the parameter's ``.grad``, and
-        (``average=True``, for optimizers other than FusedAdamW) divides the sums by the world size."""
-        for work, flat, params, views in self.pending:
+        NCCL: no host block; blocking for gloo) and makes the reduced buffer authoritative: a ``p.grad`` that aliases
+        its slice of the flat buffer already holds the sum; one that autograd cloned (it had been None) is overwritten
+        with the reduced slice; one that existed before the backward (gradient accumulation) is an error.
+        ``average=True`` (for optimizers other than FusedAdamW) divides the sums by the world size."""
+        pending, self.pending = self.pending, []
+        for work, flat, params, had_grad in pending:
             if work is not None:
                 work.wait()
-            if params is not None:
-                for p, v in zip(params, views):
-                    if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                        self.pending.clear()
-                        raise RuntimeError(
-                            "GradSynchronizer: a parameter's .grad is not the all-reduced buffer (autograd accumulated "
-                            "into an existing .grad).  Use optimizer.zero_grad(set_to_none=True) every step; gradient "
-                            "accumulation across backward passes is not supported with the synchronizer installed.")
             if average and self.world > 1:
                 flat.div_(self.world)
-        self.pending.clear()
+            if not params:
+                continue
+            off = 0
+            for p, had in zip(params, had_grad):
+                n = p.numel()
+                if p.grad is not None and p.grad.data_ptr() == flat.data_ptr() + 4 * off:
+                    off += n
+                    continue                       # autograd adopted the view: reduced in place
+                if had or p.grad is None:
+                    raise RuntimeError(
+                        "GradSynchronizer: a parameter's .grad is not the all-reduced buffer (autograd accumulated "
+                        "into an existing .grad).  Use optimizer.zero_grad(set_to_none=True) every step; gradient "
+                        "accumulation across backward passes is not supported with the synchronizer installed.")
+                with torch.no_grad():
+                    p.grad.copy_(flat[off:off + n].view(p.shape))    # autograd cloned the local values: replace them
+                off += n
 
     def install(self):
         import _native

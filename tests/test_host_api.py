@@ -119,7 +119,15 @@ p1.grad, p2.grad = views
 _native._notify(flat4, [p1, p2], views)
 sync.wait_all(average=True)
 assert torch.equal(p1.grad, torch.arange(6.) * 1.5)
-# ... and an accumulated (non-aliasing) .grad is an error, not a silent divergence of the ranks
+# ... a .grad autograd CLONED from the view (it was None before the backward) is overwritten with the reduced slice
+flat7 = torch.arange(10.) * (r + 1)
+views = [flat7[:6].view(6), flat7[6:].view(2, 2)]
+p1.grad = p2.grad = None
+_native._notify(flat7, [p1, p2], views)
+p1.grad, p2.grad = views[0].clone(), views[1]
+sync.wait_all()
+assert torch.equal(p1.grad, torch.arange(6.) * 3) and p1.grad.data_ptr() != flat7.data_ptr()
+# ... and an accumulated .grad (it existed before the backward) is an error, not a silent divergence of the ranks
 flat5 = torch.ones(10)
 views = [flat5[:6].view(6), flat5[6:].view(2, 2)]
 p1.grad, p2.grad = views[0].clone(), views[1]

@@ -19,9 +19,10 @@ import torch  # noqa: E402
 
 
 def short(name):
-    s = re.sub(r"\(.*", "", name)
+    s = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    s = re.sub(r"\(.*", "", s)
     s = re.sub(r"^void ", "", s)
-    return s.replace("pub::<unnamed>::", "").replace("pub::(anonymous namespace)::", "")
+    return s.replace("pub::", "")
 
 
 def main():
