@@ -210,14 +210,26 @@ template <typename T> __device__ __forceinline__ float silu_grad_t(float x) {
   return fmaf(x * s, 1.f - s, s);
 }
 
-// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0): ONE Philox call,
-// 16 random bits per element, keep <=> u16 >= round(p * 65536)
-__device__ __forceinline__ void dropout_keep8(uint64_t seed, uint64_t subseq, int64_t e, uint32_t thresh, bool (&keep)[8]) {
-  const uint4 r = Philox::gen(seed, subseq, (uint64_t)(e >> 3));
-  keep[0] = (r.x & 0xFFFFu) >= thresh; keep[1] = (r.x >> 16) >= thresh;
-  keep[2] = (r.y & 0xFFFFu) >= thresh; keep[3] = (r.y >> 16) >= thresh;
-  keep[4] = (r.z & 0xFFFFu) >= thresh; keep[5] = (r.z >> 16) >= thresh;
-  keep[6] = (r.w & 0xFFFFu) >= thresh; keep[7] = (r.w >> 16) >= thresh;
+// Dropout mask (replaces F.dropout's generator, src/networks.py:177; distributional parity only -- for exact parity the
+// masks are exported, pub_unet_dropout_mask).  Counter-based: 16 random bits per element from a 32-bit integer mixer
+// (two multiply-xorshift rounds, the "lowbias32" constants) of (key ^ word index), key = mix of (seed, block
+// subsequence); keep <=> u16 >= round(p * 65536).  ~35 instructions per 8 elements -- the Philox4x32-10 stream used
+// before cost ~110 and made the fused GroupNorm-backward conv epilogue issue-bound (rsample keeps Philox).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint64_t subseq) {
+  return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) ^ mix32((uint32_t)subseq * 0x9E3779B9u + 0x85EBCA6Bu)));
+}
+// keep-mask of 8 consecutive NHWC elements starting at linear element index e (e % 8 == 0)
+__device__ __forceinline__ void dropout_keep8(uint32_t key, int64_t e, uint32_t thresh, bool (&keep)[8]) {
+  const uint32_t w = (uint32_t)(e >> 1);            // index of the first of four 32-bit words (two elements each)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t r = mix32(key ^ ((w + (uint32_t)q) * 0x9E3779B1u));
+    keep[2 * q] = (r & 0xFFFFu) >= thresh; keep[2 * q + 1] = (r >> 16) >= thresh;
+  }
 }
 __device__ __forceinline__ uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.f + 0.5f); }
 

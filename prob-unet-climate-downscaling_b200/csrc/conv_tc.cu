@@ -406,9 +406,14 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
 // at ~200 cycles per MMA; software producers (LDG + STS, then cp.async) were correct but their per-stage
 // fence.proxy.async lowers to MEMBAR.ALL.CTA, which waits for the prefetches in flight and serialises the pipeline.
 //
-// Warp roles (224 threads): 0 = halo + resident-weight TMA, 1 = MMA issuer, 2..5 = epilogue, 6 = weight-ring TMA.
+// Warp roles (352 threads): 0 = halo + resident-weight TMA, 1 = MMA issuer, 2 = weight-ring TMA, 3..10 = epilogue in
+// TWO groups of four warps: group 0 drains TMEM accumulator buffer 0 (even tiles of the CTA), group 1 buffer 1 (odd
+// tiles).  The epilogue of a tile is one long dependency chain per warp (TMEM load -> residual / GroupNorm-input loads
+// from L2 -> math -> shared-memory transposition for the fused statistics -> stores); with a single group it was the
+// critical path as soon as any GroupNorm work was fused into it (profiles/r02_gn_fuse_v1_nopdl.txt).  Two groups give
+// every tile two tile periods and put four epilogue warps (two CTAs per SM) on each scheduler.
 constexpr int HALO_W = 10, HALO_H = 18, HALO_PX = HALO_W * HALO_H;
-constexpr int HTHREADS = 224;
+constexpr int HTHREADS = 352;
 
 struct HaloArgs {
   int c0, c1;
@@ -424,7 +429,7 @@ struct HaloArgs {
   int relu;
   long long* trace;   // optional event trace of CTA (0,0) (tools/halo_trace.py): [role][1024] clock64 stamps
   // ---- fused GroupNorm work in the epilogue (template parameter EPI of conv_halo_kernel)
-  uint32_t epi_off;   // byte offset (from the aligned smem base) of the 4 x [32][33] f32 transposition buffers
+  uint32_t epi_off;   // byte offset (from the aligned smem base) of the 8 x [32][33] f32 transposition buffers
   // EPI_STATS: per-(tile, epilogue warp) per-channel (sum, sum of squares) of the values as STORED (rounded to the
   // storage type): rows [(tile * 4 + warp)][cout][2] -- the forward statistics of the GroupNorm that reads y
   float* stat_part;
@@ -466,7 +471,7 @@ __device__ __forceinline__ void warp_colsum32_sq(float* tsm, int lane, const flo
   } while (0)
 
 template <int ROWB_, int ES, int EPI>
-__global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                              const __grid_constant__ CUtensorMap tmA1,
                                                              const __grid_constant__ CUtensorMap tmW, HaloArgs a) {
   typedef typename std::conditional<ES == 2, bf16, float>::type T;
@@ -549,7 +554,7 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     if (lane == 0 && !a.resident) {
       // ---------------- weight ring: one [BN][KC] tile per (K block, tap), in the order the MMA warp consumes them
       int slot = 0; uint32_t phase = 0;
@@ -616,23 +621,27 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
       __syncwarp();
     }
   } else {
-    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+    // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4, group (accumulator buffer) = (warp - 3) / 4
     const int q = warp & 3;
+    const int grp = (warp - 3) >> 2;
     const int row = q * 32 + lane;
     const int xl = row & 7, yl = row >> 3;
     int it = 0;
     int trn = 0;
-    const bool trw = warp == 2 && lane == 0;
+    const bool trw = warp == 3 && lane == 0;
     float* tsm = nullptr;
-    if (EPI != EPI_PLAIN) tsm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + a.epi_off) + q * (32 * 33);
+    if (EPI != EPI_PLAIN)
+      tsm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + a.epi_off) + (grp * 4 + q) * (32 * 33);
     const uint32_t thresh = EPI == EPI_GNBWD ? drop_thresh(a.p_drop) : 0u;
+    const uint32_t dkey = EPI == EPI_GNBWD ? dropout_key(a.seed, a.subseq) : 0u;
     const float inv_keep = (EPI == EPI_GNBWD && a.p_drop > 0.f) ? 1.f / (1.f - a.p_drop) : 1.f;
     for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      if (buf != grp) continue;                        // the other group's tile
       int t = tile;
       const int tx = t % a.tiles_x; t /= a.tiles_x;
       const int ty = t % a.tiles_y; t /= a.tiles_y;
       const int64_t pix = ((int64_t)t * a.H + ty * 16 + yl) * a.W + tx * 8 + xl;
-      const int buf = it & 1;
       mbar_wait(accfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (trw) HALO_TR(2, trn);
@@ -687,7 +696,7 @@ __global__ void __launch_bounds__(HTHREADS) conv_halo_kernel(const __grid_consta
             Vec8<T>::load(xp + g * 8, f);
             if (a.p_drop > 0.f) {
               bool keep[8];
-              dropout_keep8(a.seed, a.subseq, pix * a.cout + n + g * 8, thresh, keep);
+              dropout_keep8(dkey, pix * a.cout + n + g * 8, thresh, keep);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] = keep[j] ? v[g * 8 + j] * inv_keep : 0.f;
             }
@@ -1123,7 +1132,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   const int cblk = cin / KC;
   const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);
   const size_t wres_bytes = (size_t)cblk * 9 * b_bytes;
-  const size_t epi_bytes = epi == EPI_PLAIN ? 0 : (size_t)4 * 32 * 33 * sizeof(float);   // transposition buffers
+  const size_t epi_bytes = epi == EPI_PLAIN ? 0 : (size_t)8 * 32 * 33 * sizeof(float);   // transposition buffers (8 epilogue warps)
   const bool small_tmem = 2 * a.BN <= 256;            // two CTAs per SM are possible
   const size_t budget2 = 110 * 1024 - 2048 - epi_bytes, budget1 = 222 * 1024 - 2048 - epi_bytes;
   const int min_a = 3;

@@ -178,38 +178,75 @@ __global__ void scale_kernel(float* __restrict__ y, const float* __restrict__ sc
 __device__ __forceinline__ float softplus_ref(float x, float c) { return x > 20.f ? x : logf(expf(x) + 1.f) - c; }
 
 // grid (blocks, C, T): per (t, c) CRPS = mean_p [ mean_j |x_j - y| - 1/(2 M^2) sum_{j,k} |x_j - x_k| ] and
-// MAE = mean_p | mean_j x_j - y |.  Members are transformed to real units on load when transform != 0.
+// MAE = mean_p | mean_j x_j - y |.  Members are transformed to real units on load when transform != 0
+// (residual_to_hr, src/climex_utils.py:277-285, then invert_transfo_3vars, results.ipynb cell 2).
+//
+// A thread owns one pixel of one variable: its M members live in REGISTERS (NP = M padded to a power of two with
+// +inf), are sorted by a fully unrolled bitonic network (compile-time indices only: no local memory), and the pair
+// term is the sorted form  sum_{j<k} |x_j - x_k| = sum_i (2 i - M + 1) x_(i)  -- O(M log^2 M) min/max instead of the
+// M (M - 1) / 2 = 4 950 subtract-abs-add triples per pixel at M = 100 (and a local-memory array) of the pairwise
+// loop.  Loads are coalesced: consecutive lanes read consecutive pixels of one member plane.
 constexpr int MET_MAXM = 128;
+__device__ __forceinline__ float metrics_member(const float* __restrict__ preds, const float* __restrict__ lrinterp,
+                                                const float* __restrict__ std_hr, int transform, int64_t t, int j, int M,
+                                                int c, int C, int HW, int p) {
+  const float* pj = preds + ((t * M + j) * C) * (int64_t)HW + p;
+  float v = pj[(int64_t)c * HW];
+  if (transform) {
+    const float* li = lrinterp + (t * C) * (int64_t)HW + p;
+    v = li[(int64_t)c * HW] + v * (std_hr[c] + 1e-10f);
+    if (c == 0) v = softplus_ref(v, 1e-7f) * 24.f * 60.f * 60.f;   // kgm2sTommday's own multiplication order
+    else if (c == 1) v = v - 273.15f;
+    else {
+      const float v1 = li[(int64_t)HW] + pj[(int64_t)HW] * (std_hr[1] + 1e-10f);
+      v = (softplus_ref(v, 1e-7f) + v1) - 273.15f;   // results.ipynb cell 2: softplus default c, KToC of the sum
+    }
+  }
+  return v;
+}
+
+template <int NP>
 __global__ void __launch_bounds__(128) metrics_kernel(const float* __restrict__ preds, const float* __restrict__ hr,
                                                       const float* __restrict__ lrinterp, const float* __restrict__ std_hr,
                                                       int transform, int M, int C, int HW, float* __restrict__ part) {
   __shared__ float red[4];
   const int t = blockIdx.z, c = blockIdx.y;
   float a_crps = 0.f, a_mae = 0.f;
+  const float inv_m = 1.f / (float)M;
   for (int p = blockIdx.x * 128 + threadIdx.x; p < HW; p += gridDim.x * 128) {
-    float x[MET_MAXM];
+    float x[NP];
     const float y = hr[((int64_t)t * C + c) * HW + p];
     float mean = 0.f, s1 = 0.f;
-    for (int j = 0; j < M; ++j) {
-      const float* pj = preds + (((int64_t)t * M + j) * C) * HW + p;
-      float v = pj[(int64_t)c * HW];
-      if (transform) {
-        const float* li = lrinterp + ((int64_t)t * C) * HW + p;
-        v = li[(int64_t)c * HW] + v * (std_hr[c] + 1e-10f);
-        if (c == 0) v = softplus_ref(v, 1e-7f) * 24.f * 60.f * 60.f;   // kgm2sTommday's own multiplication order
-        else if (c == 1) v = v - 273.15f;
-        else {
-          const float v1 = li[(int64_t)HW] + pj[(int64_t)HW] * (std_hr[1] + 1e-10f);
-          v = (softplus_ref(v, 1e-7f) + v1) - 273.15f;   // results.ipynb cell 2: softplus default c, KToC of the sum
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (j < M) {
+        const float v = metrics_member(preds, lrinterp, std_hr, transform, t, j, M, c, C, HW, p);
+        x[j] = v; mean += v; s1 += fabsf(v - y);
+      } else {
+        x[j] = __int_as_float(0x7f800000);   // +inf: sorts behind the real members
+      }
+    }
+    // bitonic sorting network, ascending
+#pragma unroll
+    for (int k = 2; k <= NP; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const int l = i ^ j;
+          if (l > i) {
+            const float lo = fminf(x[i], x[l]), hi = fmaxf(x[i], x[l]);
+            if ((i & k) == 0) { x[i] = lo; x[l] = hi; } else { x[i] = hi; x[l] = lo; }
+          }
         }
       }
-      x[j] = v; mean += v; s1 += fabsf(v - y);
     }
-    float s2 = 0.f;
-    for (int j = 1; j < M; ++j)
-      for (int k = 0; k < j; ++k) s2 += fabsf(x[j] - x[k]);
-    a_crps += s1 / M - s2 / ((float)M * M);
-    a_mae += fabsf(mean / M - y);
+    float s2 = 0.f;                                    // sum_{j<k} |x_j - x_k|
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+      if (i < M) s2 = fmaf((float)(2 * i + 1 - M), x[i], s2);
+    a_crps += s1 * inv_m - s2 * inv_m * inv_m;
+    a_mae += fabsf(mean * inv_m - y);
   }
   float tot = block_sum<128>(a_crps, red);
   const int64_t o = (((int64_t)t * C + c) * gridDim.x + blockIdx.x) * 2;
@@ -342,7 +379,12 @@ int pub_ensemble_metrics(const float* preds, const float* hr, const float* lrint
   PUB_REQUIRE(ws && ws_bytes >= pub_ensemble_metrics_workspace(T, C, HW), "pub_ensemble_metrics: workspace too small");
   float* part = (float*)ws;
   dim3 grid(nblk, C, T);
-  metrics_kernel<<<grid, 128, 0, (cudaStream_t)s>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  cudaStream_t st = (cudaStream_t)s;
+  if (M <= 8) metrics_kernel<8><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (M <= 16) metrics_kernel<16><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (M <= 32) metrics_kernel<32><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (M <= 64) metrics_kernel<64><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else metrics_kernel<128><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
   PUB_LAUNCH_CHECK();
   metrics_final_kernel<<<cdiv(T * C, 128), 128, 0, (cudaStream_t)s>>>(part, nblk, HW, T * C, crps_tc, mae_tc);
   PUB_LAUNCH_CHECK();

@@ -147,7 +147,7 @@ __device__ __forceinline__ void load_affine(const float* coef, int b, int C, int
 // gradient wrt the activated output at INPUT resolution, rebuilt from dy (output resolution) + dropout
 template <typename T>
 __device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__ dy, int b, int r, int64_t pix, int C,
-                                        int v, uint32_t thresh, float inv_keep, float (&g)[8]) {
+                                        int v, uint32_t thresh, uint32_t dkey, float inv_keep, float (&g)[8]) {
   if (p.resample == 0) {
     Vec8<T>::load(dy + pix * C + v * 8, g);
   } else {
@@ -172,7 +172,7 @@ __device__ __forceinline__ void load_gy(const GnParams& p, const T* __restrict__
   }
   if (p.p_drop > 0.f) {
     bool keep[8];
-    dropout_keep8(p.seed, p.subseq, pix * C + v * 8, thresh, keep);
+    dropout_keep8(dkey, pix * C + v * 8, thresh, keep);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
   }
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
     float a[8], bb[8];
     if (MODE == 1) load_affine(p.coef, b, C, v, a, bb);
     const uint32_t thresh = drop_thresh(p.p_drop);
+    const uint32_t dkey = dropout_key(p.seed, p.subseq);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     if (MODE == 0 || p.resample == 0) {
       // this thread's vector of pixel (b, 0) and its pixel pitch (the two sources of a virtual concat differ)
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
           rr.read(st, 1, g);
           if (p.p_drop > 0.f) {
             bool keep[8];
-            dropout_keep8(p.seed, p.subseq, e, thresh, keep);
+            dropout_keep8(dkey, e, thresh, keep);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
           }
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
         const int64_t pix = (int64_t)b * HW + r;
         float x[8], g[8];
         load_vec<T>(p, pix, v, x);
-        load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
+        load_gy<T>(p, dy, b, r, pix, C, v, thresh, dkey, inv_keep, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));
@@ -287,12 +288,24 @@ __global__ void gn_finalize_kernel(GnParams p, const float* __restrict__ part0, 
   if (wid >= p.B * p.groups) return;
   const int b = wid / p.groups, g = wid % p.groups;
   double s = 0.0, ss = 0.0;
-  for (int i = lane; i < nchunk * cpg; i += 32) {
-    const int k = i / cpg, c = g * cpg + i % cpg;
-    const float* row = c < w0 ? part0 + (((int64_t)b * nchunk + k) * w0 + c) * 2
-                              : part1 + (((int64_t)b * nchunk + k) * (C - w0) + (c - w0)) * 2;
-    const float2 v = *reinterpret_cast<const float2*>(row);
-    s += (double)v.x; ss += (double)v.y;
+  // four independent loads in flight per lane: with conv-emitted partials there are hundreds of rows per image and
+  // the loop is a chain of L2 round trips otherwise (fixed order: deterministic)
+  const int total = nchunk * cpg;
+  for (int i0 = lane; i0 < total; i0 += 128) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      v[u] = make_float2(0.f, 0.f);
+      if (i < total) {
+        const int k = i / cpg, c = g * cpg + i % cpg;
+        const float* row = c < w0 ? part0 + (((int64_t)b * nchunk + k) * w0 + c) * 2
+                                  : part1 + (((int64_t)b * nchunk + k) * (C - w0) + (c - w0)) * 2;
+        v[u] = *reinterpret_cast<const float2*>(row);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s += (double)v[u].x; ss += (double)v[u].y; }
   }
   s = warp_sum_d(s); ss = warp_sum_d(ss);
   const double n = (double)cpg * p.H * p.W;
@@ -323,6 +336,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
   const int HW = p.H * p.W;
   if (p.resample != 1) {
     const uint32_t thresh = drop_thresh(p.p_drop);
+    const uint32_t dkey = dropout_key(p.seed, p.subseq);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     const int rows = p.rows;
     const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
       for (int j = 0; j < 8; ++j) o[j] = silu_t<T>(fmaf(a[j], x[j], bb[j]));
       if (p.p_drop > 0.f) {
         bool keep[8];
-        dropout_keep8(p.seed, p.subseq, e, thresh, keep);
+        dropout_keep8(dkey, e, thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = keep[j] ? o[j] * inv_keep : 0.f;
       }
@@ -404,9 +418,15 @@ __global__ void gn_bwd_group_kernel(GnParams p, const float* __restrict__ part, 
   for (int ci = 0; ci < cpg; ++ci) {
     const int c = g * cpg + ci;
     float a1 = 0.f, a2 = 0.f;
-    for (int k = lane; k < nchunk; k += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2);
-      a1 += v.x; a2 += fmaf(-mean_g, v.x, v.y);
+    for (int k0 = lane; k0 < nchunk; k0 += 128) {        // four independent loads in flight per lane
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 32 * u;
+        v[u] = k < nchunk ? *reinterpret_cast<const float2*>(part + (((int64_t)b * nchunk + k) * C + c) * 2) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a1 += v[u].x; a2 += fmaf(-mean_g, v[u].x, v[u].y); }
     }
     a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { bsum[((int64_t)b * C + c) * 2] = a1; bsum[((int64_t)b * C + c) * 2 + 1] = rstd_g * a2; }
@@ -465,6 +485,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
   load_affine(p.coef, b, C, v, a, bb);
   load_affine(bcoef, b, C, v, c2, c3);
   const uint32_t thresh = drop_thresh(p.p_drop);
+  const uint32_t dkey = dropout_key(p.seed, p.subseq);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const int HW = p.H * p.W;
   const int rows = p.rows;
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
       rr.read(st, 1, g);
       if (!FROM_DU && p.p_drop > 0.f) {
         bool keep[8];
-        dropout_keep8(p.seed, p.subseq, e, thresh, keep);
+        dropout_keep8(dkey, e, thresh, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = keep[j] ? g[j] * inv_keep : 0.f;
       }
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
     const int64_t pix = (int64_t)b * HW + r;
     float x[8], g[8], o[8];
     load_vec<T>(p, pix, v, x);
-    load_gy<T>(p, dy, b, r, pix, C, v, thresh, inv_keep, g);
+    load_gy<T>(p, dy, b, r, pix, C, v, thresh, dkey, inv_keep, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float du = g[j] * silu_grad_t<T>(fmaf(a[j], x[j], bb[j]));

@@ -221,13 +221,11 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int B, int HW, i
                                     uint64_t subseq) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // NHWC linear element index
   if (e >= (int64_t)B * HW * C) return;
-  const uint4 r = Philox::gen(seed, subseq, (uint64_t)(e >> 3));  // same stream as norm.cu::dropout_keep8
-  const int j = (int)(e & 7);
-  const uint32_t word = (j >> 1) == 0 ? r.x : ((j >> 1) == 1 ? r.y : ((j >> 1) == 2 ? r.z : r.w));
-  const uint32_t u16 = (j & 1) ? (word >> 16) : (word & 0xFFFFu);
+  bool keep[8];
+  dropout_keep8(dropout_key(seed, subseq), e & ~(int64_t)7, drop_thresh(p), keep);   // same stream as norm.cu / conv_tc.cu
   const int c = (int)(e % C);
   const int64_t pix = e / C, b = pix / HW, q = pix % HW;
-  mask[(b * C + c) * HW + q] = u16 >= (uint32_t)(p * 65536.f + 0.5f) ? 1 : 0;
+  mask[(b * C + c) * HW + q] = keep[e & 7] ? 1 : 0;
 }
 
 }  // namespace
