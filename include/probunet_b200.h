@@ -74,6 +74,24 @@ typedef struct {
 } pub_conv_args;
 int pub_conv2d_forward(const pub_conv_args* a, pub_stream_t s);
 
+/* The same launch with GroupNorm work fused into its epilogue (bf16, 3x3, shapes pub_conv2d_fused_rows() accepts):
+ *   gn_bwd == 0: stat_part rows [B * rows][cout][2] receive per-channel (sum, sum of squares) of the stored output -- the
+ *                statistics partials of the GroupNorm that reads y (networks.GroupNorm, src/networks.py:105-107);
+ *   gn_bwd == 1: a data-gradient launch whose result g = dL/d(dropout(silu(a x + b))) is stored as
+ *                du = g * keep/(1-p) * silu'(a x + b) (the backward of src/networks.py:168,173,177), x = the GroupNorm's
+ *                input (gx0 | gx1 virtual concat, gc0 channels in gx0), gcoef = its [B][cout][2] affine table (a, b) as
+ *                written by pub_groupnorm_silu_forward; the rows receive (sum du, sum du * x).
+ * rows = pub_conv2d_fused_rows(a): partial rows per image (0: this shape / dtype / backend has no fused epilogue). */
+typedef struct {
+  float* stat_part;
+  int32_t gn_bwd;
+  const void* gx0; const void* gx1; int32_t gc0, gld0, gld1;
+  const float* gcoef;
+  float p_drop; uint64_t seed, subseq;
+} pub_conv_gn_args;
+int pub_conv2d_fused_rows(const pub_conv_args* a);
+int pub_conv2d_forward_fused(const pub_conv_args* a, const pub_conv_gn_args* g, pub_stream_t s);
+
 /* OIHW f32 master weight -> packed [tap][cout][cin] dt.  transpose_flip=1 builds the
  * data-gradient operator (taps mirrored, in/out channels swapped): [tap][cin][cout].  */
 int pub_pack_conv_weight(const float* w_oihw, void* packed, int cout, int cin, int ksize,

@@ -40,6 +40,12 @@ class ConvArgs(C.Structure):
                 ("relu", C.c_int32), ("dtype", C.c_int32), ("backend", C.c_int32)]
 
 
+class ConvGnArgs(C.Structure):
+    _fields_ = [("stat_part", C.c_void_p), ("gn_bwd", C.c_int32),
+                ("gx0", C.c_void_p), ("gx1", C.c_void_p), ("gc0", C.c_int32), ("gld0", C.c_int32), ("gld1", C.c_int32),
+                ("gcoef", C.c_void_p), ("p_drop", C.c_float), ("seed", C.c_uint64), ("subseq", C.c_uint64)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("x0", C.c_void_p), ("c0", C.c_int32), ("ld0", C.c_int32),
                 ("x1", C.c_void_p), ("c1", C.c_int32), ("ld1", C.c_int32),
@@ -79,6 +85,7 @@ EXPORTS = [
     "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss", "pub_msssim_workspace", "pub_wmse_msssim_loss", "pub_climex_stats", "pub_climex_transform",
     "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
     "pub_groupnorm_scratch_bytes", "pub_groupnorm_silu_forward", "pub_groupnorm_silu_backward",
+    "pub_conv2d_fused_rows", "pub_conv2d_forward_fused",
 ]
 
 
@@ -166,8 +173,12 @@ def pack_conv_weight(w, dtype, transpose_flip=False):
 
 
 def conv2d_nhwc(x0, w_packed, bias=None, x1=None, res=None, mask=None, relu=False, ksize=3, backend=None, out=None,
-                dtype=None):
-    """x0/x1/res/mask: NHWC views [B,H,W,C] (last-dim-contiguous, arbitrary pixel stride)."""
+                dtype=None, gn_stats=False, gn_bwd=None):
+    """x0/x1/res/mask: NHWC views [B,H,W,C] (last-dim-contiguous, arbitrary pixel stride).
+
+    gn_stats=True: also returns the GroupNorm statistics partials [B, rows, cout, 2] the epilogue emitted.
+    gn_bwd=dict(x0=, x1=None, coef=, p_drop=0.0, seed=0, subseq=0): a data-gradient launch with the GroupNorm-backward
+    prologue fused (returns (du, partials)); see pub_conv2d_forward_fused."""
     require_cuda(x0, w_packed)
     B, H, W, c0 = x0.shape
     dt = dtype if dtype is not None else (BF16 if x0.dtype == torch.bfloat16 else F32)
@@ -186,6 +197,22 @@ def conv2d_nhwc(x0, w_packed, bias=None, x1=None, res=None, mask=None, relu=Fals
     a.y, a.ldy = y.data_ptr(), y.stride(2)
     a.B, a.H, a.W, a.cout, a.ksize = B, H, W, cout, ksize
     a.relu, a.dtype, a.backend = int(relu), dt, _backend if backend is None else backend
+    if gn_stats or gn_bwd is not None:
+        rows = lib().pub_conv2d_fused_rows(C.byref(a))
+        if rows <= 0:
+            raise NativeError("this conv launch has no fused GroupNorm epilogue (pub_conv2d_fused_rows == 0)")
+        part = torch.empty(B, rows, cout, 2, device=x0.device, dtype=torch.float32)
+        g = ConvGnArgs()
+        g.stat_part = part.data_ptr()
+        if gn_bwd is not None:
+            gx0, gx1 = gn_bwd["x0"], gn_bwd.get("x1")
+            g.gn_bwd, g.gx0, g.gc0, g.gld0 = 1, gx0.data_ptr(), gx0.shape[3], gx0.stride(2)
+            if gx1 is not None:
+                g.gx1, g.gld1 = gx1.data_ptr(), gx1.stride(2)
+            g.gcoef = gn_bwd["coef"].data_ptr()
+            g.p_drop, g.seed, g.subseq = float(gn_bwd.get("p_drop", 0.0)), int(gn_bwd.get("seed", 0)), int(gn_bwd.get("subseq", 0))
+        check(lib().pub_conv2d_forward_fused(C.byref(a), C.byref(g), stream()), "pub_conv2d_forward_fused")
+        return y, part
     check(lib().pub_conv2d_forward(C.byref(a), stream()), "pub_conv2d_forward")
     return y
 

@@ -142,6 +142,22 @@ int pub_conv2d_forward(const pub_conv_args* a, pub_stream_t s) {
   return conv_forward(to_params(a), a->dtype, a->backend, (cudaStream_t)s);
 }
 
+int pub_conv2d_fused_rows(const pub_conv_args* a) {
+  if (!a || !a->x0 || !a->w || !a->y) return 0;
+  return conv_fused_rows(to_params(a), a->dtype, a->backend);
+}
+
+int pub_conv2d_forward_fused(const pub_conv_args* a, const pub_conv_gn_args* g, pub_stream_t s) {
+  PUB_REQUIRE(a && g && a->x0 && a->w && a->y && g->stat_part, "pub_conv2d_forward_fused: null argument");
+  ConvParams p = to_params(a);
+  PUB_REQUIRE(conv_fused_rows(p, a->dtype, a->backend) > 0, "pub_conv2d_forward_fused: no fused epilogue for this launch "
+              "(bf16 3x3, W %% 8 == 0, H %% 16 == 0, channels %% 32 == 0 through the tcgen05 halo kernel only)");
+  p.stat_part = g->stat_part; p.gn_bwd = g->gn_bwd;
+  p.gx0 = g->gx0; p.gx1 = g->gx1; p.gc0 = g->gc0; p.gld0 = g->gld0; p.gld1 = g->gld1; p.gcoef = g->gcoef;
+  p.p_drop = g->p_drop; p.seed = g->seed; p.subseq = g->subseq;
+  return conv_forward(p, a->dtype, a->backend, (cudaStream_t)s);
+}
+
 int pub_pack_conv_weight(const float* w, void* packed, int cout, int cin, int ksize, int dtype, int tflip,
                          pub_stream_t s) {
   PUB_REQUIRE(w && packed, "pub_pack_conv_weight: null argument");

@@ -142,6 +142,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive f32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ descriptors
 // smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
@@ -429,7 +441,7 @@ struct HaloArgs {
   int relu;
   long long* trace;   // optional event trace of CTA (0,0) (tools/halo_trace.py): [role][1024] clock64 stamps
   // ---- fused GroupNorm work in the epilogue (template parameter EPI of conv_halo_kernel)
-  uint32_t epi_off;   // byte offset (from the aligned smem base) of the 8 x [32][33] f32 transposition buffers
+  uint32_t epi_off;   // byte offset (from the aligned smem base) of the 8 x [16][33] f32 transposition buffers
   // EPI_STATS: per-(tile, epilogue warp) per-channel (sum, sum of squares) of the values as STORED (rounded to the
   // storage type): rows [(tile * 4 + warp)][cout][2] -- the forward statistics of the GroupNorm that reads y
   float* stat_part;
@@ -441,28 +453,6 @@ struct HaloArgs {
   float p_drop; uint64_t seed, subseq;
 };
 enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_GNBWD = 2 };
-
-// per-channel sums over the 32 pixels (lanes) of a warp's 32 x 32 accumulator chunk: every lane writes its 32 values
-// as a column of a [32][33] f32 buffer (conflict-free both ways), then lane j adds up row j in a fixed order
-__device__ __forceinline__ float warp_colsum32(float* tsm, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) tsm[j * 33 + lane] = v[j];
-  __syncwarp();
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) s += tsm[lane * 33 + i];
-  __syncwarp();
-  return s;
-}
-__device__ __forceinline__ void warp_colsum32_sq(float* tsm, int lane, const float (&v)[32], float& s1, float& s2) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) tsm[j * 33 + lane] = v[j];
-  __syncwarp();
-  s1 = 0.f; s2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) { const float x = tsm[lane * 33 + i]; s1 += x; s2 = fmaf(x, x, s2); }
-  __syncwarp();
-}
 
 // role r, event counter n: stamps clock64 into trace[r*1024 + n]
 #define HALO_TR(r, n)                                                                   \
@@ -622,6 +612,11 @@ __global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_con
     }
   } else {
     // ---------------- epilogue: warps 3..10; TMEM lane quarter = warp % 4, group (accumulator buffer) = (warp - 3) / 4
+    // The accumulator is drained in 16-column pieces: 32-column pieces plus the fused GroupNorm arithmetic needed more
+    // than the 80 registers two resident CTAs leave each thread, and with ~216 KB of the SM configured as shared memory
+    // the spills missed L1 (hit rate 4.5 %) -- ~8 000 cycles per tile in the GroupNorm-backward epilogue (ncu,
+    // profiles/r02_gnbwd_epilogue_spills_ncu.txt).
+    constexpr int CW = 16;
     const int q = warp & 3;
     const int grp = (warp - 3) >> 2;
     const int row = q * 32 + lane;
@@ -631,10 +626,11 @@ __global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_con
     const bool trw = warp == 3 && lane == 0;
     float* tsm = nullptr;
     if (EPI != EPI_PLAIN)
-      tsm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + a.epi_off) + (grp * 4 + q) * (32 * 33);
+      tsm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + a.epi_off) + (grp * 4 + q) * (CW * 33);
     const uint32_t thresh = EPI == EPI_GNBWD ? drop_thresh(a.p_drop) : 0u;
     const uint32_t dkey = EPI == EPI_GNBWD ? dropout_key(a.seed, a.subseq) : 0u;
     const float inv_keep = (EPI == EPI_GNBWD && a.p_drop > 0.f) ? 1.f / (1.f - a.p_drop) : 1.f;
+    const int cl = lane & (CW - 1), half = lane >> 4;      // column sums: lane (cl, half) adds half a column
     for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       if (buf != grp) continue;                        // the other group's tile
@@ -645,26 +641,31 @@ __global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_con
       mbar_wait(accfull0 + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (trw) HALO_TR(2, trn);
-      for (int cb = 0; cb < a.BN; cb += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.BN + cb), r);
-        if (cb + 32 >= a.BN) {
+      for (int cb = 0; cb < a.BN; cb += CW) {
+        float v[CW];
+        {
+          uint32_t r[CW];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.BN + cb), r);
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (cb + CW >= a.BN) {                           // last piece read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(accempty0 + 8 * buf);
         }
         const int n = n0 + cb;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (a.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + n + j);
+          for (int j = 0; j < CW; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
         }
         if (a.res) {
           const T* rp = (const T*)a.res + pix * a.ld_res + n;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < CW / 8; ++g) {
             float f[8];
             Vec8<T>::load(rp + g * 8, f);
 #pragma unroll
@@ -673,27 +674,39 @@ __global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_con
         }
         if (a.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (a.mask) {
           const T* mp = (const T*)a.mask + pix * a.ld_mask + n;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < CW / 8; ++g) {
             float f[8];
             Vec8<T>::load(mp + g * 8, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[g * 8 + j] = f[j] > 0.f ? v[g * 8 + j] : 0.f;
           }
         }
-        float xs[EPI == EPI_GNBWD ? 32 : 1];
+        uint4 xr[EPI == EPI_GNBWD ? CW / 8 : 1];          // the GroupNorm input of this pixel, raw bf16 (kept packed)
         if (EPI == EPI_GNBWD) {
           // v = dL/d(dropout(silu(a x + b)))  ->  du = v * keep / (1 - p) * silu'(a x + b)
+          // The (a, b) pairs of this piece's channels are fetched by ONE coalesced load (lane = channel) and broadcast
+          // through shared memory (a chain of dependent uniform loads per thread costs an L2 round trip each).  The
+          // first 2 * CW floats of the warp's transposition buffer hold them until the sums start.
           const T* xp = n < a.gc0 ? (const T*)a.gx0 + pix * a.gld0 + n : (const T*)a.gx1 + pix * a.gld1 + (n - a.gc0);
-          const float4* cf = reinterpret_cast<const float4*>(a.gcoef + ((int64_t)t * a.cout + n) * 2);
+          float2 ab = make_float2(0.f, 0.f);
+          if (lane < CW) ab = __ldg(reinterpret_cast<const float2*>(a.gcoef + ((int64_t)t * a.cout + n + lane) * 2));
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < CW / 8; ++g) xr[g] = __ldg(reinterpret_cast<const uint4*>(xp + g * 8));
+          if (lane < CW) reinterpret_cast<float2*>(tsm)[lane] = ab;
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < CW / 8; ++g) {
             float f[8];
-            Vec8<T>::load(xp + g * 8, f);
+            {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[g]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { const float2 q2 = __bfloat1622float2(h2[i]); f[2 * i] = q2.x; f[2 * i + 1] = q2.y; }
+            }
             if (a.p_drop > 0.f) {
               bool keep[8];
               dropout_keep8(dkey, pix * a.cout + n + g * 8, thresh, keep);
@@ -702,36 +715,58 @@ __global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_con
             }
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
-              const float4 c4 = __ldg(cf + (g * 8 + j) / 2);      // (a, b) of two channels
+              const float4 c4 = reinterpret_cast<const float4*>(tsm)[(g * 8 + j) / 2];      // (a, b) of two channels
               v[g * 8 + j] *= silu_grad_t<T>(fmaf(c4.x, f[j], c4.y));
               v[g * 8 + j + 1] *= silu_grad_t<T>(fmaf(c4.z, f[j + 1], c4.w));
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xs[g * 8 + j] = f[j];
           }
+          __syncwarp();                                  // the coefficient slots are reused by the column sums below
         }
         T* yp = (T*)a.y + pix * a.ldy + n;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < CW / 8; ++g) {
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = ES == 4 ? round_tf32(v[g * 8 + j]) : v[g * 8 + j];
           Vec8<T>::store(yp + g * 8, f);
         }
         if (EPI != EPI_PLAIN) {
-          // statistics of the values as the consumer will read them (rounded to the storage type)
+          // per-channel sums over the warp's 32 pixels of the values as the consumer will read them (rounded to the
+          // storage type): every lane writes its CW values as a column of a [CW][33] f32 buffer (conflict-free both
+          // ways), then lane (cl, half) adds 16 pixels of channel cl in a fixed order and the halves are combined
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = to_f<T>(from_f<T>(v[j]));
-          float s1, s2;
-          if (EPI == EPI_STATS) {
-            warp_colsum32_sq(tsm, lane, v, s1, s2);
-          } else {
-            s1 = warp_colsum32(tsm, lane, v);
+          for (int j = 0; j < CW; ++j) v[j] = to_f<T>(from_f<T>(v[j]));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= xs[j];
-            s2 = warp_colsum32(tsm, lane, v);
+          for (int j = 0; j < CW; ++j) tsm[j * 33 + lane] = v[j];
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = tsm[cl * 33 + half * 16 + i];
+            s1 += x;
+            if (EPI == EPI_STATS) s2 = fmaf(x, x, s2);
           }
-          *reinterpret_cast<float2*>(a.stat_part + ((int64_t)(tile * 4 + q) * a.cout + n + lane) * 2) = make_float2(s1, s2);
+          __syncwarp();
+          if (EPI == EPI_GNBWD) {
+#pragma unroll
+            for (int g = 0; g < CW / 8; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[g]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 q2 = __bfloat1622float2(h2[i]);
+                tsm[(g * 8 + 2 * i) * 33 + lane] = v[g * 8 + 2 * i] * q2.x;
+                tsm[(g * 8 + 2 * i + 1) * 33 + lane] = v[g * 8 + 2 * i + 1] * q2.y;
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s2 += tsm[cl * 33 + half * 16 + i];
+            __syncwarp();
+          }
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (half == 0)
+            *reinterpret_cast<float2*>(a.stat_part + ((int64_t)(tile * 4 + q) * a.cout + n + cl) * 2) = make_float2(s1, s2);
         }
       }
       if (trw) HALO_TR(2, trn);
@@ -1132,7 +1167,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   const int cblk = cin / KC;
   const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);
   const size_t wres_bytes = (size_t)cblk * 9 * b_bytes;
-  const size_t epi_bytes = epi == EPI_PLAIN ? 0 : (size_t)8 * 32 * 33 * sizeof(float);   // transposition buffers (8 epilogue warps)
+  const size_t epi_bytes = epi == EPI_PLAIN ? 0 : (size_t)8 * 16 * 33 * sizeof(float);   // transposition buffers (8 epilogue warps)
   const bool small_tmem = 2 * a.BN <= 256;            // two CTAs per SM are possible
   const size_t budget2 = 110 * 1024 - 2048 - epi_bytes, budget1 = 222 * 1024 - 2048 - epi_bytes;
   const int min_a = 3;
