@@ -35,7 +35,7 @@ extern int g_opt_conv_halo;   // -1: from PUB_CONV_HALO (default on); 0/1 forced
 extern int g_opt_wgrad_box3;  // 1 (default): 3x3 wgrad loads x as three (8+2) x 8 boxes; 0: nine tap boxes (A/B: pub_debug_option("wgrad_box3", v))
 extern int g_opt_fcomb_fwd_mma;  // fcomb forward in bf16 mode: 1 = tensor-core kernel (bf16 operands), 0 = f32 FMA kernel
 extern int g_opt_wgrad_fused_bias;  // 1 (default): bias gradients summed from the dy tiles staged by the wgrad kernel; 0: separate pass
-extern int g_opt_gn_fuse;  // 1 (default): GroupNorm statistics / backward prologue fused into the halo conv epilogues; 0: separate passes
+extern int g_opt_gn_fuse;  // GroupNorm work fused into the halo conv epilogues: 0 none, 1 forward statistics, 2 + backward prologue
 extern long long* g_halo_trace;  // device buffer for conv_halo_kernel event stamps (pub_debug_pointer("halo_trace", p)), else null
 extern unsigned long long g_launch_count;  // kernels enqueued by this library (bench.py's gpu_launches)
 #define PUB_LAUNCH_CHECK()          \

@@ -375,7 +375,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
     ConvParams cd = conv_params(dy, u->out_ch, u->out_ch, nullptr, 0, 0, pl.wp_out, nullptr, nullptr, 0, pl.s1, fc, B, H, W, fc, 3);
     GnParams go = gn_params(pl, last.out, fc, fc, nullptr, 0, 0, H, W, p[0], p[1], nullptr, 0, 0.f, 0, 0, pl.stats_o, pl.coef_o);
     // the data-gradient conv stores du = g * silu'(a x + b) and its partial sums (GroupNorm-backward prologue fused)
-    const int rows = conv_fused_rows(cd, dt, backend);
+    const int rows = g_opt_gn_fuse >= 2 ? conv_fused_rows(cd, dt, backend) : 0;
     if (rows) { cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = last.out; cd.gc0 = fc; cd.gld0 = fc; cd.gcoef = pl.coef_o; }
     PUB_TRY(conv_forward(cd, dt, backend, s));
     if (rows) PUB_TRY(gn_backward_from_du(go, pl.s1, pl.du_part, rows, pl.dx_last, nullptr, 0, g[0], g[1], nullptr, dt, s));
@@ -441,7 +441,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
       ConvParams cd = conv_params(gp, b.d.cout, gld, nullptr, 0, 0, b.wp1, nullptr, nullptr, 0, pl.s1, b.d.cout, B, b.Ho, b.Wo, b.d.cout, 3);
-      rows1 = conv_fused_rows(cd, dt, backend);
+      rows1 = g_opt_gn_fuse >= 2 ? conv_fused_rows(cd, dt, backend) : 0;
       if (rows1) {
         cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = b.h; cd.gc0 = b.d.cout; cd.gld0 = b.d.cout; cd.gcoef = b.coef1;
         cd.p_drop = pdrop; cd.seed = seed; cd.subseq = (uint64_t)i;
@@ -459,7 +459,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       wp.B = B; wp.H = b.Ho; wp.W = b.Wo; wp.cout = b.d.cout; wp.ks = 3;
       PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
       ConvParams cd = conv_params(pl.s2, b.d.cout, b.d.cout, nullptr, 0, 0, b.wp0, nullptr, nullptr, 0, pl.s1, b.d.cin, B, b.Ho, b.Wo, b.d.cin, 3);
-      rows0 = mode == 0 ? conv_fused_rows(cd, dt, backend) : 0;     // resampling blocks: GroupNorm at another resolution
+      rows0 = (mode == 0 && g_opt_gn_fuse >= 2) ? conv_fused_rows(cd, dt, backend) : 0;   // resampling blocks: GroupNorm at another resolution
       if (rows0) {
         cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = v0.p; cd.gx1 = v1.p; cd.gc0 = b.c0; cd.gld0 = v0.ld; cd.gld1 = v1.ld;
         cd.gcoef = b.coef0;
