@@ -36,6 +36,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "ensemble"],
+                    help="train: BASELINE.json configs[2] (train samples/s, the headline metric); ensemble: configs[3] "
+                         "(prior-sampling ensemble members/s: M members per field + CRPS/MAE, fields sharded over the GPUs)")
+    ap.add_argument("--fields", type=int, default=512, help="ensemble workload: fields per GPU and pass (weak scaling)")
+    ap.add_argument("--field-batch", type=int, default=64, help="ensemble workload: fields per model call")
+    ap.add_argument("--ens-members", type=int, default=100, help="ensemble workload: members per field")
+    ap.add_argument("--strong", action="store_true", help="train: --batch is the GLOBAL batch, split over the GPUs (strong scaling)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--res", type=int, default=128)
     ap.add_argument("--members", type=int, default=15, help="ELBO ensemble size M (src/main.py:136)")
@@ -167,7 +174,9 @@ def run_reference(args):
         "impl": "reference", "metric": "train_samples_per_s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": dict(workload_config(args), per_gpu_batch=b, workload_per_gpu_batch=args.batch,
+                       sample=f"each step is one training step on a batch of {b} of the workload's {args.batch} samples (same "
+                              "model, loss, resolution, optimizer); samples/s is per sample, so the figures are comparable"),
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} train steps of batch {b} (same model/loss/resolution; oracle/probunet_oracle.py + torch.optim.AdamW, fp32)"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -189,18 +198,19 @@ def workload_config(args):
 # roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions)
 # ------------------------------------------------------------------------------------------------
 def conv_inventory(model, B, H):
-    """Every conv launch of one training step: (kind, c0, c1, cout, res, ks) -> count."""
+    """Every conv launch of one training step: (kind, c0, c1, cout, res, ks, dtype) -> count.  dtype is the one the
+    step really runs the layer in: the U-Net in bf16, the two Gaussian encoders in tf32 (f32 storage, kind::tf32)."""
     from networks import UNetBlock
     inv = {}
 
-    def add(kind, c0, c1, cout, r, ks):
-        inv[(kind, c0, c1, cout, r, ks)] = inv.get((kind, c0, c1, cout, r, ks), 0) + 1
+    def add(kind, c0, c1, cout, r, ks, dt):
+        inv[(kind, c0, c1, cout, r, ks, dt)] = inv.get((kind, c0, c1, cout, r, ks, dt), 0) + 1
 
-    def conv3(cin, cout, r, ks=3, c1=0, dgrad=True):
-        add("fwd", cin - c1, c1, cout, r, ks)
-        add("wgrad", cin - c1, c1, cout, r, ks)
+    def conv3(cin, cout, r, ks=3, c1=0, dgrad=True, dt="bf16"):
+        add("fwd", cin - c1, c1, cout, r, ks, dt)
+        add("wgrad", cin - c1, c1, cout, r, ks, dt)
         if dgrad:
-            add("fwd", cout, 0, cin, r, ks)          # data gradient runs the forward kernel on transposed weights
+            add("fwd", cout, 0, cin, r, ks, dt)      # data gradient runs the forward kernel on transposed weights
 
     r, c = H, model.unet.in_channels
     skips = []
@@ -221,36 +231,42 @@ def conv_inventory(model, B, H):
         if not is_dec:
             skips.append(c)
     conv3(c, model.unet.out_channels, r)
+    import _native as N
+    enc_dt = {N.TF32: "tf32", N.BF16: "bf16", N.F32: "f32"}[N.resolve_encoder_dtype(model.unet.compute_dtype)]
     for encmod in (model.prior, model.posterior):
         rr, cc = H, encmod.input_channels
         for i, nf in enumerate(encmod.num_filters):
             if i: rr //= 2
             for k in range(3):
-                conv3(cc, nf, rr, dgrad=not (i == 0 and k == 0)); cc = nf
+                conv3(cc, nf, rr, dgrad=not (i == 0 and k == 0), dt=enc_dt); cc = nf
     return inv
 
 
-def conv_roofline(model, B, H, pk, pk_kind):
+def conv_replay(model, B, H, pk):
+    """Every distinct tcgen05 conv launch of the step replayed ALONE in the dtype the step runs it in, L2 flushed,
+    median of 3 (isolated timings: burst peak as the denominator)."""
     import _native as N
     inv = conv_inventory(model, B, H)
     flush = torch.empty(256 * 1024 * 1024, device="cuda", dtype=torch.uint8)
-    tot_t, tot_f, tc_t, tc_f = 0.0, 0.0, 0.0, 0.0
+    tot_t, tot_f = 0.0, 0.0
     detail = []
     g = torch.Generator(device="cuda").manual_seed(0)
-    for (kind, c0, c1, cout, r, ks), cnt in sorted(inv.items()):
-        if (c0 + c1) % 32 or cout % 32:
-            continue                                  # first/last tiny-channel layers run on the SIMT kernel
-        x0 = torch.randn(B, r, r, c0, device="cuda", generator=g).bfloat16()
-        x1 = torch.randn(B, r, r, c1, device="cuda", generator=g).bfloat16() if c1 else None
+    for (kind, c0, c1, cout, r, ks, dt), cnt in sorted(inv.items()):
+        if (c0 + c1) % 32 or cout % 32 or dt == "f32":
+            continue                                  # first/last tiny-channel layers run on the SIMT kernels
+        ndt = N.BF16 if dt == "bf16" else N.TF32
+        cast = (lambda t: t.bfloat16()) if dt == "bf16" else (lambda t: t.float())
+        x0 = cast(torch.randn(B, r, r, c0, device="cuda", generator=g))
+        x1 = cast(torch.randn(B, r, r, c1, device="cuda", generator=g)) if c1 else None
         flops = 2.0 * B * r * r * (c0 + c1) * cout * ks * ks
         ts = []
         if kind == "fwd":
-            w = torch.randn(ks * ks, cout, c0 + c1, device="cuda", generator=g).bfloat16()
-            y = torch.empty(B, r, r, cout, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: N.conv2d_nhwc(x0, w, None, x1=x1, ksize=ks, out=y)
+            w = cast(torch.randn(ks * ks, cout, c0 + c1, device="cuda", generator=g))
+            y = torch.empty(B, r, r, cout, device="cuda", dtype=x0.dtype)
+            fn = lambda: N.conv2d_nhwc(x0, w, None, x1=x1, ksize=ks, out=y, dtype=ndt)
         else:
-            dy = torch.randn(B, r, r, cout, device="cuda", generator=g).bfloat16()
-            fn = lambda: N.conv2d_wgrad_nhwc(x0, dy, ks, x1=x1, want_bias=False)
+            dy = cast(torch.randn(B, r, r, cout, device="cuda", generator=g))
+            fn = lambda: N.conv2d_wgrad_nhwc(x0, dy, ks, x1=x1, want_bias=False, dtype=ndt)
         fn()
         for _ in range(3):
             flush.zero_()
@@ -259,17 +275,246 @@ def conv_roofline(model, B, H, pk, pk_kind):
             ts.append(e0.elapsed_time(e1) * 1e-3)
         t = statistics.median(ts)
         tot_t += t * cnt; tot_f += flops * cnt
-        detail.append({"kind": kind, "c0": c0, "c1": c1, "cout": cout, "res": r, "ks": ks, "count": cnt,
+        detail.append({"kind": kind, "c0": c0, "c1": c1, "cout": cout, "res": r, "ks": ks, "dtype": dt, "count": cnt,
                        "us": round(t * 1e6, 1), "tflops": round(flops / t / 1e12, 1)})
-    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    burst = pk["bf16_tflops"]
     ach = tot_f / tot_t / 1e12
+    return {"achieved": ach, "peak": burst, "frac": ach / burst, "conv_time_per_step_ms": tot_t * 1e3,
+            "conv_gflop_per_step": tot_f / 1e9,
+            "how": "each distinct conv launch of the step replayed alone through the C ABI in its real dtype (U-Net bf16, "
+                   "Gaussian encoders tf32) with CUDA events on the launching stream, L2 flushed (256 MiB write) before every "
+                   "timed launch, median of 3; denominator = MEASURED_PEAKS.json bf16_tflops (burst: isolated timings)"}, detail
+
+
+CONV_FAMILY = ("conv_halo_kernel", "conv_tc_kernel", "wgrad_tc_kernel")
+
+
+def in_step_kernel_times(step_fn, N):
+    """Per-kernel device time of ONE real step (CUPTI activity records through torch.profiler), with programmatic
+    dependent launch switched off for that step so that kernel durations do not overlap."""
+    from torch.profiler import profile, ProfilerActivity
+    N.lib().pub_debug_option(b"pdl", 0)
+    try:
+        step_fn(); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn()
+            torch.cuda.synchronize()
+    finally:
+        N.lib().pub_debug_option(b"pdl", 1)
+    agg, first, last = {}, None, None
+    for ev in prof.events():
+        if ev.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        dur = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        nm = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        nm = nm.split("(")[0].replace("void ", "").replace("pub::", "")
+        c = agg.setdefault(nm, [0, 0.0]); c[0] += 1; c[1] += dur
+        tr = ev.time_range
+        first = tr.start if first is None else min(first, tr.start)
+        last = tr.end if last is None else max(last, tr.end)
+    return agg, (last - first) / 1e3 if first is not None else None
+
+
+def conv_roofline(model, B, H, pk, pk_kind, step_fn, N):
+    """roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions): algorithmic FLOPs of all conv
+    launches of one step / their device time INSIDE a real step, against the sustained cuBLAS bf16 peak."""
+    replay, detail = conv_replay(model, B, H, pk)
+    agg, span_ms = in_step_kernel_times(step_fn, N)
+    fam = {k: v for k, v in agg.items() if any(k.startswith(f) for f in CONV_FAMILY)}
+    conv_ms = sum(v[1] for v in fam.values()) / 1e3
+    total_ms = sum(v[1] for v in agg.values()) / 1e3
+    peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    ach = replay["conv_gflop_per_step"] / conv_ms / 1e3 if conv_ms > 0 else 0.0
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-            "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
-            "kernel": "conv_tc_kernel / conv_halo_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM), all conv launches of one step",
-            "how": "each distinct conv launch of the step replayed alone through the C ABI with CUDA events on the "
-                   "launching stream, L2 flushed (256 MiB write) before every timed launch, median of 3; "
-                   "achieved = sum(count*2*B*H*W*Cin*Cout*k*k) / sum(count*time)",
-            "conv_time_per_step_ms": tot_t * 1e3, "conv_gflop_per_step": tot_f / 1e9}, detail
+            "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)",
+            "kernel": "conv_halo_kernel / conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM; bf16 U-Net + tf32 Gaussian "
+                      "encoders), all launches of one training step",
+            "how": "achieved = sum over the step's tcgen05 conv launches of 2*B*H*W*Cin*Cout*k*k / their summed device time "
+                   "inside ONE real training step (CUPTI kernel records via torch.profiler, programmatic dependent launch "
+                   "off for that step so durations do not overlap)",
+            "conv_time_in_step_ms": conv_ms, "kernel_time_in_step_ms": total_ms, "profiled_step_span_ms": span_ms,
+            "share_of_step": conv_ms / total_ms if total_ms else None,
+            "conv_gflop_per_step": replay["conv_gflop_per_step"], "conv_launches_in_step": sum(v[0] for v in fam.values()),
+            "isolated_replay": replay,
+            "step_kernels_top": [{"kernel": k[:60], "launches": v[0], "ms": round(v[1] / 1e3, 3)} for k, v in top]}, detail
+
+
+def gpu_eager_baseline(args, steps=3):
+    """Informational: the oracle's training step (functional torch restatement of the reference: cuDNN / cuBLAS / ATen
+    kernels, the reference's own O(M^2) afCRPS) on the SAME GPU -- what `python main.py` of the reference would run at
+    best on this box -- in fp32 (TF32 off) and under bf16 autocast."""
+    from helpers import canonical_model
+    from oracle import probunet_oracle as O
+    from climex_synth import make_fields
+    B, R, L = args.batch, args.res, args.latent
+    M = args.members if args.loss in ("afcrps", "crps") else 1
+    m = canonical_model(latent_dim=L)
+    sd = {k: v.detach().clone().cuda() for k, v in m.state_dict().items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "resample_filter" not in k}
+    full = dict(sd); full.update(leaves)
+    opt = torch.optim.AdamW(list(leaves.values()), lr=1e-4, fused=True)
+    cfg = O.ProbUNetCfg(latent_dim=L)
+    f = make_fields(B, R, R, 16 if R >= 128 else 8, seed=1237)
+    x, y = f["inputs"].cuda(), f["targets"].cuda()
+    enc, dec = O.unet_topology(cfg.unet())
+    keys = [(b.key, b.cout, (b.up, b.down)) for b in enc + dec if not b.is_conv]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for mode in ("fp32", "bf16_autocast"):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+            torch.backends.cudnn.benchmark = True
+
+            def step():
+                eps = torch.randn(M, B, L, device="cuda", generator=g)
+                masks, h = {}, R
+                for k, c, (up, down) in keys:
+                    h = h * 2 if up else (h // 2 if down else h)
+                    masks[k] = torch.rand(B, c, h, h, device="cuda", generator=g) >= 0.1
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode != "fp32")):
+                    o = O.elbo(full, cfg, x, y, eps, args.loss, drop_masks=masks)
+                o[0].backward()
+                opt.step()
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["what"] = (f"oracle/probunet_oracle.py (PyTorch eager: cuDNN/cuBLAS/ATen) training step on this GPU, batch {B}, "
+                   f"{R}x{R}, {args.loss} M={M}, torch.optim.AdamW(fused); informational -- not the reference arm")
+    del leaves, full, sd, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# ensemble workload (BASELINE.json configs[3]): M prior members per field + residual_to_hr + inverse transforms +
+# CRPS / MAE per (field, variable); fields sharded over the ranks, no collective except the final gather of [T,3]
+# ------------------------------------------------------------------------------------------------
+ENS_FIELD_GFLOP = 28.757       # U-Net + prior forward, once per field (SURVEY.md 8d)
+ENS_MEMBER_MFLOP = 36.7        # fcomb layers 1-2 per member (layer-0 feature half hoisted)
+ENS_MEMBER_BYTES = 207e3       # algorithmic minimum per member (SURVEY.md 8d): 3*H*W*4 B written + features read once
+
+
+def ensemble_measure(args, model, dist, rank, world, N, fields, steps, warmup):
+    from climex_synth import make_fields
+    from parallel import gather_scores
+    R, Mm, FB = args.res, args.ens_members, min(args.field_batch, fields)
+    T = fields
+    ff = make_fields(T, R, R, 16 if R >= 128 else 8, seed=99 + rank)
+    sig = ff["std_hr"]
+    # truth in real units (setup, not timed): residual_to_hr of the true residual + the inverse variable transforms
+    hr_t = ff["lrinterp"] + ff["targets"] * (sig + 1e-10)
+    sp = lambda v: torch.where(v > 20.0, v, torch.log(torch.exp(v) + 1.0) - 1e-7)   # noqa: E731
+    hr_real = torch.stack([sp(hr_t[:, 0]) * 24 * 60 * 60, hr_t[:, 1] - 273.15, sp(hr_t[:, 2]) + hr_t[:, 1] - 273.15], dim=1)
+    host = {k: v.contiguous().pin_memory() for k, v in (("x", ff["inputs"]), ("hr", hr_real), ("li", ff["lrinterp"]))}
+    dev = {k: v.cuda() for k, v in host.items()}
+    sd_ = sig.cuda()
+    scores = torch.empty(T, 6, device="cuda")
+
+    def one_pass(src, h2d):
+        for i in range(0, T, FB):
+            sl = slice(i, min(T, i + FB))
+            if h2d:
+                x, hr, li = (src[k][sl].cuda(non_blocking=True) for k in ("x", "hr", "li"))
+            else:
+                x, hr, li = (src[k][sl] for k in ("x", "hr", "li"))
+            crps, mae = model.sample_and_score(x, Mm, hr, li, sd_)
+            scores[sl, :3], scores[sl, 3:] = crps, mae
+        return gather_scores(scores, [T] * world) if world > 1 else scores        # the only collective
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, warmup)):
+        one_pass(dev, False)
+    barrier()
+    l0 = N.lib().pub_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        allv = one_pass(dev, False)
+        ev[i + 1].record()
+    barrier()
+    launches = N.lib().pub_launch_count() - l0
+    t_dev = ev[0].elapsed_time(ev[-1]) * 1e-3
+    each = [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(steps)]
+    one_pass(host, True).cpu()                     # warm-up of the end-to-end path
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        res = one_pass(host, True).cpu()           # D2H of the [T*world, 6] scores: the result the caller reads
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - w0
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    members = T * Mm * world * steps
+    floor_s = max((ENS_FIELD_GFLOP * 1e9 * T + ENS_MEMBER_MFLOP * 1e6 * T * Mm) / (1e12 * 1356.1),
+                  ENS_MEMBER_BYTES * T * Mm / (6544e9))
+    return {"members_per_s": members / t_dev, "e2e_members_per_s": members / t_e2e, "fields_per_gpu": T, "members": Mm,
+            "field_batch": FB, "ms_per_pass": 1e3 * t_dev / steps, "ms_per_pass_each": each,
+            "e2e_ms_per_pass": 1e3 * t_e2e / steps, "gpu_launches": int(launches),
+            "h2d_bytes_per_pass": int(sum(v.numel() * 4 for v in host.values())), "d2h_bytes_per_pass": int(T * world * 6 * 4),
+            "mean_crps": [round(float(v), 5) for v in allv[:, :3].mean(dim=0)],
+            "roofline_floor_ms_per_pass": 1e3 * floor_s,
+            "frac_of_floor": floor_s / (t_dev / steps),
+            "includes": "per field: U-Net + prior once; per member: Philox rsample, fcomb, residual_to_hr + inverse transforms, "
+                        "CRPS (sorted form) + MAE; per pass: one gather of the [T,6] scores"}
+
+
+def run_ensemble(args, dist, rank, world, local, N, pk, pk_kind):
+    from helpers import canonical_model
+    model = canonical_model(latent_dim=args.latent, compute_dtype=args.dtype, device="cuda")
+    model.eval()
+    N.manual_seed(1000 + rank)
+    sampler = ClockSampler(local); sampler.start()
+    ensemble_measure(args, model, dist, rank, world, N, min(args.fields, 64), 1, 1)     # allocator / library warm-up
+    sampler.mark()
+    e = ensemble_measure(args, model, dist, rank, world, N, args.fields, args.steps, max(args.warmup, 3))
+    clocks = sampler.read()
+    sampler.stop()
+    T, Mm, R = args.fields, args.ens_members, args.res
+    line = {
+        "metric": "ensemble_members_per_s", "value": e["members_per_s"], "unit": "members/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": e["ms_per_pass"],
+        "ms_per_step_each": e["ms_per_pass_each"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"probunet_ensemble_{R}x{R}_T{T}pergpu_M{Mm}_L{args.latent}",
+                   "reference_config": "BASELINE.json configs[3]: prior-sampling ensemble, 100 members per low-res field + CRPS, "
+                                       "sample-parallel", "fields_per_gpu": T, "members": Mm, "field_batch": e["field_batch"],
+                   "resolution": R, "latent_dim": args.latent,
+                   "step": "one pass over the rank's fields: sample_and_score per field batch + one gather of the scores",
+                   "l2_policy": f"members of one field batch ({e['field_batch']} x {Mm} x 3 x {R} x {R} f32) >> 126 MB L2; no explicit flush"},
+        "e2e": {"value": e["e2e_members_per_s"], "unit": "members/s", "h2d_bytes_per_step": e["h2d_bytes_per_pass"],
+                "d2h_bytes_per_step": e["d2h_bytes_per_pass"], "ms_per_step": e["e2e_ms_per_pass"]},
+        "gpu_launches": e["gpu_launches"], "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": (ENS_FIELD_GFLOP * T + ENS_MEMBER_MFLOP * 1e-3 * T * Mm) / e["ms_per_pass"],
+                     "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "unit": "TFLOP/s", "traffic": None,
+                     "kernel": "whole pass: conv_halo_kernel family (U-Net + prior once per field) + fcomb_fwd per member",
+                     "how": "algorithmic FLOPs per pass (28.757 GFLOP per field + 36.7 MFLOP per member, SURVEY.md 8d) / pass time; "
+                            "the per-member HBM floor (207 kB) is reported as roofline_floor"},
+        "ensemble": e,
+    }
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -294,7 +539,12 @@ def run_b200(args):
     N.lib()
     pk, pk_kind = peaks()
 
+    if args.workload == "ensemble":
+        return run_ensemble(args, dist, rank, world, local, N, pk, pk_kind)
     B, R = args.batch, args.res
+    if args.strong:
+        assert args.batch % world == 0, "--strong: the global batch must be divisible by the number of GPUs"
+        B = args.batch // world
     M = args.members if args.loss in ("afcrps", "crps") else 1
     model = canonical_model(latent_dim=args.latent, loss_type=args.loss, compute_dtype=args.dtype, device="cuda")
     model.train()                                      # dropout on, as the reference trains
@@ -366,8 +616,8 @@ def run_b200(args):
         "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
         "ms_per_step_each": [round(v, 2) for v in per_step], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": workload_config(args),
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": dict(workload_config(args), per_gpu_batch=B, global_batch=B * world),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * t_e2e / args.steps, "ms_per_step_each": e2e_each},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": 1e3 * cpu_enqueue,
@@ -380,46 +630,36 @@ def run_b200(args):
     if rank == 0 and not args.no_aux:
         # ---- roofline of the dominant kernel family, measured live
         try:
-            model.eval()
-            roof, detail = conv_roofline(model, B, R, pk, pk_kind)
-            roof["share_of_step"] = roof["conv_time_per_step_ms"] / line["ms_per_step"]
-            # DRAM traffic of the same kernel family over one step, from the committed ncu launch list
-            # (profiles/r01d_launches_step.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed)
+            roof, detail = conv_roofline(model, B, R, pk, pk_kind, lambda: step_device(x, y), N)
+            # DRAM traffic of the same kernel family over one step: from the ncu launch list of THIS round's build
+            # (profiles/r02_launches_step.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch, summed); ncu cannot
+            # run inside the bench, so the value is only reported when that file exists and says which commit it is from
             try:
-                fam = json.load(open(os.path.join(ROOT, "profiles", "r01d_launches_step_family.json")))["conv_family"]
-                roof["traffic"] = fam["dram_bytes"]
-                roof["traffic_source"] = ("profiles/r01d_launches_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
-                                          f"{fam['launches']} conv-family launches of one step; ncu share of step {fam['share_of_step']:.3f})")
+                fam = json.load(open(os.path.join(ROOT, "profiles", "r02_launches_step_family.json")))
+                cf = fam["conv_family"]
+                roof["traffic"] = cf["dram_bytes"]
+                roof["traffic_source"] = (f"profiles/r02_launches_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                          f"{cf['launches']} conv-family launches of one step, build {fam.get('build', '?')}; "
+                                          f"ncu share of step {cf['share_of_step']:.3f})")
             except Exception:
-                pass
+                roof["traffic"] = None
             line["roofline"] = roof
             line["roofline_detail_top"] = sorted(detail, key=lambda d: -d["us"] * d["count"])[:8]
         except Exception as ex:  # never lose the headline line
             line["roofline"] = {"error": repr(ex)}
-    if rank == 0 and not args.no_aux and world == 1:     # the remaining extras (and the CPU baseline) at N = 1 only
-        # ---- auxiliary: ensemble members/s (BASELINE config 4 shape: M=100 prior members per field + CRPS/MAE)
+    if not args.no_aux:
+        # ---- second half of BASELINE.json's metric: ensemble members/s (configs[3]), every rank its own fields, one
+        # final gather -- a short run here; `--workload ensemble` is the full-length line
         try:
-            import metrics as MET
+            sync.uninstall()
             model.eval()
-            T, Mm = 64, 100
-            ff = make_fields(T, R, R, 16 if R >= 128 else 8, seed=99)
-            xi, hr, li, sd_ = ff["inputs"].cuda(), ff["hr"].cuda(), ff["lrinterp"].cuda(), ff["std_hr"].cuda()
-            for _ in range(2):
-                ens = model.sample(xi, Mm)
-            torch.cuda.synchronize()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-            ev[0].record()
-            for i in range(5):
-                ens = model.sample(xi, Mm)
-                crps, mae = MET.ensemble_scores_from_residuals(ens, hr, li, sd_)
-                ev[i + 1].record()
-            torch.cuda.synchronize()
-            ens_ms = [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(5)]
-            line["ensemble"] = {"members_per_s": T * Mm / (statistics.median(ens_ms) * 1e-3), "fields": T, "members": Mm,
-                                "ms_per_pass_each": ens_ms,
-                                "includes": "unet+prior once per field, fcomb x M, residual_to_hr+CRPS+MAE kernel"}
+            ens = ensemble_measure(args, model, dist, rank, world, N, fields=min(args.fields, 128), steps=3, warmup=1)
+            if rank == 0:
+                line["ensemble"] = ens
         except Exception as ex:
-            line["ensemble"] = {"error": repr(ex)}
+            if rank == 0:
+                line["ensemble"] = {"error": repr(ex)}
+    if rank == 0 and not args.no_aux and world == 1:     # the remaining extras (and the CPU baseline) at N = 1 only
         # ---- auxiliary: GPU-side dataset transform (__getitem__ math, src/climex_utils.py:197-225)
         try:
             from climex_gpu import ClimexBatchTransform
@@ -439,6 +679,14 @@ def run_b200(args):
                                       "(reads 1x, writes 3x; the reference does this per sample on the host)"}
         except Exception as ex:
             line["feeder"] = {"error": repr(ex)}
+        # ---- same-box PyTorch-eager baseline (informational)
+        try:
+            del model, opt
+            torch.cuda.empty_cache()
+            N.workspaces.clear()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(args)
+        except Exception as ex:
+            line["gpu_eager_baseline"] = {"error": repr(ex)}
         # ---- CPU baseline: the oracle on the host cores, bounded sample
         try:
             torch.cuda.synchronize()

@@ -163,6 +163,15 @@ class ProbabilisticUNet(nn.Module):
         z = self.prior_latent_space.rsample((n,), eps=eps)
         return _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)
 
+    @torch.no_grad()
+    def sample_and_score(self, x, n, hr_real, lrinterp, std_hr, eps=None):
+        """Additive API for the ensemble evaluation of results.ipynb cells 6, 11, 12: n prior members per field
+        (``sample``), ``residual_to_hr`` + ``invert_transfo_3vars`` (src/climex_utils.py:277-285, results.ipynb cell 2)
+        and ``metrics.crps_over_groundtruth`` / ``compute_mae`` (src/metrics.py:11-71) against ``hr_real`` [B,3,H,W]
+        (real units) -> (crps [B,3], mae [B,3]) on the device; the members never leave the GPU."""
+        ens = self.sample(x, n, eps=eps)
+        return _native.ensemble_metrics(ens, hr_real, lrinterp, std_hr)
+
     def elbo(self, x, target, t=None, M=None, alpha=0.95, alpha_w=0.007, beta_w=0.048, lam_w=0.0, eps=None):
         """ELBO = beta_0*recon + beta_1*KL(q||p) [+ beta_2*KL(q||N(0,I))]; the reconstruction
         term and the return tuple follow ``self.loss_type`` exactly as the three variants in
