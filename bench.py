@@ -324,7 +324,7 @@ def conv_roofline(model, B, H, pk, pk_kind, step_fn, N):
     conv_ms = sum(v[1] for v in fam.values()) / 1e3
     total_ms = sum(v[1] for v in agg.values()) / 1e3
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-    ach = replay["conv_gflop_per_step"] / conv_ms / 1e3 if conv_ms > 0 else 0.0
+    ach = replay["conv_gflop_per_step"] / conv_ms if conv_ms > 0 else 0.0      # GFLOP / ms == TFLOP/s
     top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
             "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)",

@@ -187,45 +187,57 @@ __device__ __forceinline__ float softplus_ref(float x, float c) { return x > 20.
 // M (M - 1) / 2 = 4 950 subtract-abs-add triples per pixel at M = 100 (and a local-memory array) of the pairwise
 // loop.  Loads are coalesced: consecutive lanes read consecutive pixels of one member plane.
 constexpr int MET_MAXM = 128;
-__device__ __forceinline__ float metrics_member(const float* __restrict__ preds, const float* __restrict__ lrinterp,
-                                                const float* __restrict__ std_hr, int transform, int64_t t, int j, int M,
-                                                int c, int C, int HW, int p) {
-  const float* pj = preds + ((t * M + j) * C) * (int64_t)HW + p;
-  float v = pj[(int64_t)c * HW];
-  if (transform) {
-    const float* li = lrinterp + (t * C) * (int64_t)HW + p;
-    v = li[(int64_t)c * HW] + v * (std_hr[c] + 1e-10f);
-    if (c == 0) v = softplus_ref(v, 1e-7f) * 24.f * 60.f * 60.f;   // kgm2sTommday's own multiplication order
-    else if (c == 1) v = v - 273.15f;
-    else {
-      const float v1 = li[(int64_t)HW] + pj[(int64_t)HW] * (std_hr[1] + 1e-10f);
-      v = (softplus_ref(v, 1e-7f) + v1) - 273.15f;   // results.ipynb cell 2: softplus default c, KToC of the sum
-    }
-  }
-  return v;
+// softplus without a branch (a data-dependent branch between the member loads keeps the compiler from batching them)
+__device__ __forceinline__ float softplus_sel(float x, float c) {
+  const float sp = logf(expf(x) + 1.f) - c;
+  return x > 20.f ? x : sp;
 }
 
 template <int NP>
-__global__ void __launch_bounds__(128) metrics_kernel(const float* __restrict__ preds, const float* __restrict__ hr,
-                                                      const float* __restrict__ lrinterp, const float* __restrict__ std_hr,
-                                                      int transform, int M, int C, int HW, float* __restrict__ part) {
+__global__ void __launch_bounds__(128, 3) metrics_kernel(const float* __restrict__ preds, const float* __restrict__ hr,
+                                                         const float* __restrict__ lrinterp, const float* __restrict__ std_hr,
+                                                         int transform, int M, int C, int HW, float* __restrict__ part) {
   __shared__ float red[4];
   const int t = blockIdx.z, c = blockIdx.y;
   float a_crps = 0.f, a_mae = 0.f;
   const float inv_m = 1.f / (float)M;
+  const float INF = __int_as_float(0x7f800000);
+  const int64_t mstride = (int64_t)C * HW;                 // floats between two members of one (field, variable, pixel)
   for (int p = blockIdx.x * 128 + threadIdx.x; p < HW; p += gridDim.x * 128) {
     float x[NP];
     const float y = hr[((int64_t)t * C + c) * HW + p];
-    float mean = 0.f, s1 = 0.f;
+    const float* pc = preds + ((int64_t)t * M * C + c) * HW + p;
+    // phase 1: the M raw loads, nothing else -- independent, so they are all in flight together (with the transform
+    // interleaved, every load waited for the previous member's branchy arithmetic: 6.3 ms per 64 x 100 members
+    // instead of < 1 ms, profiles/r02_ensemble_pass_cupti.txt)
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      if (j < M) {
-        const float v = metrics_member(preds, lrinterp, std_hr, transform, t, j, M, c, C, HW, p);
-        x[j] = v; mean += v; s1 += fabsf(v - y);
+    for (int j = 0; j < NP; ++j) x[j] = j < M ? __ldg(pc + j * mstride) : INF;   // +inf sorts behind the real members
+    if (transform) {
+      // residual_to_hr (src/climex_utils.py:277-285) + invert_transfo_3vars (results.ipynb cell 2)
+      const float li = lrinterp[((int64_t)t * C + c) * HW + p], sc = std_hr[c] + 1e-10f;
+      if (c == 0) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (j < M) x[j] = softplus_sel(fmaf(x[j], sc, li), 1e-7f) * 24.f * 60.f * 60.f;   // kgm2sTommday's own order
+      } else if (c == 1) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (j < M) x[j] = fmaf(x[j], sc, li) - 273.15f;
       } else {
-        x[j] = __int_as_float(0x7f800000);   // +inf: sorts behind the real members
+        const float li1 = lrinterp[((int64_t)t * C + 1) * HW + p], s1c = std_hr[1] + 1e-10f;
+        const float* p1 = preds + ((int64_t)t * M * C + 1) * HW + p;
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (j < M) x[j] = softplus_sel(fmaf(x[j], sc, li), 1e-7f);
+#pragma unroll
+        for (int j = 0; j < NP; ++j)                      // second batch of independent loads: the tasmin member
+          if (j < M) x[j] = (x[j] + fmaf(__ldg(p1 + j * mstride), s1c, li1)) - 273.15f;
       }
     }
+    float mean = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+      if (j < M) { mean += x[j]; s1 += fabsf(x[j] - y); }
     // bitonic sorting network, ascending
 #pragma unroll
     for (int k = 2; k <= NP; k <<= 1) {

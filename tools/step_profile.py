@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--res", type=int, default=128)
     ap.add_argument("--members", type=int, default=15)
     ap.add_argument("--loss", default="afcrps")
+    ap.add_argument("--ensemble", type=int, default=0, help="profile one sample_and_score pass with this many members instead of a training step")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_profile.txt"))
     args = ap.parse_args()
     import __graft_entry__ as G
@@ -53,6 +54,12 @@ def main():
         out[0].backward()
         opt.step()
 
+    if args.ensemble:
+        model.eval()
+        hr, li, sd_ = f["hr"].cuda(), f["lrinterp"].cuda(), f["std_hr"].cuda()
+
+        def step():                                          # noqa: F811
+            model.sample_and_score(x, args.ensemble, hr, li, sd_)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
