@@ -52,6 +52,8 @@ unsigned long long pub_launch_count(void);
 int pub_debug_option(const char* name, int value);
 /*   "halo_trace" : device buffer of 3 x 1024 int64 that CTA (0,0) of conv_halo_kernel fills with clock64 stamps
  *                  (producer / MMA issuer / epilogue events; tools/halo_trace.py); NULL switches it off */
+/*   "seed_salt"  : device uint32 xor-ed into every dropout key / rsample seed (CUDA-graph replays, see the end of this
+ *                  file); NULL (default) switches it off */
 int pub_debug_pointer(const char* name, void* p);
 
 /* ------------------------------------------------------------------------------------
@@ -278,6 +280,16 @@ typedef struct { float* p; const float* g; float* m; float* v; int64_t n; } pub_
 int pub_adamw_step(const pub_adamw_entry* device_table, int n_tensors, int64_t max_numel,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                    float grad_scale, pub_stream_t s);
+
+/* CUDA-graph variants (the whole training step captured once and replayed): a captured graph
+ * replays the kernel ARGUMENTS of the capture, so whatever changes from step to step lives in device memory.
+ * counters[0] = optimizer step count, counters[1] = random salt; pub_advance_counters (one tiny launch at the top of
+ * the captured step) advances both; pub_debug_pointer("seed_salt", &counters[1]) makes every dropout key and rsample
+ * seed of the library depend on the salt; pub_adamw_step_dev reads the step count for its bias corrections. */
+int pub_advance_counters(int* counters, pub_stream_t s);
+int pub_adamw_step_dev(const pub_adamw_entry* device_table, int n_tensors, int64_t max_numel,
+                       float lr, float beta1, float beta2, float eps, float weight_decay,
+                       const int* step_dev, float grad_scale, pub_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -424,6 +424,19 @@ def residual_to_real(residual: Tensor, lrinterp: Tensor, std_hr: Tensor) -> Tens
     return invert_transfo_3vars(lrinterp + residual * (std_hr + 1e-10))
 
 
+def return_level_pixel_series(members_hr: Tensor, variable: str) -> Tensor:
+    """test_return_levels.ipynb cell 2: the per-pixel daily value extracted from a residual_to_hr'd member
+    (``members_hr`` [..., 3] = the three stored variables at the chosen pixel): pr = kgm2sTommday(softplus(x0)),
+    tasmin = KToC(x1), tasmax = KToC(x1 + softplus(x2, c=0)) -- note c = 0 here, unlike results.ipynb cell 2."""
+    if variable == "pr":
+        return softplus_ref(members_hr[..., 0]) * 24 * 60 * 60
+    if variable == "tasmin":
+        return members_hr[..., 1] - 273.15
+    if variable == "tasmax":
+        return (members_hr[..., 1] + softplus_ref(members_hr[..., 2], c=0.0)) - 273.15
+    raise ValueError("Unsupported variable")
+
+
 # --------------------------------------------------------------------------------------
 # dataset transform  (src/climex_utils.py:197-225, 255-264, 277-285)
 # --------------------------------------------------------------------------------------

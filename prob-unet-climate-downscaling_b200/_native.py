@@ -85,7 +85,7 @@ EXPORTS = [
     "pub_fcomb_backward_workspace", "pub_fcomb_backward", "pub_loss_workspace", "pub_ensemble_loss", "pub_l1_loss", "pub_msssim_workspace", "pub_wmse_msssim_loss", "pub_climex_stats", "pub_climex_transform",
     "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
     "pub_groupnorm_scratch_bytes", "pub_groupnorm_silu_forward", "pub_groupnorm_silu_backward",
-    "pub_conv2d_fused_rows", "pub_conv2d_forward_fused",
+    "pub_conv2d_fused_rows", "pub_conv2d_forward_fused", "pub_advance_counters", "pub_adamw_step_dev",
 ]
 
 

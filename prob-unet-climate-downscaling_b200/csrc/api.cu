@@ -20,6 +20,7 @@ int g_opt_gn_fuse = 1;
 cudaStream_t g_pack_stream = nullptr;
 unsigned long long g_since_pack = 0;
 long long* g_halo_trace = nullptr;
+const uint32_t* g_seed_salt = nullptr;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -131,6 +132,7 @@ struct EnvOpts {
 int pub_debug_pointer(const char* name, void* p) {
   PUB_REQUIRE(name != nullptr, "pub_debug_pointer: null name");
   if (strcmp(name, "halo_trace") == 0) { g_halo_trace = (long long*)p; return 0; }
+  if (strcmp(name, "seed_salt") == 0) { g_seed_salt = (const uint32_t*)p; return 0; }
   set_error("pub_debug_pointer: unknown name '%s'", name);
   return -1;
 }

@@ -36,6 +36,10 @@ extern int g_opt_wgrad_box3;  // 1 (default): 3x3 wgrad loads x as three (8+2) x
 extern int g_opt_fcomb_fwd_mma;  // fcomb forward in bf16 mode: 1 = tensor-core kernel (bf16 operands), 0 = f32 FMA kernel
 extern int g_opt_wgrad_fused_bias;  // 1 (default): bias gradients summed from the dy tiles staged by the wgrad kernel; 0: separate pass
 extern int g_opt_gn_fuse;  // GroupNorm work fused into the halo conv epilogues: 0 none, 1 forward statistics, 2 + backward prologue
+// CUDA-graph support: a device word mixed into every dropout key / rsample seed, advanced once per step by
+// pub_advance_counters (a graph replays the same kernel ARGUMENTS every step, so per-step randomness has to come from
+// device memory).  nullptr (default): unused, the (seed, offset) arguments alone decide -- what the parity tests run.
+extern const uint32_t* g_seed_salt;
 extern long long* g_halo_trace;  // device buffer for conv_halo_kernel event stamps (pub_debug_pointer("halo_trace", p)), else null
 extern unsigned long long g_launch_count;  // kernels enqueued by this library (bench.py's gpu_launches)
 #define PUB_LAUNCH_CHECK()          \

@@ -451,6 +451,7 @@ struct HaloArgs {
   const void* gx0; const void* gx1; int gc0, gld0, gld1;
   const float* gcoef;          // [B][cout][2]
   float p_drop; uint64_t seed, subseq;
+  const uint32_t* salt;
 };
 enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_GNBWD = 2 };
 
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(HTHREADS, 2) conv_halo_kernel(const __grid_con
     if (EPI != EPI_PLAIN)
       tsm = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + a.epi_off) + (grp * 4 + q) * (CW * 33);
     const uint32_t thresh = EPI == EPI_GNBWD ? drop_thresh(a.p_drop) : 0u;
-    const uint32_t dkey = EPI == EPI_GNBWD ? dropout_key(a.seed, a.subseq) : 0u;
+    const uint32_t dkey = EPI == EPI_GNBWD ? (dropout_key(a.seed, a.subseq) ^ (a.salt ? __ldg(a.salt) : 0u)) : 0u;
     const float inv_keep = (EPI == EPI_GNBWD && a.p_drop > 0.f) ? 1.f / (1.f - a.p_drop) : 1.f;
     const int cl = lane & (CW - 1), half = lane >> 4;      // column sums: lane (cl, half) adds half a column
     for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
@@ -1162,7 +1163,7 @@ int conv_halo(const ConvParams& p, int dtype, cudaStream_t s) {
   a.w_early = p.w_settled && weights_settled_on(s);
   a.stat_part = p.stat_part;
   a.gx0 = p.gx0; a.gx1 = p.gx1; a.gc0 = p.gx1 ? p.gc0 : p.cout; a.gld0 = p.gld0; a.gld1 = p.gld1;
-  a.gcoef = p.gcoef; a.p_drop = p.p_drop; a.seed = p.seed; a.subseq = p.subseq;
+  a.gcoef = p.gcoef; a.p_drop = p.p_drop; a.seed = p.seed; a.subseq = p.subseq; a.salt = p.salt;
   const int n_tiles = p.cout / a.BN;
   const int cblk = cin / KC;
   const size_t b_bytes = (size_t)a.BN * rowb, a_stage = align_up((size_t)HALO_PX * rowb, 1024);

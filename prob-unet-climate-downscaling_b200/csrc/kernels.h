@@ -27,6 +27,7 @@ struct ConvParams {
   const void* gx0; const void* gx1; int gc0, gld0, gld1;
   const float* gcoef;
   float p_drop; uint64_t seed, subseq;
+  const uint32_t* salt;   // optional device word xor-ed into the dropout key (g_seed_salt; set by the engines)
 };
 
 struct WgradParams {
@@ -77,6 +78,7 @@ struct GnParams {
   const float* film;                                      // [2C] (scale | shift) or nullptr
   int resample;                                           // 0 none, 1 down (2x2 mean), 2 up (nearest 2x)
   float p_drop; uint64_t seed; uint64_t subseq;           // dropout on the activated output (p_drop = 0: off)
+  const uint32_t* salt;                                   // optional device word xor-ed into the dropout key (g_seed_salt)
   float* stats;                                           // [B][G][2] mean, rstd   (saved for backward)
   float* coef;                                            // [B][C][2] scratch: per-(b,c) affine a,b
   float* partial;                                         // scratch for the two-stage reductions

@@ -15,7 +15,8 @@ constexpr int NT = 256;
 // ------------------------------------------------------------------ rsample
 __global__ void rsample_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
                                    const float* __restrict__ eps_in, uint64_t seed, uint64_t offset, int M, int BL,
-                                   float* __restrict__ z, float* __restrict__ eps_out) {
+                                   float* __restrict__ z, float* __restrict__ eps_out, const uint32_t* __restrict__ salt) {
+  if (salt) seed ^= (uint64_t)__ldg(salt) << 20;   // per-step device word (CUDA-graph replays reuse the arguments)
   const int64_t n = (int64_t)M * BL;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -290,6 +291,30 @@ __global__ void __launch_bounds__(NT) adamw_kernel(const pub_adamw_entry* __rest
   }
 }
 
+// the same update with the step count read from device memory (a captured graph replays fixed arguments)
+__global__ void __launch_bounds__(NT) adamw_dev_kernel(const pub_adamw_entry* __restrict__ tab, float lr, float b1, float b2,
+                                                       float eps, float wd, const int* __restrict__ step_dev, float gscale) {
+  const float st = (float)__ldg(step_dev);
+  const float bc1 = 1.f - powf(b1, st), bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  const pub_adamw_entry e = tab[blockIdx.y];
+  const float step = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < e.n; i += (int64_t)gridDim.x * NT) {
+    const float g = e.g[i] * gscale;
+    float p = e.p[i] * (1.f - lr * wd);
+    const float m = b1 * e.m[i] + (1.f - b1) * g;
+    const float v = b2 * e.v[i] + (1.f - b2) * g * g;
+    p -= step * m / (sqrtf(v) / bc2_sqrt + eps);
+    e.p[i] = p; e.m[i] = m; e.v[i] = v;
+  }
+}
+// counters[0]: optimizer step (+1), counters[1]: random salt (next value of a 32-bit mixer sequence)
+__global__ void advance_counters_kernel(int* __restrict__ counters) {
+  if (threadIdx.x == 0) {
+    counters[0] += 1;
+    counters[1] = (int)mix32((uint32_t)counters[1] * 0x9E3779B1u + 0x7F4A7C15u);
+  }
+}
+
 inline int grid_for(int64_t n) {
   int64_t g = (n + NT - 1) / NT;
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -307,7 +332,7 @@ int pub_rsample_forward(const float* mu, const float* sigma, const float* eps_in
                         int B, int L, float* z, float* eps_out, pub_stream_t s) {
   PUB_REQUIRE(mu && sigma && z, "pub_rsample_forward: null argument");
   const int64_t n = (int64_t)M * B * L;
-  rsample_fwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)s>>>(mu, sigma, eps_in, seed, offset, M, B * L, z, eps_out);
+  rsample_fwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)s>>>(mu, sigma, eps_in, seed, offset, M, B * L, z, eps_out, g_seed_salt);
   PUB_LAUNCH_CHECK();
   return 0;
 }
@@ -413,6 +438,25 @@ int pub_adamw_step(const pub_adamw_entry* table, int n_tensors, int64_t max_nume
   if (gx > 64) gx = 64;
   dim3 grid(gx, n_tensors);
   adamw_kernel<<<grid, NT, 0, (cudaStream_t)s>>>(table, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int pub_adamw_step_dev(const pub_adamw_entry* table, int n_tensors, int64_t max_numel, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, const int* step_dev, float grad_scale, pub_stream_t s) {
+  PUB_REQUIRE(table && n_tensors > 0 && step_dev, "pub_adamw_step_dev: bad arguments");
+  int gx = cdiv(max_numel, (int64_t)NT * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, n_tensors);
+  adamw_dev_kernel<<<grid, NT, 0, (cudaStream_t)s>>>(table, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale);
+  PUB_LAUNCH_CHECK();
+  return 0;
+}
+
+int pub_advance_counters(int* counters, pub_stream_t s) {
+  PUB_REQUIRE(counters, "pub_advance_counters: null argument");
+  advance_counters_kernel<<<1, 32, 0, (cudaStream_t)s>>>(counters);
   PUB_LAUNCH_CHECK();
   return 0;
 }

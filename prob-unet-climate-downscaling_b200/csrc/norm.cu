@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(GN_NT, MODE == 0 ? 4 : 3) gn_partial_kernel(Gn
     float a[8], bb[8];
     if (MODE == 1) load_affine(p.coef, b, C, v, a, bb);
     const uint32_t thresh = drop_thresh(p.p_drop);
-    const uint32_t dkey = dropout_key(p.seed, p.subseq);
+    const uint32_t dkey = dropout_key(p.seed, p.subseq) ^ (p.salt ? __ldg(p.salt) : 0u);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     if (MODE == 0 || p.resample == 0) {
       // this thread's vector of pixel (b, 0) and its pixel pitch (the two sources of a virtual concat differ)
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_apply_kernel(GnParams p, T* __res
   const int HW = p.H * p.W;
   if (p.resample != 1) {
     const uint32_t thresh = drop_thresh(p.p_drop);
-    const uint32_t dkey = dropout_key(p.seed, p.subseq);
+    const uint32_t dkey = dropout_key(p.seed, p.subseq) ^ (p.salt ? __ldg(p.salt) : 0u);
     const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
     const int rows = p.rows;
     const int r0 = blockIdx.x * rows, r1 = min(HW, r0 + rows);
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(GN_NT, 3) gn_bwd_apply_kernel(GnParams p, cons
   load_affine(p.coef, b, C, v, a, bb);
   load_affine(bcoef, b, C, v, c2, c3);
   const uint32_t thresh = drop_thresh(p.p_drop);
-  const uint32_t dkey = dropout_key(p.seed, p.subseq);
+  const uint32_t dkey = dropout_key(p.seed, p.subseq) ^ (p.salt ? __ldg(p.salt) : 0u);
   const float inv_keep = p.p_drop > 0.f ? 1.f / (1.f - p.p_drop) : 1.f;
   const int HW = p.H * p.W;
   const int rows = p.rows;

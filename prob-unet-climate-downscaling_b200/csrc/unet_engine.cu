@@ -184,7 +184,7 @@ GnParams gn_params(const Plan& pl, const void* x0, int c0, int ld0, const void* 
   g.x0 = x0; g.x1 = x1; g.c0 = c0; g.c1 = c1; g.ld0 = ld0; g.ld1 = ld1;
   g.B = pl.B; g.H = H; g.W = W; g.groups = groups_of(c0 + c1);
   g.gamma = gamma; g.beta = beta; g.film = film; g.resample = resample;
-  g.p_drop = p_drop; g.seed = seed; g.subseq = subseq;
+  g.p_drop = p_drop; g.seed = seed; g.subseq = subseq; g.salt = g_seed_salt;
   g.stats = stats; g.coef = coef; g.partial = (float*)pl.gn_scratch;
   return g;
 }
@@ -444,7 +444,7 @@ int pub_unet_backward(pub_unet* u, int B, int H, int W, const void* dout, int do
       rows1 = g_opt_gn_fuse >= 2 ? conv_fused_rows(cd, dt, backend) : 0;
       if (rows1) {
         cd.stat_part = pl.du_part; cd.gn_bwd = 1; cd.gx0 = b.h; cd.gc0 = b.d.cout; cd.gld0 = b.d.cout; cd.gcoef = b.coef1;
-        cd.p_drop = pdrop; cd.seed = seed; cd.subseq = (uint64_t)i;
+        cd.p_drop = pdrop; cd.seed = seed; cd.subseq = (uint64_t)i; cd.salt = g_seed_salt;
       }
       PUB_TRY(conv_forward(cd, dt, backend, s));
     }

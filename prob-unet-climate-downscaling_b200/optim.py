@@ -17,6 +17,17 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = grad_scale
         self._tables = {}
+        self._step_dev = None      # device int32 step counter (CUDA-graph mode, see graph.GraphedTrainStep)
+
+    def use_device_step(self, counter):
+        """counter: 1-element int32 CUDA tensor holding the optimizer step count, advanced on the device
+        (pub_advance_counters) before every step -- required under CUDA-graph capture, where the host-side step count
+        would be frozen into the captured kernel arguments.  None switches back to the host count."""
+        if counter is not None:
+            assert counter.is_cuda and counter.dtype == torch.int32 and counter.numel() >= 1
+            host_steps = {g.get("step", 0) for g in self.param_groups}
+            assert len(host_steps) == 1, "parameter groups with different step counts cannot share one device counter"
+        self._step_dev = counter
 
     def _table(self, gi, plist):
         """Device table of {p, g, m, v, n} rows; rebuilt only when a pointer changes."""
@@ -55,6 +66,12 @@ class FusedAdamW(torch.optim.Optimizer):
             group["step"] = group.get("step", 0) + 1
             _, dev, _, maxn = self._table(gi, plist)
             b1, b2 = group["betas"]
+            if self._step_dev is not None:
+                N.check(N.lib().pub_adamw_step_dev(N.ptr(dev), len(plist), C.c_int64(maxn), C.c_float(group["lr"]),
+                                                   C.c_float(b1), C.c_float(b2), C.c_float(group["eps"]),
+                                                   C.c_float(group["weight_decay"]), N.ptr(self._step_dev),
+                                                   C.c_float(self.grad_scale), N.stream()), "pub_adamw_step_dev")
+                continue
             N.check(N.lib().pub_adamw_step(N.ptr(dev), len(plist), C.c_int64(maxn), C.c_float(group["lr"]), C.c_float(b1),
                                            C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]),
                                            int(group["step"]), C.c_float(self.grad_scale), N.stream()), "pub_adamw_step")

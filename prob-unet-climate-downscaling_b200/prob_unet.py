@@ -164,6 +164,23 @@ class ProbabilisticUNet(nn.Module):
         return _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)
 
     @torch.no_grad()
+    def sample_pixels(self, x, n, pixels, eps=None):
+        """Additive API for the return-level analysis of test_return_levels.ipynb cell 2, which runs the full model
+        ``num_samples`` times per day at batch 1 to read ONE pixel: here the U-Net and the prior run once per field and
+        ``fcomb`` is evaluated only at the requested pixels (a gather of the [B,H,W,F] feature map in front of the
+        per-pixel MLP -- fcomb has no spatial coupling, so this is exact).  ``pixels``: sequence of (y, x);
+        returns the n prior members at those pixels, [B, n, C, P], in the model's (residual) domain."""
+        ys = torch.as_tensor([int(p[0]) for p in pixels], device=x.device)
+        xs = torch.as_tensor([int(p[1]) for p in pixels], device=x.device)
+        if int(ys.max()) >= x.shape[2] or int(xs.max()) >= x.shape[3] or int(ys.min()) < 0 or int(xs.min()) < 0:
+            raise IndexError("sample_pixels: pixel outside the field")
+        feat = self.unet(x, _nhwc_out=True)                              # [B,H,W,F] engine layout
+        self.prior_latent_space = self.prior(x)
+        z = self.prior_latent_space.rsample((n,), eps=eps)
+        fpix = feat[:, ys, xs, :].unsqueeze(1).contiguous()              # [B,1,P,F]: a 1 x P "image"
+        return _native.fcomb_apply(self.fcomb, fpix, z, nhwc=True)[:, :, :, 0, :]
+
+    @torch.no_grad()
     def sample_and_score(self, x, n, hr_real, lrinterp, std_hr, eps=None):
         """Additive API for the ensemble evaluation of results.ipynb cells 6, 11, 12: n prior members per field
         (``sample``), ``residual_to_hr`` + ``invert_transfo_3vars`` (src/climex_utils.py:277-285, results.ipynb cell 2)

@@ -57,6 +57,14 @@ stored = torch.randn(5, 3, 16, 16, generator=g) * torch.tensor([3.0, 9.0, 4.0]).
 out["tf_stored"] = stored.numpy()
 out["tf_real"] = ns["invert_transfo_3vars"](stored.clone()).numpy()
 
+# ---- the per-pixel conversions of test_return_levels.ipynb cell 2 (composed from the real functions exactly as there:
+# tasmax uses softplus(..., c=0) in THAT notebook)
+hp = torch.randn(64, 3, 4, 4, generator=g) * torch.tensor([3.0, 9.0, 4.0]).view(1, 3, 1, 1) + torch.tensor([-1.0, 272.0, 3.0]).view(1, 3, 1, 1)
+out["rl_hr"] = hp.numpy()
+out["rl_pr"] = CU.kgm2sTommday(CU.softplus(hp[:, 0].clone())).numpy()
+out["rl_tasmax"] = CU.KToC(hp[:, 1] + CU.softplus(hp[:, 2].clone(), c=0)).numpy()
+out["rl_tasmin"] = CU.KToC(hp[:, 1].clone()).numpy()
+
 # ---- metrics.compute_mae (src/metrics.py:48-71) run for real; only the module-level `import pysteps` is stubbed
 # (compute_mae never calls it).  crps_over_groundtruth needs pysteps itself and stays a restatement (oracle header).
 sys.modules["pysteps"] = types.ModuleType("pysteps")

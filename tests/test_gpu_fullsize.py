@@ -220,3 +220,59 @@ def test_fused_groupnorm_epilogues_match_the_separate_passes():
     bad = [(n, rel_err(g, runs[0][1][n])) for n, g in runs[2][1].items()
            if float(runs[0][1][n].norm()) > 1e-7 and rel_err(g, runs[0][1][n]) > 3e-2]
     assert not bad, bad[:8]
+
+
+def test_cuda_graph_training_step_matches_eager_steps():
+    """graph.GraphedTrainStep: the whole step (elbo + backward + fused AdamW) captured once and replayed.
+    (a) deterministic setting (eval(): dropout off, injected eps): parameters after warm-up + capture + 3 replays are
+    BIT-identical to the same number of eager steps through the same device-step optimizer path; the step count
+    lives on the device.  (b) train(): the device salt gives every replay new dropout masks and eps."""
+    import ctypes as C
+    import _native as N
+    from climex_synth import make_fields
+    from graph import GraphedTrainStep
+    from optim import FusedAdamW
+    Bs, M = 8, 4
+    f = make_fields(Bs, R, R, 16, seed=21)
+    x, y = f["inputs"].cuda(), f["targets"].cuda()
+    eps = torch.randn(M, Bs, 32, generator=torch.Generator().manual_seed(22)).cuda()
+
+    def fresh(train):
+        m = canonical_model(compute_dtype="bf16", device="cuda")
+        m.train(train)
+        return m, FusedAdamW(m.parameters(), lr=1e-3)
+
+    m1, o1 = fresh(False)
+    g = GraphedTrainStep(m1, o1, x, y, M=M, warmup=2, eps=eps)
+    for _ in range(3):
+        out = g(x, y)
+    torch.cuda.synchronize()
+    n_steps = int(g.counters[0].item())
+    assert n_steps == 2 + 1 + 3                        # warm-up + the capture pass + 3 replays
+    assert g.launches_per_step > 500
+    loss_g = float(out[0])
+    g.close()
+    assert o1.param_groups[0]["step"] == n_steps        # close() hands the count back to the host
+    m2, o2 = fresh(False)
+    counters = torch.zeros(2, device="cuda", dtype=torch.int32)
+    o2.use_device_step(counters[0:1])
+    m2.sync_scalars = False
+    for _ in range(n_steps):
+        N.lib().pub_advance_counters(N.ptr(counters), N.stream())
+        o2.zero_grad(set_to_none=True)
+        out2 = m2.elbo(x, y, None, M=M, eps=eps)
+        out2[0].backward()
+        o2.step()
+    torch.cuda.synchronize()
+    assert int(counters[0].item()) == n_steps
+    for (n1, p), q in zip(m1.named_parameters(), m2.parameters()):
+        assert torch.equal(p, q), n1
+    assert loss_g == float(out2[0])
+    # (b) randomness under replay
+    m3, o3 = fresh(True)
+    g3 = GraphedTrainStep(m3, o3, x, y, M=M, warmup=1)
+    a = float(g3(x, y)[0]); b = float(g3(x, y)[0])
+    with torch.no_grad():
+        before = [p.detach().clone() for p in m3.parameters()]
+    g3.close()
+    assert a != b and all(bool(torch.isfinite(p).all()) for p in before)

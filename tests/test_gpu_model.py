@@ -206,6 +206,33 @@ def test_sample_members_and_metrics(setup, golden):
     np.testing.assert_allclose(a2.cpu().numpy(), O.compute_mae(hr_real, real), rtol=2e-3, atol=1e-4)
 
 
+def test_pixel_targeted_sampling_equals_the_full_field_members(setup, golden):
+    """SURVEY.md 8f rank 4 (test_return_levels.ipynb cell 2 reads one pixel of a full forward pass per member and day):
+    sample_pixels evaluates fcomb at the requested pixels only; it must equal the full-field members there, and the
+    oracle's full forward."""
+    name, m, sd = setup
+    x, _, _ = _inputs(golden)
+    n = 5
+    eps = torch.randn(n, 2, 32, generator=torch.Generator().manual_seed(19)).cuda()
+    pix = [(0, 0), (63, 63), (17, 40), (5, 62), (33, 1), (8, 8), (60, 3)]
+    vals = m.sample_pixels(x, n, pix, eps=eps)                      # [B,n,3,P]
+    assert vals.shape == (2, n, 3, len(pix))
+    full = m.sample(x, n, eps=eps)
+    ys, xs = [p[0] for p in pix], [p[1] for p in pix]
+    assert rel_err(vals, full[..., ys, xs]) < 1e-6 if name == "fp32" else rel_err(vals, full[..., ys, xs]) < 2e-5
+    with torch.no_grad():
+        feat = O.unet_forward(sd, x.cpu(), CFG.unet())
+        mu, sig = O.gaussian_encoder(sd, "prior", x.cpu(), None, CFG.num_filters)
+        ref = torch.stack([O.fcomb(sd, feat, mu + sig * eps[i].cpu()) for i in range(n)], dim=1)[..., ys, xs]
+    assert rel_err(vals, ref) < TOL[name]
+    # the per-pixel series in real units (return-level notebook formulas; c = 0 for tasmax there)
+    hr_pix = 270.0 + 3.0 * vals.permute(0, 1, 3, 2).cpu()             # stand-in for residual_to_hr at the pixels
+    for var in ("pr", "tasmin", "tasmax"):
+        assert torch.isfinite(O.return_level_pixel_series(hr_pix, var)).all()
+    with pytest.raises(IndexError):
+        m.sample_pixels(x, 2, [(64, 0)])
+
+
 def test_loss_kernels_known_answers(golden):
     import prob_unet_utils as U
     e, t = torch.from_numpy(golden["L_ens"]).cuda().requires_grad_(True), torch.from_numpy(golden["L_tgt"]).cuda()

@@ -171,6 +171,9 @@ def test_inverse_transforms_and_mae_match_the_real_reference_functions():
     np.testing.assert_array_equal((x * 24 * 60 * 60).numpy(), g["tf_mmday"])
     real = O.invert_transfo_3vars(torch.from_numpy(g["tf_stored"]))
     np.testing.assert_allclose(real.numpy(), g["tf_real"], rtol=1e-6, atol=1e-6)
+    hp = torch.from_numpy(g["rl_hr"]).permute(0, 2, 3, 1)            # [..., 3]: test_return_levels.ipynb cell 2
+    for var in ("pr", "tasmin", "tasmax"):
+        np.testing.assert_allclose(O.return_level_pixel_series(hp, var).numpy(), g["rl_" + var], rtol=1e-6, atol=1e-6)
     gt, pe = torch.from_numpy(g["mae_gt"]), torch.from_numpy(g["mae_pred"])
     np.testing.assert_allclose(O.compute_mae(gt, pe), g["mae_ens"], rtol=1e-6)
     np.testing.assert_allclose(O.compute_mae(gt, pe[:, 0]), g["mae_det"], rtol=1e-6)
