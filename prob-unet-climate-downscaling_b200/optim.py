@@ -17,6 +17,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = grad_scale
         self._tables = {}
+        self._events = {}
         self._step_dev = None      # device int32 step counter (CUDA-graph mode, see graph.GraphedTrainStep)
 
     def use_device_step(self, counter):
@@ -30,19 +31,35 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step_dev = counter
 
     def _table(self, gi, plist):
-        """Device table of {p, g, m, v, n} rows; rebuilt only when a pointer changes."""
+        """Device table of {p, g, m, v, n} rows; refreshed only when a pointer changes.  The pinned staging buffer and
+        the device buffer are allocated ONCE per group: a refresh inside a CUDA-graph capture (the gradients live at
+        new addresses in the graph's memory pool) must not allocate pinned memory -- that invalidates the capture --
+        so it only rewrites the staging buffer on the host and enqueues the H2D copy (a memcpy node of the graph)."""
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
         ent = self._tables.get(gi)
-        if ent is None or ent[0] != key:
-            rows = (N.AdamWEntry * len(plist))()
-            for i, p in enumerate(plist):
-                st = self.state[p]
-                rows[i].p, rows[i].g = p.data_ptr(), p.grad.data_ptr()
-                rows[i].m, rows[i].v, rows[i].n = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
-            host = torch.frombuffer(bytearray(bytes(rows)), dtype=torch.uint8).pin_memory()
-            dev = host.to(plist[0].device, non_blocking=True)
-            ent = (key, dev, host, max(p.numel() for p in plist))
-            self._tables[gi] = ent
+        if ent is not None and ent[0] == key:
+            return ent
+        nbytes = C.sizeof(N.AdamWEntry) * len(plist)
+        if ent is None or ent[2].numel() != nbytes:
+            host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            dev = torch.empty(nbytes, dtype=torch.uint8, device=plist[0].device)
+        else:
+            dev, host = ent[1], ent[2]
+        capturing = torch.cuda.is_current_stream_capturing()
+        ev = self._events.get(gi)
+        if ev is not None and not capturing:
+            ev.synchronize()          # the previous H2D copy of this staging buffer must have finished before it is rewritten
+        rows = (N.AdamWEntry * len(plist)).from_address(host.data_ptr())
+        for i, p in enumerate(plist):
+            st = self.state[p]
+            rows[i].p, rows[i].g = p.data_ptr(), p.grad.data_ptr()
+            rows[i].m, rows[i].v, rows[i].n = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+        dev.copy_(host, non_blocking=True)
+        if not capturing:
+            ev = self._events.setdefault(gi, torch.cuda.Event())
+            ev.record()
+        ent = (key, dev, host, max(p.numel() for p in plist))
+        self._tables[gi] = ent
         return ent
 
     @torch.no_grad()
