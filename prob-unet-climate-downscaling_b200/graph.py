@@ -43,17 +43,29 @@ class GraphedTrainStep:
         model.sync_scalars = False
         optimizer.use_device_step(self.counters[0:1])
         N.check(N.lib().pub_debug_pointer(b"seed_salt", C.c_void_p(self.counters[1:2].data_ptr())), "seed_salt")
-        # eager warm-up on a side stream: allocates workspaces / optimizer state, sets kernel attributes, builds NCCL
+        # Autograd binds every parameter's AccumulateGrad node to the stream that was current when the node was created,
+        # and keeps the node while any graph references it.  model.{prior,posterior}_latent_space hold the encoders'
+        # graph of the LAST step, so nodes created by earlier eager steps on the (legacy) default stream would survive
+        # into the capture, where touching the legacy stream is an error: drop them, and warm up / capture on ONE stream.
+        self._drop_graph_references()
+        self.stream = torch.cuda.Stream()
+        # eager warm-up on that stream: allocates workspaces / optimizer state, sets kernel attributes, builds NCCL
         # communicators -- nothing of that may happen for the first time during capture
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
             for _ in range(max(1, warmup)):
                 self._body()
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(self.stream)
         torch.cuda.synchronize()
         self.graph = None
         self.recapture()
+
+    def _drop_graph_references(self):
+        import gc
+        self.model.prior_latent_space = None
+        self.model.posterior_latent_space = None
+        self.out = None
+        gc.collect()
 
     def _body(self):
         N.check(N.lib().pub_advance_counters(N.ptr(self.counters), N.stream()), "pub_advance_counters")
@@ -65,10 +77,11 @@ class GraphedTrainStep:
         return out
 
     def recapture(self):
+        self._drop_graph_references()
         self.opt.zero_grad(set_to_none=True)
         l0 = N.lib().pub_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.stream):
             self.out = self._body()
         self.launches_per_step = int(N.lib().pub_launch_count() - l0)
 
