@@ -225,7 +225,7 @@ def test_fused_groupnorm_epilogues_match_the_separate_passes():
 def test_cuda_graph_training_step_matches_eager_steps():
     """graph.GraphedTrainStep: the whole step (elbo + backward + fused AdamW) captured once and replayed.
     (a) deterministic setting (eval(): dropout off, injected eps): parameters after warm-up + capture + 3 replays are
-    BIT-identical to the same number of eager steps through the same device-step optimizer path; the step count
+    BIT-identical to the same number (warm-up + replays) of eager steps through the same device-step optimizer path; the step count
     lives on the device.  (b) train(): the device salt gives every replay new dropout masks and eps."""
     import ctypes as C
     import _native as N
@@ -248,7 +248,7 @@ def test_cuda_graph_training_step_matches_eager_steps():
         out = g(x, y)
     torch.cuda.synchronize()
     n_steps = int(g.counters[0].item())
-    assert n_steps == 2 + 1 + 3                        # warm-up + the capture pass + 3 replays
+    assert n_steps == 2 + 3                            # 2 eager warm-up steps + 3 replays (the capture pass only records)
     assert g.launches_per_step > 500
     loss_g = float(out[0])
     g.close()
