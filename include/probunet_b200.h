@@ -281,6 +281,24 @@ int pub_adamw_step(const pub_adamw_entry* device_table, int n_tensors, int64_t m
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                    float grad_scale, pub_stream_t s);
 
+/* ------------------------------------------------------------------------------------
+ * Ensemble post-processing diagnostics of results.ipynb, all on the device:
+ *   pub_radial_psd  : psd() / compute_psd_tensor() of cell 4 -- torch.fft.fftn power spectrum, azimuthal mean over the
+ *                     radial bins [k + 0.5, k + 1.5) (scipy.stats.binned_statistic "mean") times the shell area, for every
+ *                     (sample, variable) field of data [N, C, H, H] f32 (H a power of two <= 128), and the mean over
+ *                     the N samples.  transfo / units: the inverse variable transforms of that cell fused into the load
+ *                     (pr = kgm2sTommday(softplus(x0)), tasmin = KToC(x1), tasmax = KToC(softplus(x2, c=0) + x1)).
+ *                     table: bin -> pixel list, built once per H on the host (pub_psd_build_table) and copied to the device.
+ *   pub_histogram   : np.histogram(values, bins=edges) of cell 15 (edges f64 ascending, last bin closed); counts must be
+ *                     zeroed by the caller and are accumulated (several calls add up).
+ * ---------------------------------------------------------------------------------- */
+size_t pub_psd_table_ints(int H);
+int pub_psd_build_table(int H, int* table_host);
+int pub_radial_psd(const float* data, int N, int C, int H, int transfo, int units, const int* table_dev,
+                   float* psd_fields, float* psd_mean, pub_stream_t s);
+int pub_histogram(const float* values, int64_t n, const double* edges_dev, int nbins, unsigned long long* counts,
+                  pub_stream_t s);
+
 /* CUDA-graph variants (the whole training step captured once and replayed): a captured graph
  * replays the kernel ARGUMENTS of the capture, so whatever changes from step to step lives in device memory.
  * counters[0] = optimizer step count, counters[1] = random salt; pub_advance_counters (one tiny launch at the top of

@@ -424,6 +424,39 @@ def residual_to_real(residual: Tensor, lrinterp: Tensor, std_hr: Tensor) -> Tens
     return invert_transfo_3vars(lrinterp + residual * (std_hr + 1e-10))
 
 
+def psd_radial(image2d: Tensor):
+    """results.ipynb cell 4 ``psd``: torch.fft.fftn power, radial wavenumber grid from fftfreq, mean per bin
+    [k + 0.5, k + 1.5) (scipy.stats.binned_statistic 'mean': last edge closed) times the shell area."""
+    H, W = image2d.shape
+    power = (torch.abs(torch.fft.fftn(image2d)) ** 2).flatten().numpy().astype(np.float64)
+    kfreq = torch.fft.fftfreq(H) * H
+    kx, ky = torch.meshgrid(kfreq, kfreq, indexing="ij")
+    kr = torch.sqrt(kx ** 2 + ky ** 2).flatten().numpy().astype(np.float64)
+    kbins = np.arange(0.5, H // 2 + 1, 1.0)
+    idx = np.searchsorted(kbins, kr, side="right") - 1
+    idx[kr == kbins[-1]] = len(kbins) - 2
+    ok = (idx >= 0) & (idx < len(kbins) - 1)
+    sums = np.bincount(idx[ok], weights=power[ok], minlength=len(kbins) - 1)
+    cnt = np.bincount(idx[ok], minlength=len(kbins) - 1)
+    vals = sums / cnt * np.pi * (kbins[1:] ** 2 - kbins[:-1] ** 2)
+    return 0.5 * (kbins[1:] + kbins[:-1]), vals
+
+
+def compute_psd_tensor(data: Tensor, transfo: bool):
+    """results.ipynb cell 4 ``compute_psd_tensor`` (tasmax: softplus with c = 0 in THIS cell)."""
+    d = data.reshape(-1, *data.shape[-3:]) if data.dim() == 5 else data
+    acc = [[], [], []]
+    for smp in d:
+        s0, s1, s2 = smp[0].clone(), smp[1].clone(), smp[2].clone()
+        if transfo:
+            s0 = softplus_ref(s0)
+            s2 = softplus_ref(s2, c=0.0) + s1
+        chans = (s0 * 24 * 60 * 60, s1 - 273.15, s2 - 273.15)
+        for i in range(3):
+            acc[i].append(psd_radial(chans[i])[1])
+    return np.stack([np.mean(np.stack(a, axis=0), axis=0) for a in acc], axis=0)
+
+
 def return_level_pixel_series(members_hr: Tensor, variable: str) -> Tensor:
     """test_return_levels.ipynb cell 2: the per-pixel daily value extracted from a residual_to_hr'd member
     (``members_hr`` [..., 3] = the three stored variables at the chosen pixel): pr = kgm2sTommday(softplus(x0)),

@@ -86,6 +86,7 @@ EXPORTS = [
     "pub_scale_by_device_scalar", "pub_ensemble_metrics_workspace", "pub_ensemble_metrics", "pub_adamw_step",
     "pub_groupnorm_scratch_bytes", "pub_groupnorm_silu_forward", "pub_groupnorm_silu_backward",
     "pub_conv2d_fused_rows", "pub_conv2d_forward_fused", "pub_advance_counters", "pub_adamw_step_dev",
+    "pub_psd_table_ints", "pub_psd_build_table", "pub_radial_psd", "pub_histogram",
 ]
 
 
@@ -101,7 +102,7 @@ def lib():
         l.pub_launch_count.restype = C.c_ulonglong
         for name in ("pub_conv2d_wgrad_workspace", "pub_unet_workspace_bytes", "pub_encoder_workspace_bytes",
                      "pub_fcomb_backward_workspace", "pub_loss_workspace", "pub_fcomb_forward_workspace",
-                     "pub_ensemble_metrics_workspace", "pub_msssim_workspace", "pub_groupnorm_scratch_bytes"):
+                     "pub_ensemble_metrics_workspace", "pub_msssim_workspace", "pub_groupnorm_scratch_bytes", "pub_psd_table_ints"):
             if hasattr(l, name):
                 getattr(l, name).restype = C.c_size_t
         _lib = l
@@ -884,3 +885,45 @@ def ensemble_metrics(preds, hr, lrinterp=None, std_hr=None):
                                      int(tr), T, M, Cc, H * W, ptr(crps), ptr(mae), ptr(ws), C.c_size_t(nws), stream()),
           "pub_ensemble_metrics")
     return crps, mae
+
+
+# ======================================================================================
+# ensemble post-processing diagnostics (results.ipynb cells 4 and 15)
+# ======================================================================================
+_psd_tables = {}
+
+
+def _psd_table(H, device):
+    key = (H, str(device))
+    if key not in _psd_tables:
+        n = lib().pub_psd_table_ints(H)
+        host = torch.empty(n, dtype=torch.int32)
+        used = lib().pub_psd_build_table(H, C.c_void_p(host.data_ptr()))
+        if used < 0:
+            raise NativeError("pub_psd_build_table: " + lib().pub_last_error().decode())
+        _psd_tables[key] = host.to(device)
+    return _psd_tables[key]
+
+
+def radial_psd(data, transfo=False, units=False):
+    """data [N,C,H,H] f32 -> (psd per field [N,C,H/2], mean over N [C,H/2]); see pub_radial_psd."""
+    require_cuda(data)
+    Nn, Cc, H, W = data.shape
+    if H != W:
+        raise ValueError("radial_psd expects square fields")
+    d = data.contiguous().float()
+    per = torch.empty(Nn, Cc, H // 2, device=d.device, dtype=torch.float32)
+    mean = torch.empty(Cc, H // 2, device=d.device, dtype=torch.float32)
+    check(lib().pub_radial_psd(ptr(d), Nn, Cc, H, int(transfo), int(units), ptr(_psd_table(H, d.device)), ptr(per),
+                               ptr(mean), stream()), "pub_radial_psd")
+    return per, mean
+
+
+def histogram(values, edges):
+    """np.histogram(values, bins=edges) -> int64 counts [len(edges) - 1] on the device."""
+    require_cuda(values)
+    v = values.contiguous().float().reshape(-1)
+    e = torch.as_tensor(edges, dtype=torch.float64).to(v.device).contiguous()
+    counts = torch.zeros(e.numel() - 1, device=v.device, dtype=torch.int64)
+    check(lib().pub_histogram(ptr(v), C.c_int64(v.numel()), ptr(e), e.numel() - 1, ptr(counts), stream()), "pub_histogram")
+    return counts

@@ -39,3 +39,24 @@ def ensemble_scores_from_residuals(residual_preds, hr, lrinterp, std_hr):
     """Additive API: members are standardised residuals; residual_to_hr + inverse transforms
     (src/climex_utils.py:277-285, results.ipynb cell 2) are fused into the metric kernel."""
     return N.ensemble_metrics(_dev(residual_preds), _dev(hr), _dev(lrinterp), _dev(std_hr))
+
+
+def compute_psd_tensor(data, transfo):
+    """results.ipynb cell 4 (``compute_psd_tensor`` + ``psd``): radially averaged power spectral density of every
+    (sample[, member], variable) field in real units, mean over samples -> {'pr': P(k), 'tasmin': P(k), 'tasmax': P(k)}
+    (numpy, length H/2), plus ``kvals`` under the key 'k'.  data: [T,3,H,W] or [T,M,3,H,W]; ``transfo`` as in the
+    notebook (True: data still in the stored-transform domain)."""
+    d = _dev(data)
+    if d.dim() == 5:
+        d = d.reshape(-1, *d.shape[2:])
+    _, mean = N.radial_psd(d, transfo=bool(transfo), units=True)
+    m = mean.double().cpu().numpy()
+    H = d.shape[-1]
+    out = {v: m[i].copy() for i, v in enumerate(_VARS)}
+    out["k"] = 0.5 * (torch.arange(0.5, H // 2 + 1, 1.0)[1:] + torch.arange(0.5, H // 2 + 1, 1.0)[:-1]).numpy()
+    return out
+
+
+def value_histogram(values, edges):
+    """results.ipynb cell 15: ``np.histogram(values, bins=edges)`` counts (the caller takes log(count + 1))."""
+    return N.histogram(_dev(values), edges).cpu().numpy()

@@ -65,6 +65,27 @@ out["rl_pr"] = CU.kgm2sTommday(CU.softplus(hp[:, 0].clone())).numpy()
 out["rl_tasmax"] = CU.KToC(hp[:, 1] + CU.softplus(hp[:, 2].clone(), c=0)).numpy()
 out["rl_tasmin"] = CU.KToC(hp[:, 1].clone()).numpy()
 
+# ---- results.ipynb cell 4 (psd / compute_psd_tensor), executed from the notebook's own source with the real scipy
+cell4 = "".join(nb["cells"][4]["source"])
+assert "def compute_psd_tensor" in cell4 and "def psd" in cell4
+import scipy.stats as _stats  # noqa: E402
+ns4 = {"torch": torch, "np": np, "stats": _stats, "cu": CU}
+exec(compile(cell4, "results.ipynb:cell4", "exec"), ns4)
+pf = torch.randn(6, 3, 32, 32, generator=g) * torch.tensor([2.0, 6.0, 3.0]).view(1, 3, 1, 1) + torch.tensor([0.5, 275.0, 4.0]).view(1, 3, 1, 1)
+pf = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(pf, (1, 1, 1, 1), mode="circular"), 3, 1)   # some spectral slope
+out["psd_fields"] = pf.numpy()
+k4, p4 = ns4["psd"](pf[0, 1].clone())
+out["psd_k"], out["psd_single"] = np.asarray(k4), np.asarray(p4)
+for tf in (True, False):
+    r4 = ns4["compute_psd_tensor"](pf.clone(), transfo=tf)
+    out["psd_tensor_" + ("transfo" if tf else "plain")] = np.stack([r4[v] for v in ("pr", "tasmin", "tasmax")], axis=0)
+r5 = ns4["compute_psd_tensor"](pf.clone().reshape(2, 3, 3, 32, 32), transfo=True)       # the [T, M, 3, H, W] form
+out["psd_tensor_5d"] = np.stack([r5[v] for v in ("pr", "tasmin", "tasmax")], axis=0)
+# ---- cell 15: np.histogram over np.linspace(min, max, NBINS) edges
+hv = (torch.randn(5000, generator=g) * 3 + 1).numpy()
+he = np.linspace(hv.min(), hv.max(), 100)
+out["hist_values"], out["hist_edges"], out["hist_counts"] = hv, he, np.histogram(hv, bins=he)[0]
+
 # ---- metrics.compute_mae (src/metrics.py:48-71) run for real; only the module-level `import pysteps` is stubbed
 # (compute_mae never calls it).  crps_over_groundtruth needs pysteps itself and stays a restatement (oracle header).
 sys.modules["pysteps"] = types.ModuleType("pysteps")
