@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "ensemble"],
+    ap.add_argument("--workload", default="train", choices=["train", "ensemble", "detunet", "latent256"],
                     help="train: BASELINE.json configs[2] (train samples/s, the headline metric); ensemble: configs[3] "
                          "(prior-sampling ensemble members/s: M members per field + CRPS/MAE, fields sharded over the GPUs)")
     ap.add_argument("--fields", type=int, default=512, help="ensemble workload: fields per GPU and pass (weak scaling)")
@@ -518,6 +518,140 @@ def run_ensemble(args, dist, rank, world, local, N, pk, pk_kind):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1]: deterministic U-Net (src/deterministic_unet_main.py:52 -> networks.UNet defaults:
+# model_channels 16, channel_mult [1,4,8,16], 14.79 M parameters, 66.25 GFLOP per training sample at 128^2) trained
+# with MSE (src/trainmodel.py:158-160) and AdamW
+# ------------------------------------------------------------------------------------------------
+def run_detunet(args, dist, rank, world, local, N, pk):
+    import networks
+    from helpers import dezero
+    from climex_synth import make_fields
+    from optim import FusedAdamW
+    from parallel import GradSynchronizer
+    B, R = (args.batch if args.batch != 64 else 16), args.res          # src/trainmodel.py:36 batch 16 (override with --batch)
+    torch.manual_seed(42)
+    net = networks.UNet(img_resolution=(R, R), in_channels=3, out_channels=3, label_dim=0, use_diffuse=False,
+                        compute_dtype=args.dtype)
+    dezero(net)
+    net = net.cuda().train()
+    N.manual_seed(1000 + rank)
+    opt = FusedAdamW(net.parameters(), lr=1e-4, grad_scale=1.0 / world)
+    GradSynchronizer().install()
+    f = make_fields(B, R, R, 16 if R >= 128 else 8, seed=1234 + 1 + rank)
+    xh, yh = f["inputs"].pin_memory(), f["targets"].pin_memory()
+    x, y = xh.cuda(), yh.cuda()
+
+    def step(xd, yd):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(net(xd, class_labels=None), yd)   # nn.MSELoss on a [B,3,H,W] tensor: glue
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(x, y)
+    barrier(); sampler.mark()
+    l0 = N.lib().pub_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x, y)
+    e1.record(); barrier()
+    launches = N.lib().pub_launch_count() - l0
+    clocks = sampler.read()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        lv = step(xh.cuda(non_blocking=True), yh.cuda(non_blocking=True)).item()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - w0
+    sampler.stop()
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    n = B * world * args.steps
+    val = n / t_dev
+    line = {"metric": "train_samples_per_s", "value": val, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"deterministic_unet_train_{R}x{R}_b{B}pergpu_mse",
+                       "reference_config": "BASELINE.json configs[1]: deterministic U-Net baseline (deterministic_unet_main.py) "
+                                           "training on 128x128 pr/tasmin/tasmax", "per_gpu_batch": B, "resolution": R,
+                       "model": "networks.UNet(model_channels 16, channel_mult [1,4,8,16]), 14.79 M parameters",
+                       "optimizer": "AdamW lr 1e-4 (fused)", "dropout": 0.1,
+                       "note": "the 16-channel 128^2 level and the 3-channel ends run on the fp32-FMA conv kernels (C % 32 != 0)"},
+            "e2e": {"value": n / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "model_tflops_per_gpu": val / world * 66.25 * (R / 128.0) ** 2 / 1e3,
+            "final_loss": float(loss.detach())}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: posterior latent exploration sweep (src/latent_exploration_posterior.py:255-343) on 256x256
+# grids: per latent_dim, posterior means of N fields, unet(x0) once, two 10x10 grids decoded through fcomb on an
+# expanded (non-contiguous) feature view.  PCA stays on the host (sklearn) and is not timed.
+# ------------------------------------------------------------------------------------------------
+def run_latent256(args, dist, rank, world, local, N, pk):
+    from helpers import canonical_model
+    from climex_synth import make_fields
+    R = 256 if args.res == 128 else args.res
+    NF, FB = 64, 16                                   # fields per latent_dim, fields per posterior call
+    rows = []
+    f = make_fields(NF, R, R, 16, seed=77 + rank)
+    x, y = f["inputs"].cuda(), f["targets"].cuda()
+    tot_t, tot_units = 0.0, 0
+    for L in (2, 8, 16, 32, 64):
+        m = canonical_model(latent_dim=L, compute_dtype=args.dtype, device="cuda")
+        m.eval()
+
+        def sweep():
+            with torch.no_grad():
+                mus = torch.cat([m.posterior(x[i:i + FB], y[i:i + FB]).base_dist.loc for i in range(0, NF, FB)])   # :255-263
+                feat = m.unet(x[:1])                                                                           # :290
+                grids = []
+                for _ in range(2):                                                                             # deciles, +-3 sigma
+                    zs = mus[:1] + torch.linspace(-3, 3, 100, device="cuda").unsqueeze(1) * mus.std(dim=0, keepdim=True)
+                    grids.append(m.fcomb(feat.expand(100, -1, -1, -1), zs))                                    # :308-343
+            return mus, grids
+        for _ in range(2):
+            sweep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            mus, grids = sweep()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        rows.append({"latent_dim": L, "ms_per_sweep": round(ms, 3), "posterior_fields_per_s": NF / ms * 1e3,
+                     "decodes_per_sweep": 200})
+        tot_t += ms * 1e-3; tot_units += NF
+        del m
+        N.workspaces.clear(); torch.cuda.empty_cache()
+    line = {"metric": "posterior_fields_per_s", "value": tot_units / tot_t, "unit": "fields/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": 2, "ms_per_step": 1e3 * tot_t / 5, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"posterior_latent_sweep_{R}x{R}_N{NF}_latent_2_8_16_32_64",
+                       "reference_config": "BASELINE.json configs[4]: posterior latent exploration sweep over latent_dim on 256x256 grids",
+                       "fields": NF, "field_batch": FB, "resolution": R,
+                       "step": "per latent_dim: posterior means of 64 fields + unet(x0) + 2 x 100 fcomb decodes on an expanded feature view"},
+            "per_latent_dim": rows}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -541,6 +675,10 @@ def run_b200(args):
 
     if args.workload == "ensemble":
         return run_ensemble(args, dist, rank, world, local, N, pk, pk_kind)
+    if args.workload == "detunet":
+        return run_detunet(args, dist, rank, world, local, N, pk)
+    if args.workload == "latent256":
+        return run_latent256(args, dist, rank, world, local, N, pk)
     B, R = args.batch, args.res
     if args.strong:
         assert args.batch % world == 0, "--strong: the global batch must be divisible by the number of GPUs"
