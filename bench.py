@@ -789,6 +789,7 @@ def run_b200(args):
         # ---- the same step captured once in a CUDA graph and replayed (graph.GraphedTrainStep): no host work per step
         try:
             from graph import GraphedTrainStep
+            loss = None               # a live loss keeps the eager steps' autograd graph (bound to the default stream) alive
             gstep = GraphedTrainStep(model, opt, x, y, M=M if args.loss in ("afcrps", "crps") else None, warmup=2)
             for _ in range(3):
                 gstep(x, y)

@@ -81,8 +81,16 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         l0 = N.lib().pub_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=self.stream):
-            self.out = self._body()
+        try:
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.out = self._body()
+        except Exception as ex:
+            self.graph = None
+            raise N.NativeError(
+                "CUDA-graph capture of the training step failed.  The usual cause: a tensor from an earlier EAGER step (the "
+                "last loss, a kept elbo() output) still references that step's autograd graph, whose AccumulateGrad nodes "
+                "are bound to the default stream -- which must not be touched during capture.  Drop those references "
+                f"(`del loss`) before constructing GraphedTrainStep.  Original error: {ex!r}") from ex
         self.launches_per_step = int(N.lib().pub_launch_count() - l0)
 
     def __call__(self, x, y):
