@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--fields", type=int, default=512, help="ensemble workload: fields per GPU and pass (weak scaling)")
     ap.add_argument("--field-batch", type=int, default=64, help="ensemble workload: fields per model call")
     ap.add_argument("--ens-members", type=int, default=100, help="ensemble workload: members per field")
+    ap.add_argument("--graph", action="store_true",
+                    help="train: step through graph.GraphedTrainStep (the step captured once in a CUDA graph, replayed per batch)")
     ap.add_argument("--strong", action="store_true", help="train: --batch is the GLOBAL batch, split over the GPUs (strong scaling)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--res", type=int, default=128)
@@ -694,12 +696,18 @@ def run_b200(args):
     x_host, y_host = f["inputs"].pin_memory(), f["targets"].pin_memory()
     x, y = x_host.cuda(), y_host.cuda()
 
-    def step_device(xd, yd):
+    def step_eager(xd, yd):
         opt.zero_grad(set_to_none=True)
         out = model.elbo(xd, yd, None, M=M) if args.loss in ("afcrps", "crps") else model.elbo(xd, yd, None)
         out[0].backward()
         opt.step()
         return out[0]
+
+    step_device = step_eager
+    if args.graph:
+        from graph import GraphedTrainStep
+        gmain = GraphedTrainStep(model, opt, x, y, M=M if args.loss in ("afcrps", "crps") else None, warmup=3)
+        step_device = lambda xd, yd: gmain(xd, yd)[0]       # noqa: E731  (copies the batch into the graph's static inputs)
 
     def barrier():
         if world > 1:
@@ -724,6 +732,8 @@ def run_b200(args):
     cpu_enqueue = (time.perf_counter() - c0) / args.steps
     barrier()
     launches = (N.lib().pub_launch_count() - l0)
+    if args.graph:
+        launches = gmain.launches_per_step * args.steps      # replays do not pass through the library's launch counter
     clocks = sampler.read()
     t_dev = evs[0].elapsed_time(evs[-1]) * 1e-3
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
@@ -755,7 +765,8 @@ def run_b200(args):
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
         "ms_per_step_each": [round(v, 2) for v in per_step], "higher_is_better": True,
         "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": dict(workload_config(args), per_gpu_batch=B, global_batch=B * world),
+        "config": dict(workload_config(args), per_gpu_batch=B, global_batch=B * world,
+                       stepping="CUDA graph replay (graph.GraphedTrainStep)" if args.graph else "eager (model.elbo + backward + FusedAdamW.step)"),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * t_e2e / args.steps, "ms_per_step_each": e2e_each},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": 1e3 * cpu_enqueue,
@@ -765,6 +776,8 @@ def run_b200(args):
         "grad_sync": {"collectives_per_step": sync.calls // max(1, (max(args.warmup, 3) + 2 * args.steps)),
                       "bytes_per_step": sync.bytes // max(1, (max(args.warmup, 3) + 2 * args.steps)), "world": world},
     }
+    if args.graph:
+        args.no_aux = True          # the auxiliary legs re-use the eager step; run them without --graph
     if rank == 0 and not args.no_aux:
         # ---- roofline of the dominant kernel family, measured live
         try:
