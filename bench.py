@@ -799,35 +799,6 @@ def run_b200(args):
         except Exception as ex:  # never lose the headline line
             line["roofline"] = {"error": repr(ex)}
     if not args.no_aux:
-        # ---- the same step captured once in a CUDA graph and replayed (graph.GraphedTrainStep): no host work per step
-        try:
-            from graph import GraphedTrainStep
-            loss = None               # a live loss keeps the eager steps' autograd graph (bound to the default stream) alive
-            gstep = GraphedTrainStep(model, opt, x, y, M=M if args.loss in ("afcrps", "crps") else None, warmup=2)
-            for _ in range(3):
-                gstep(x, y)
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            h0 = time.perf_counter()
-            for _ in range(args.steps):
-                gout = gstep(x, y)
-            host_ms = 1e3 * (time.perf_counter() - h0) / args.steps
-            g1.record()
-            barrier()
-            tg = torch.tensor([g0.elapsed_time(g1) * 1e-3], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            if rank == 0:
-                line["cuda_graph"] = {"samples_per_s": samples / float(tg[0]), "ms_per_step": 1e3 * float(tg[0]) / args.steps,
-                                      "host_enqueue_ms_per_step": host_ms, "launches_per_step": gstep.launches_per_step,
-                                      "what": "graph.GraphedTrainStep: elbo + backward + all-reduce + fused AdamW captured once, "
-                                              "replayed per step (device-side step counter and random salt; scalars stay on the device)"}
-            gstep.close()
-            del gstep, gout
-        except Exception as ex:
-            if rank == 0:
-                line["cuda_graph"] = {"error": repr(ex)[:300]}
         # ---- second half of BASELINE.json's metric: ensemble members/s (configs[3]), every rank its own fields, one
         # final gather -- a short run here; `--workload ensemble` is the full-length line
         try:
