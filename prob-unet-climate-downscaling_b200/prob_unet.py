@@ -141,6 +141,29 @@ class ProbabilisticUNet(nn.Module):
         # waiting for the GPU; the values are the same.
         self.sync_scalars = True
 
+    # The three sub-networks are independent until fcomb / KL.  The U-Net's 32^2 and 16^2 levels and the encoders' late
+    # stages launch fewer tiles than the GPU has SMs, so the two Gaussian encoders run on a side stream next to the
+    # U-Net (autograd replays that in backward: each backward node runs on its forward's stream).  Off:
+    # PROBUNET_B200_ENCODER_STREAM=0.
+    def _encoders_beside_unet(self, x, target):
+        import os
+        if os.environ.get("PROBUNET_B200_ENCODER_STREAM", "1") == "0" or not x.is_cuda \
+                or torch.cuda.is_current_stream_capturing():
+            feat = self.unet(x, _nhwc_out=True)
+            prior = self.prior(x)
+            post = self.posterior(x, target) if target is not None else None
+            return feat, prior, post
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            prior = self.prior(x)
+            post = self.posterior(x, target) if target is not None else None
+        feat = self.unet(x, _nhwc_out=True)
+        cur.wait_stream(self._side)
+        return feat, prior, post
+
     def set_compute_dtype(self, name):
         self.unet.compute_dtype = self.prior.compute_dtype = self.posterior.compute_dtype = name
 
@@ -158,8 +181,7 @@ class ProbabilisticUNet(nn.Module):
     @torch.no_grad()
     def sample(self, x, n, eps=None):
         """n prior members per field: U-Net and prior run once, fcomb n times -> [B,n,C,H,W]."""
-        feat = self.unet(x, _nhwc_out=True)
-        self.prior_latent_space = self.prior(x)
+        feat, self.prior_latent_space, _ = self._encoders_beside_unet(x, None)
         z = self.prior_latent_space.rsample((n,), eps=eps)
         return _native.fcomb_apply(self.fcomb, feat, z, nhwc=True)
 
@@ -199,9 +221,7 @@ class ProbabilisticUNet(nn.Module):
             M = 5 if lt in ("afcrps", "crps") else 1
         if lt in ("afcrps", "crps") and M < 2:
             raise ValueError(f"M must be at least 2 to compute afCRPS but got M={M}")
-        feat = self.unet(x, _nhwc_out=True)
-        self.prior_latent_space = self.prior(x)
-        self.posterior_latent_space = self.posterior(x, target)
+        feat, self.prior_latent_space, self.posterior_latent_space = self._encoders_beside_unet(x, target)
         q, p = self.posterior_latent_space.base_dist, self.prior_latent_space.base_dist
         kl_div = _native.kl_normal(q.loc, q.scale, p.loc, p.scale)
         if lt == "l1":
