@@ -147,21 +147,32 @@ class ProbabilisticUNet(nn.Module):
     # PROBUNET_B200_ENCODER_STREAM=0.
     def _encoders_beside_unet(self, x, target):
         import os
-        if os.environ.get("PROBUNET_B200_ENCODER_STREAM", "1") == "0" or not x.is_cuda \
-                or torch.cuda.is_current_stream_capturing():
+        mode = int(os.environ.get("PROBUNET_B200_ENCODER_STREAM", "1"))
+        if mode == 0 or not x.is_cuda or torch.cuda.is_current_stream_capturing():
             feat = self.unet(x, _nhwc_out=True)
             prior = self.prior(x)
             post = self.posterior(x, target) if target is not None else None
             return feat, prior, post
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream()
+            self._side = [torch.cuda.Stream(), torch.cuda.Stream()]
         cur = torch.cuda.current_stream()
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
+        s_prior, s_post = self._side[0], self._side[1 if mode >= 3 else 0]
+        unet_first = mode in (2, 4)          # experiment: autograd enqueues backward nodes in reverse creation order
+        feat = self.unet(x, _nhwc_out=True) if unet_first else None
+        s_prior.wait_stream(cur)
+        if s_post is not s_prior:
+            s_post.wait_stream(cur)
+        with torch.cuda.stream(s_prior):
             prior = self.prior(x)
-            post = self.posterior(x, target) if target is not None else None
-        feat = self.unet(x, _nhwc_out=True)
-        cur.wait_stream(self._side)
+        post = None
+        if target is not None:
+            with torch.cuda.stream(s_post):
+                post = self.posterior(x, target)
+        if not unet_first:
+            feat = self.unet(x, _nhwc_out=True)
+        cur.wait_stream(s_prior)
+        if s_post is not s_prior:
+            cur.wait_stream(s_post)
         return feat, prior, post
 
     def set_compute_dtype(self, name):
