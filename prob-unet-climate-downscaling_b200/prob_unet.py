@@ -142,12 +142,13 @@ class ProbabilisticUNet(nn.Module):
         self.sync_scalars = True
 
     # The three sub-networks are independent until fcomb / KL.  The U-Net's 32^2 and 16^2 levels and the encoders' late
-    # stages launch fewer tiles than the GPU has SMs, so the two Gaussian encoders run on a side stream next to the
-    # U-Net (autograd replays that in backward: each backward node runs on its forward's stream).  Off:
-    # PROBUNET_B200_ENCODER_STREAM=0.
+    # stages launch fewer tiles than the GPU has SMs, so the two Gaussian encoders run on side streams next to the
+    # U-Net (autograd replays that in backward: each backward node runs on its forward's stream).  Measured at B = 64:
+    # 23.2 -> 22.5 ms per step (profiles/r02_encoder_streams_ab.txt).  PROBUNET_B200_ENCODER_STREAM: 0 off, 1 one side
+    # stream, 3 (default) one per encoder, 2 / 4 the same with the U-Net enqueued first (slower).
     def _encoders_beside_unet(self, x, target):
         import os
-        mode = int(os.environ.get("PROBUNET_B200_ENCODER_STREAM", "1"))
+        mode = int(os.environ.get("PROBUNET_B200_ENCODER_STREAM", "3"))
         if mode == 0 or not x.is_cuda or torch.cuda.is_current_stream_capturing():
             feat = self.unet(x, _nhwc_out=True)
             prior = self.prior(x)
