@@ -296,6 +296,8 @@ def in_step_kernel_times(step_fn, N):
     dependent launch switched off for that step so that kernel durations do not overlap."""
     from torch.profiler import profile, ProfilerActivity
     N.lib().pub_debug_option(b"pdl", 0)
+    saved_stream_mode = os.environ.get("PROBUNET_B200_ENCODER_STREAM")
+    os.environ["PROBUNET_B200_ENCODER_STREAM"] = "0"     # one stream: concurrent kernels would stretch each other's durations
     try:
         step_fn(); torch.cuda.synchronize()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -303,6 +305,10 @@ def in_step_kernel_times(step_fn, N):
             torch.cuda.synchronize()
     finally:
         N.lib().pub_debug_option(b"pdl", 1)
+        if saved_stream_mode is None:
+            os.environ.pop("PROBUNET_B200_ENCODER_STREAM", None)
+        else:
+            os.environ["PROBUNET_B200_ENCODER_STREAM"] = saved_stream_mode
     agg, first, last = {}, None, None
     for ev in prof.events():
         if ev.device_type != torch.autograd.DeviceType.CUDA:
@@ -333,8 +339,8 @@ def conv_roofline(model, B, H, pk, pk_kind, step_fn, N):
             "kernel": "conv_halo_kernel / conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit GEMM; bf16 U-Net + tf32 Gaussian "
                       "encoders), all launches of one training step",
             "how": "achieved = sum over the step's tcgen05 conv launches of 2*B*H*W*Cin*Cout*k*k / their summed device time "
-                   "inside ONE real training step (CUPTI kernel records via torch.profiler, programmatic dependent launch "
-                   "off for that step so durations do not overlap)",
+                   "inside ONE real training step (CUPTI kernel records via torch.profiler; programmatic dependent launch "
+                   "and the encoder side streams are off for that step so kernel durations do not overlap)",
             "conv_time_in_step_ms": conv_ms, "kernel_time_in_step_ms": total_ms, "profiled_step_span_ms": span_ms,
             "share_of_step": conv_ms / total_ms if total_ms else None,
             "conv_gflop_per_step": replay["conv_gflop_per_step"], "conv_launches_in_step": sum(v[0] for v in fam.values()),
