@@ -43,7 +43,8 @@ unsigned long long pub_launch_count(void);
 /* bring-up / A-B measurement knobs (tools/ only; never needed for correct results).
  *   "conv_halo" 0|1|2 : 3x3 tcgen05 convolutions through the per-tap TMA kernel (0), the halo kernel where it measured
  *                       faster (1, default) or wherever it is legal (2)
- *   "fcomb_fwd_mma" 0|1 : fcomb forward in bf16 mode with the f32 FMA kernel (0) or the tensor-core kernel (1, default)
+ *   "fcomb_fwd_mma" 0|1|2|3 : fcomb forward in bf16 mode with the f32 FMA kernel (0), the tensor-core kernels (1, default:
+ *                       bf16 hi + lo split for M <= 32, tf32 for larger ensembles), always tf32 (2), always the split (3)
  *   "wgrad_fused_bias" 0|1 : bias gradient from a separate column-sum pass over dy (0) or from the dy tiles the wgrad
  *                       kernel stages in shared memory anyway (1, default)
  *   "wgrad_box3" 0|1  : 3x3 weight gradient with nine tap boxes (0) or three (8+2) x 8 boxes + row-offset taps (1, default)

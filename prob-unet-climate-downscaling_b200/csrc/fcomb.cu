@@ -705,6 +705,132 @@ __global__ void __launch_bounds__(NT) fcomb_fwd_mma_kernel(FcombDev a, float* __
   }
 }
 
+// ---- forward for LARGE ensembles (M > 32: prior-ensemble sampling, BASELINE configs[3]) on tf32 warp-level MMAs.
+// The hi + lo split above costs three bf16 MMAs per product (30 per member and 16 pixels) plus the splitting
+// arithmetic; tf32 keeps 10 mantissa bits of both operands in ONE m16n8k8 MMA (20 per member and 16 pixels, no
+// splitting).  Operand rounding is 2^-11 relative -- 8x finer than plain bf16, whose 0.8 % CRPS shift is what ruled it
+// out (tests: output within 1e-3 of the f32 kernel, CRPS within 0.5 %).  The accumulator fragment of one layer becomes
+// the A fragment of the next WITHOUT data movement: an m16n8 accumulator holds columns (2t, 2t+1) of n-tile q, an
+// m16k8 A fragment wants k = (t, t+4) of k-step q -- so k-step q simply uses the permuted K order
+// (t -> column 8q + 2t, t + 4 -> column 8q + 2t + 1) and the B fragments are loaded with the same permutation (one
+// 8-byte load of two adjacent weights).  All layer-1 / layer-2 B fragments (40 registers) stay in registers over the
+// member loop.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma1688_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+constexpr int WPT = F + 8;   // f32 row pitch of the tf32 weight matrices: 8-byte B-fragment loads hit 64 distinct words
+struct FcombFwdTf32Smem {
+  float w0[F][WPT];    // [j][i]  feature half of layer 0, tf32-rounded
+  float w1[F][WPT];    // [k][j]
+  float w2[8][WPT];    // [c][k], rows >= CO zero
+  float b1[F];
+  float b2[4];
+};
+
+__global__ void __launch_bounds__(NT) fcomb_fwd_tf32_kernel(FcombDev a, float* __restrict__ out) {
+  __shared__ __align__(16) FcombFwdTf32Smem s;
+  extern __shared__ float dyn[];  // zbs[M][F]
+  float* zbs = dyn;
+  const int b = blockIdx.y, HW = a.H * a.W, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < F * F; i += NT) {
+    const int r = i / F, c = i % F;
+    s.w1[r][c] = __uint_as_float(to_tf32(a.w1[i]));
+    s.w0[r][c] = __uint_as_float(to_tf32(a.w0[r * (F + a.L) + c]));
+  }
+  for (int i = tid; i < 8 * F; i += NT) {
+    const int c = i / F, k = i % F;
+    s.w2[c][k] = c < CO ? __uint_as_float(to_tf32(a.w2[c * F + k])) : 0.f;
+  }
+  if (tid < F) s.b1[tid] = a.b1[tid];
+  if (tid < 4) s.b2[tid] = tid < CO ? a.b2[tid] : 0.f;
+  for (int i = tid; i < a.M * F; i += NT) zbs[i] = a.zb[((int64_t)(i / F) * a.B + b) * F + i % F];
+  __syncthreads();
+  // B fragments in the permuted K order: k-step q, n-tile q2 -> (W[8 q2 + g][8 q + 2t], W[8 q2 + g][8 q + 2t + 1])
+  uint2 bw1[4][4], bw2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int q2 = 0; q2 < 4; ++q2) bw1[q][q2] = *reinterpret_cast<const uint2*>(&s.w1[8 * q2 + g][8 * q + 2 * t]);
+    bw2[q] = *reinterpret_cast<const uint2*>(&s.w2[g][8 * q + 2 * t]);
+  }
+  float bb[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { bb[q][0] = s.b1[8 * q + 2 * t]; bb[q][1] = s.b1[8 * q + 2 * t + 1]; }
+  const float bo0 = s.b2[2 * t < CO ? 2 * t : 3], bo1 = s.b2[2 * t + 1 < CO ? 2 * t + 1 : 3];
+  const int ntile = (HW + 15) / 16;
+  for (int tile = blockIdx.x * 4 + warp; tile < ntile; tile += gridDim.x * 4) {
+    const int p0 = tile * 16 + g, p1 = p0 + 8;
+    const bool v0 = p0 < HW, v1 = p1 < HW;
+    // ---- base[px][j] = sum_i f[px][i] W0f[j][i]: the features are bf16 (exact in tf32); same permuted K order
+    float base[4][4];
+    {
+      const bf16* f0 = (const bf16*)a.feat + ((int64_t)b * HW + p0) * F;
+      const bf16* f1 = (const bf16*)a.feat + ((int64_t)b * HW + p1) * F;
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) base[q2][r] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t u0 = v0 ? *reinterpret_cast<const uint32_t*>(f0 + 8 * q + 2 * t) : 0u;   // columns 8q+2t, 8q+2t+1
+        const uint32_t u1 = v1 ? *reinterpret_cast<const uint32_t*>(f1 + 8 * q + 2 * t) : 0u;
+        const uint32_t a0 = u0 << 16, a2 = u0 & 0xFFFF0000u, a1 = u1 << 16, a3 = u1 & 0xFFFF0000u;
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) {
+          const uint2 w = *reinterpret_cast<const uint2*>(&s.w0[8 * q2 + g][8 * q + 2 * t]);
+          mma1688_tf32(base[q2], a0, a1, a2, a3, w.x, w.y);
+        }
+      }
+    }
+    for (int m = 0; m < a.M; ++m) {
+      // ---- h1 = relu(base + zb[m]) as the A fragments of the four k-steps
+      uint32_t h1a[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 z = *reinterpret_cast<const float2*>(&zbs[m * F + 8 * q + 2 * t]);
+        h1a[q][0] = to_tf32(fmaxf(base[q][0] + z.x, 0.f));   // (row g,   col 2t)   -> k = t
+        h1a[q][2] = to_tf32(fmaxf(base[q][1] + z.y, 0.f));   // (row g,   col 2t+1) -> k = t + 4
+        h1a[q][1] = to_tf32(fmaxf(base[q][2] + z.x, 0.f));   // (row g+8, col 2t)
+        h1a[q][3] = to_tf32(fmaxf(base[q][3] + z.y, 0.f));   // (row g+8, col 2t+1)
+      }
+      // ---- h2 = relu(h1 W1^T + b1)
+      uint32_t h2a[4][4];
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        float acc[4] = {bb[q2][0], bb[q2][1], bb[q2][0], bb[q2][1]};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          mma1688_tf32(acc, h1a[q][0], h1a[q][1], h1a[q][2], h1a[q][3], bw1[q][q2].x, bw1[q][q2].y);
+        h2a[q2][0] = to_tf32(fmaxf(acc[0], 0.f)); h2a[q2][2] = to_tf32(fmaxf(acc[1], 0.f));
+        h2a[q2][1] = to_tf32(fmaxf(acc[2], 0.f)); h2a[q2][3] = to_tf32(fmaxf(acc[3], 0.f));
+      }
+      // ---- out = h2 W2^T + b2
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mma1688_tf32(o, h2a[q][0], h2a[q][1], h2a[q][2], h2a[q][3], bw2[q].x, bw2[q].y);
+      float* op = out + (((int64_t)b * a.M + m) * CO) * HW;
+      if (2 * t < CO) {
+        if (v0) op[(int64_t)(2 * t) * HW + p0] = o[0] + bo0;
+        if (v1) op[(int64_t)(2 * t) * HW + p1] = o[2] + bo0;
+      }
+      if (2 * t + 1 < CO) {
+        if (v0) op[(int64_t)(2 * t + 1) * HW + p0] = o[1] + bo1;
+        if (v1) op[(int64_t)(2 * t + 1) * HW + p1] = o[3] + bo1;
+      }
+    }
+  }
+}
+
 // final reduction over CTAs (fixed order) + the latent-half gradients
 __global__ void fcomb_bwd_final_kernel(const float* __restrict__ part, int nx, int B, int M, int L,
                                        const float* __restrict__ z, const float* __restrict__ w0,
@@ -816,13 +942,26 @@ int pub_fcomb_forward(const pub_fcomb_args* a, void* ws, size_t ws_bytes, pub_st
   PUB_LAUNCH_CHECK();
   const FcombDev d = make_dev(a, zb);
   const int HW = a->H * a->W;
-  if (!a->feat_nchw && a->dtype == PUB_BF16 && g_opt_fcomb_fwd_mma) {
+  if (!a->feat_nchw && a->dtype == PUB_BF16 && g_opt_fcomb_fwd_mma) {   // 1 auto, 2 tf32, 3 split
     const size_t dynm = (size_t)a->M * F * 4;
     int gxm = cdiv(4 * num_sms(), a->B);
     const int ntile = cdiv(HW, 64);      // 4 warps x 16 pixels per CTA iteration
     if (gxm > ntile) gxm = ntile;
     if (gxm < 1) gxm = 1;
-    fcomb_fwd_mma_kernel<<<dim3(gxm, a->B), NT, dynm, st>>>(d, a->out);
+    // M > 32 (ensemble sampling): one tf32 MMA per product; M <= 32 (the ELBO's ensembles): bf16 hi + lo split.
+    // pub_debug_option("fcomb_fwd_mma", 2 / 3) forces the tf32 / the split kernel.
+    const bool tf32 = g_opt_fcomb_fwd_mma == 2 || (g_opt_fcomb_fwd_mma == 1 && a->M > 32);
+    if (tf32) {
+      static bool attr_t = false;
+      if (!attr_t) {
+        PUB_CUDA(cudaFuncSetAttribute(fcomb_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_t = true;
+      }
+      PUB_REQUIRE(dynm <= 64 * 1024, "pub_fcomb_forward: M too large for the tf32 kernel's latent-bias table");
+      fcomb_fwd_tf32_kernel<<<dim3(gxm, a->B), NT, dynm, st>>>(d, a->out);
+    } else {
+      fcomb_fwd_mma_kernel<<<dim3(gxm, a->B), NT, dynm, st>>>(d, a->out);
+    }
     PUB_LAUNCH_CHECK();
     return 0;
   }
