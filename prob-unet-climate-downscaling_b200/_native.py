@@ -355,12 +355,22 @@ class _WorkspacePool:
     MAX_FREE = 6          # buffers kept per device; beyond that the smallest ones are released to the allocator
 
     def __init__(self):
-        self.free = {}    # device -> list of free buffers, most recently returned last
+        self.free = {}    # (device, stream) -> list of free buffers, most recently returned last
+
+    @staticmethod
+    def _key(device):
+        # Buffers are handed back when the work that uses them has been ENQUEUED, not finished: reuse is only ordered
+        # on the same stream, so every stream has its own free list (the Gaussian encoders run on side streams, an
+        # ensemble pipeline may alternate streams per field batch).
+        device = torch.device(device)
+        if device.type != "cuda":
+            return device
+        return (device, torch.cuda.current_stream(device).cuda_stream)
 
     def take(self, nbytes, device):
         """Best fit: the smallest free buffer that is large enough (a ragged last batch or a validation batch reuses
         the training step's workspace instead of pinning another multi-GB block)."""
-        lst = self.free.get(device, [])
+        lst = self.free.get(self._key(device), [])
         best = None
         for i, b in enumerate(lst):
             if b.numel() >= nbytes and (best is None or b.numel() < lst[best].numel()):
@@ -372,7 +382,7 @@ class _WorkspacePool:
     def give(self, ws):
         if ws is None:
             return
-        lst = self.free.setdefault(ws.device, [])
+        lst = self.free.setdefault(self._key(ws.device), [])
         lst.append(ws)
         while len(lst) > self.MAX_FREE:
             lst.pop(min(range(len(lst)), key=lambda i: lst[i].numel()))

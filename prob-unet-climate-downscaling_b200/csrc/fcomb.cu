@@ -352,7 +352,8 @@ struct __align__(16) FcombMmaSmem {
   float red[2 * F * F + CO * F + F + 4];
 };
 
-__global__ void __launch_bounds__(NT, 2) fcomb_bwd_mma_kernel(FcombDev a, const float* __restrict__ dout,
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) fcomb_bwd_mma_kernel(FcombDev a, const float* __restrict__ dout,
                                                                bf16* __restrict__ dfeat, float* __restrict__ part) {
   __shared__ FcombMmaSmem s;
   extern __shared__ float dyn[];  // zbs[M][F] | Sacc[4 warps][M][F]
@@ -995,10 +996,12 @@ int pub_fcomb_backward(const pub_fcomb_args* a, const float* dout, void* dfeat, 
     const size_t dynm = (size_t)a->M * F * 4 * 5;
     static bool attr_m = false;
     if (!attr_m) {
-      PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      PUB_CUDA(cudaFuncSetAttribute(fcomb_bwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       attr_m = true;
     }
-    fcomb_bwd_mma_kernel<<<grid, NT, dynm, st>>>(d, dout, (bf16*)dfeat, part);
+    if (g_opt_fcomb_bwd_occ >= 3 && dynm <= 40 * 1024) fcomb_bwd_mma_kernel<3><<<grid, NT, dynm, st>>>(d, dout, (bf16*)dfeat, part);
+    else fcomb_bwd_mma_kernel<2><<<grid, NT, dynm, st>>>(d, dout, (bf16*)dfeat, part);
     PUB_LAUNCH_CHECK();
     fcomb_bwd_final_kernel<<<16, 256, 0, st>>>(part, gx, a->B, a->M, a->L, a->z, a->w0, dz, dw0, db0, dw1, db1, dw2, db2, Stot);
     PUB_LAUNCH_CHECK();

@@ -194,8 +194,8 @@ __device__ __forceinline__ float softplus_sel(float x, float c) {
   return x > 20.f ? x : sp;
 }
 
-template <int NP>
-__global__ void __launch_bounds__(128, 3) metrics_kernel(const float* __restrict__ preds, const float* __restrict__ hr,
+template <int NP, int MINB>
+__global__ void __launch_bounds__(128, MINB) metrics_kernel(const float* __restrict__ preds, const float* __restrict__ hr,
                                                          const float* __restrict__ lrinterp, const float* __restrict__ std_hr,
                                                          int transform, int M, int C, int HW, float* __restrict__ part) {
   __shared__ float red[4];
@@ -417,11 +417,12 @@ int pub_ensemble_metrics(const float* preds, const float* hr, const float* lrint
   float* part = (float*)ws;
   dim3 grid(nblk, C, T);
   cudaStream_t st = (cudaStream_t)s;
-  if (M <= 8) metrics_kernel<8><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
-  else if (M <= 16) metrics_kernel<16><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
-  else if (M <= 32) metrics_kernel<32><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
-  else if (M <= 64) metrics_kernel<64><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
-  else metrics_kernel<128><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  if (M <= 8) metrics_kernel<8, 3><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (M <= 16) metrics_kernel<16, 3><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (M <= 32) metrics_kernel<32, 3><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (M <= 64) metrics_kernel<64, 3><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else if (g_opt_metrics_occ >= 4) metrics_kernel<128, 4><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
+  else metrics_kernel<128, 3><<<grid, 128, 0, st>>>(preds, hr, lrinterp, std_hr, transform, M, C, HW, part);
   PUB_LAUNCH_CHECK();
   metrics_final_kernel<<<cdiv(T * C, 128), 128, 0, (cudaStream_t)s>>>(part, nblk, HW, T * C, crps_tc, mae_tc);
   PUB_LAUNCH_CHECK();

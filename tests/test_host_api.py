@@ -81,7 +81,7 @@ def test_workspace_pool_reuses_the_best_fit_and_stays_bounded():
     assert pool.take(2000, dev).numel() == 2000        # nothing fits: allocate
     for n in range(10):
         pool.give(torch.empty(10 + n, dtype=torch.uint8))
-    assert len(pool.free[dev]) == pool.MAX_FREE and min(b.numel() for b in pool.free[dev]) == 14
+    assert len(pool.free[dev]) == pool.MAX_FREE and min(b.numel() for b in pool.free[dev]) == 14   # CPU: keyed by device
     pool.clear()
     assert not pool.free
 
