@@ -431,31 +431,11 @@ def ensemble_measure(args, model, dist, rank, world, N, fields, steps, warmup):
     scores = torch.empty(T, 6, device="cuda")
 
     nstreams = max(1, int(os.environ.get("PROBUNET_B200_ENSEMBLE_STREAMS", "2")))
-    streams = [torch.cuda.Stream() for _ in range(nstreams)] if nstreams > 1 else []
-
-    def one_batch(src, h2d, sl):
-        if h2d:
-            x, hr, li = (src[k][sl].cuda(non_blocking=True) for k in ("x", "hr", "li"))
-        else:
-            x, hr, li = (src[k][sl] for k in ("x", "hr", "li"))
-        crps, mae = model.sample_and_score(x, Mm, hr, li, sd_)
-        scores[sl, :3], scores[sl, 3:] = crps, mae
 
     def one_pass(src, h2d):
-        # field batches are independent: alternate them over two streams so that the latency-bound per-member kernels
-        # (fcomb, the sorting CRPS kernel: few resident warps) of one batch overlap the U-Net of the next
-        cur = torch.cuda.current_stream()
-        for s_ in streams:
-            s_.wait_stream(cur)
-        for k, i in enumerate(range(0, T, FB)):
-            sl = slice(i, min(T, i + FB))
-            if streams:
-                with torch.cuda.stream(streams[k % nstreams]):
-                    one_batch(src, h2d, sl)
-            else:
-                one_batch(src, h2d, sl)
-        for s_ in streams:
-            cur.wait_stream(s_)
+        # the public call: field batches alternate over two streams (host fields are copied per batch on its stream)
+        crps, mae = model.sample_and_score(src["x"], Mm, src["hr"], src["li"], sd_, field_batch=FB, streams=nstreams)
+        scores[:, :3], scores[:, 3:] = crps, mae
         return gather_scores(scores, [T] * world) if world > 1 else scores        # the only collective
 
     def barrier():

@@ -215,13 +215,41 @@ class ProbabilisticUNet(nn.Module):
         return _native.fcomb_apply(self.fcomb, fpix, z, nhwc=True)[:, :, :, 0, :]
 
     @torch.no_grad()
-    def sample_and_score(self, x, n, hr_real, lrinterp, std_hr, eps=None):
+    def sample_and_score(self, x, n, hr_real, lrinterp, std_hr, eps=None, field_batch=None, streams=2):
         """Additive API for the ensemble evaluation of results.ipynb cells 6, 11, 12: n prior members per field
         (``sample``), ``residual_to_hr`` + ``invert_transfo_3vars`` (src/climex_utils.py:277-285, results.ipynb cell 2)
-        and ``metrics.crps_over_groundtruth`` / ``compute_mae`` (src/metrics.py:11-71) against ``hr_real`` [B,3,H,W]
-        (real units) -> (crps [B,3], mae [B,3]) on the device; the members never leave the GPU."""
-        ens = self.sample(x, n, eps=eps)
-        return _native.ensemble_metrics(ens, hr_real, lrinterp, std_hr)
+        and ``metrics.crps_over_groundtruth`` / ``compute_mae`` (src/metrics.py:11-71) against ``hr_real`` [T,3,H,W]
+        (real units) -> (crps [T,3], mae [T,3]) on the device; the members never leave the GPU.
+
+        ``field_batch``: score the T fields in batches of that many (x / hr_real / lrinterp may then be pinned HOST
+        tensors: each batch is copied on its own stream).  Batches are independent, so they alternate over ``streams``
+        CUDA streams: the per-member kernels of one batch (fcomb, the sorting CRPS kernel -- few resident warps each)
+        overlap the U-Net of the next (539 k -> 604 k members/s on one B200, profiles/r02_ensemble_streams_ab.txt)."""
+        T = x.shape[0]
+        dev = std_hr.device
+        if field_batch is None or T <= field_batch:
+            x, hr_real, lrinterp = (v.to(dev, non_blocking=True) for v in (x, hr_real, lrinterp))
+            ens = self.sample(x, n, eps=eps)
+            return _native.ensemble_metrics(ens, hr_real, lrinterp, std_hr)
+        if eps is not None:
+            raise ValueError("eps injection is per call: pass field_batch=None")
+        crps = torch.empty(T, self.num_classes, device=dev, dtype=torch.float32)
+        mae = torch.empty_like(crps)
+        nst = max(1, int(streams))
+        if getattr(self, "_batch_streams", None) is None or len(self._batch_streams) != nst:
+            self._batch_streams = [torch.cuda.Stream(dev) for _ in range(nst)]
+        cur = torch.cuda.current_stream(dev)
+        for s_ in self._batch_streams:
+            s_.wait_stream(cur)
+        for k, i in enumerate(range(0, T, field_batch)):
+            sl = slice(i, min(T, i + field_batch))
+            with torch.cuda.stream(self._batch_streams[k % nst]):
+                xb, hb, lb = (v[sl].to(dev, non_blocking=True) for v in (x, hr_real, lrinterp))
+                c, a = _native.ensemble_metrics(self.sample(xb, n), hb, lb, std_hr)
+                crps[sl], mae[sl] = c, a
+        for s_ in self._batch_streams:
+            cur.wait_stream(s_)
+        return crps, mae
 
     def elbo(self, x, target, t=None, M=None, alpha=0.95, alpha_w=0.007, beta_w=0.048, lam_w=0.0, eps=None):
         """ELBO = beta_0*recon + beta_1*KL(q||p) [+ beta_2*KL(q||N(0,I))]; the reconstruction
