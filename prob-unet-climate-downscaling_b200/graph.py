@@ -13,10 +13,18 @@ The ELBO's reconstruction terms are returned as device tensors (model.sync_scala
 would be a host sync and cannot be captured; read them every N steps instead (de-synced logging).
 """
 import ctypes as C
+import os
+import sys
+import time
 
 import torch
 
 import _native as N
+
+
+def _dbg(msg):
+    if os.environ.get("PROBUNET_B200_GRAPH_DEBUG"):
+        print(f"[graph {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
 class GraphedTrainStep:
@@ -53,12 +61,15 @@ class GraphedTrainStep:
         # communicators -- nothing of that may happen for the first time during capture
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
-            for _ in range(max(1, warmup)):
+            for i in range(max(1, warmup)):
                 self._body()
+                _dbg(f"warm-up step {i} enqueued")
         torch.cuda.current_stream().wait_stream(self.stream)
         torch.cuda.synchronize()
+        _dbg("warm-up done")
         self.graph = None
         self.recapture()
+        _dbg(f"captured {self.launches_per_step} launches")
 
     def _drop_graph_references(self):
         import gc
@@ -97,6 +108,7 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        _dbg("replay enqueued")
         return self.out
 
     def close(self):
