@@ -149,7 +149,8 @@ class ProbabilisticUNet(nn.Module):
     def _encoders_beside_unet(self, x, target):
         import os
         mode = int(os.environ.get("PROBUNET_B200_ENCODER_STREAM", "3"))
-        if mode == 0 or not x.is_cuda or torch.cuda.is_current_stream_capturing():
+        if mode == 0 or not x.is_cuda or (torch.cuda.is_current_stream_capturing()
+                                          and os.environ.get("PROBUNET_B200_GRAPH_STREAMS", "1") == "0"):
             feat = self.unet(x, _nhwc_out=True)
             prior = self.prior(x)
             post = self.posterior(x, target) if target is not None else None
