@@ -801,6 +801,34 @@ def run_b200(args):
             line["roofline_detail_top"] = sorted(detail, key=lambda d: -d["us"] * d["count"])[:8]
         except Exception as ex:  # never lose the headline line
             line["roofline"] = {"error": repr(ex)}
+    if not args.no_aux and world == 1:
+        # ---- the same step captured once in a CUDA graph and replayed (graph.GraphedTrainStep; single GPU only here:
+        # the multi-GPU capture with NCCL nodes is validated at 16 samples per GPU)
+        try:
+            from graph import GraphedTrainStep
+            loss = None               # a live loss keeps the eager steps' autograd graph (bound to the default stream) alive
+            gstep = GraphedTrainStep(model, opt, x, y, M=M if args.loss in ("afcrps", "crps") else None, warmup=2)
+            for _ in range(3):
+                gstep(x, y)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            h0 = time.perf_counter()
+            for _ in range(args.steps):
+                gout = gstep(x, y)
+            host_ms = 1e3 * (time.perf_counter() - h0) / args.steps
+            g1.record()
+            torch.cuda.synchronize()
+            tg = g0.elapsed_time(g1) * 1e-3
+            line["cuda_graph"] = {"samples_per_s": B * args.steps / tg, "ms_per_step": 1e3 * tg / args.steps,
+                                  "host_enqueue_ms_per_step": host_ms, "launches_per_step": gstep.launches_per_step,
+                                  "what": "graph.GraphedTrainStep: elbo + backward + fused AdamW captured once (encoder side "
+                                          "streams included), replayed per step; device-side step counter and random salt; "
+                                          "ELBO scalars stay on the device"}
+            gstep.close()
+            del gstep, gout
+        except Exception as ex:
+            line["cuda_graph"] = {"error": repr(ex)[:300]}
     if not args.no_aux:
         # ---- second half of BASELINE.json's metric: ensemble members/s (configs[3]), every rank its own fields, one
         # final gather -- a short run here; `--workload ensemble` is the full-length line
