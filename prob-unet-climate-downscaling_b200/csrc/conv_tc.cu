@@ -789,6 +789,7 @@ struct TcWgradArgs {
   int stages;
   float* part;            // [split][tap][cout][cin] f32
   int box3;               // 3x3, 8x8 patches: x as one (8+2) x (8+2) halo box, taps as row offsets (see wgrad_tc_kernel)
+  int swap;               // box3 with cout <= 64: operand roles swapped, D[(dy, ci)][co] (see wgrad_tc_kernel)
   float* bias_part;       // [split][cout] column sums of dy (bias gradient partials) or nullptr
 };
 
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   const uint32_t B_BYTES = box3 ? WG_BOX_BYTES : (uint32_t)a.taps * WG_GROUP_BYTES;
   const uint32_t STAGE_BYTES = WG_A_BYTES + B_BYTES;
   uint32_t ncols = 32;
-  while ((int)ncols < a.taps * 32) ncols <<= 1;
+  while ((int)ncols < (a.swap ? 3 * a.cout : a.taps * 32)) ncols <<= 1;
 
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 128, split = blockIdx.z;
   const int cin = a.c0 + a.c1;
@@ -897,6 +898,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     const uint32_t idesc1 = make_idesc(128, n1 * 32, 1, 1, fmt);
     const uint32_t idesc2 = n2 ? make_idesc(128, n2 * 32, 1, 1, fmt) : 0u;
     const uint32_t idesc3 = make_idesc(128, 96, 1, 1, fmt);
+    const uint32_t idesc_sw = make_idesc(128, a.cout, 1, 1, fmt);
     const uint64_t adesc0 = make_desc(base, WG_GROUP_BYTES, SBO_WG, LAYOUT);
     const uint64_t bdesc0 = make_desc(base + WG_A_BYTES, WG_GROUP_BYTES, SBO_WG, LAYOUT);
     // box3: K groups (patch rows) and N groups (vertical taps) are both 10 rows apart; in the tf32 layout an atom holds
@@ -910,7 +912,23 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
       tc_fence_after();
       const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * sstep);
       if (elect_one()) {
-        if (box3) {
+        if (a.swap) {
+          // Cout <= 64: with dy as the M operand three quarters (half) of every M = 128 instruction are padding, and an
+          // MMA costs max(M, 128) * N / 256 tensor cycles whatever M is (ncu: tensor pipe 63 % busy at 32 -> 32).
+          // Swapped: A = the x halo box (M = 4 groups of 32 input channels: the three vertical taps + one group of
+          // padding rows nobody reads back), B = dy (N = Cout): N / 2 = 16 or 32 cycles per MMA instead of 48.
+          // D[(dy, ci)][co] per dx at TMEM column dx * Cout; the descriptors are the same two, exchanged.
+          const uint64_t xd = bdesc3 + (uint64_t)((uint32_t)stage * sstep);
+#pragma unroll
+          for (int k = 0; k < WG_P / KROWS; ++k) {
+            const uint32_t acc = (!first || k != 0) ? 1u : 0u;
+            const uint64_t ka = (uint64_t)(k * (KSTEP_BYTES >> 4));
+            const uint64_t kb = (uint64_t)(k * ((KROWS / 8) * 10 * ROW >> 4));
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              umma<ES>(tmem_base + (uint32_t)(dx * a.cout), xd + kb + (uint64_t)((dx - 1) * (int)(ROW >> 4)), ad + ka, idesc_sw, acc);
+          }
+        } else if (box3) {
           const uint64_t bd = bdesc3 + (uint64_t)((uint32_t)stage * sstep);
 #pragma unroll
           for (int k = 0; k < WG_P / KROWS; ++k) {
@@ -996,6 +1014,23 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
     }
     mbar_wait(accbar, 0);
     tc_fence_after();
+    if (a.swap) {
+      // TMEM lane = (vertical tap q, input channel ci0 + lane); columns dx * Cout + co.  For a fixed co the 32 lanes
+      // of a warp write 32 consecutive ci: coalesced 128-byte stores.  Lane quarter 3 holds the padding group.
+      if (q < 3) {
+        const int ci = ci0 + lane;
+        for (int dx = 0; dx < 3; ++dx) {
+          const int tap = q * 3 + dx;
+          for (int cb = 0; cb < a.cout; cb += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(dx * a.cout + cb), r);
+            float* o = a.part + (((int64_t)split * a.taps + tap) * a.cout + cb) * cin + ci;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[(int64_t)j * cin] = has_work ? __uint_as_float(r[j]) : 0.f;
+          }
+        }
+      }
+    } else {
     for (int tap = 0; tap < a.taps; ++tap) {
       uint32_t r[32];
       // box3 keeps the accumulators ordered [dx][dy]
@@ -1011,6 +1046,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
           *reinterpret_cast<float4*>(o + j) = v;
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -1343,6 +1379,7 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   a.B = p.B; a.H = p.H; a.W = p.W; a.TW = pl.tw; a.TH = pl.th;
   a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
   a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages; a.box3 = pl.box3;
+  a.swap = (pl.box3 && p.cout <= 64 && g_opt_wgrad_swap) ? 1 : 0;
   a.part = (float*)ws;
   float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * taps * p.cout * cin * sizeof(float), 256));
   a.bias_part = (p.dbias && g_opt_wgrad_fused_bias) ? bpart : nullptr;
