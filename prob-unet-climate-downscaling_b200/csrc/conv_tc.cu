@@ -1379,7 +1379,7 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   a.B = p.B; a.H = p.H; a.W = p.W; a.TW = pl.tw; a.TH = pl.th;
   a.tiles_x = pl.tiles_x; a.tiles_y = pl.tiles_y; a.tiles_total = pl.tiles_total;
   a.tiles_per_split = pl.tiles_per_split; a.stages = pl.stages; a.box3 = pl.box3;
-  a.swap = (pl.box3 && p.cout <= 64 && g_opt_wgrad_swap) ? 1 : 0;
+  a.swap = (pl.box3 && es == 2 && p.cout <= 64 && g_opt_wgrad_swap) ? 1 : 0;   // bf16 only: the tf32 MN-major atom layout (BASE32B) did not survive the exchange
   a.part = (float*)ws;
   float* bpart = (float*)((char*)ws + align_up((size_t)pl.nsplit * taps * p.cout * cin * sizeof(float), 256));
   a.bias_part = (p.dbias && g_opt_wgrad_fused_bias) ? bpart : nullptr;
