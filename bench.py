@@ -781,6 +781,10 @@ def run_b200(args):
     }
     if args.graph:
         args.no_aux = True          # the auxiliary legs re-use the eager step; run them without --graph
+    # The timed regions are over.  The auxiliary legs below run training steps on rank 0 ONLY (in-step roofline, CUDA
+    # graph): with the synchronizer still installed those steps would issue NCCL all-reduces no other rank joins.
+    sync.wait_all()
+    GradSynchronizer.uninstall()
     if rank == 0 and not args.no_aux:
         # ---- roofline of the dominant kernel family, measured live
         try:
@@ -833,7 +837,6 @@ def run_b200(args):
         # ---- second half of BASELINE.json's metric: ensemble members/s (configs[3]), every rank its own fields, one
         # final gather -- a short run here; `--workload ensemble` is the full-length line
         try:
-            sync.uninstall()
             model.eval()
             ens = ensemble_measure(args, model, dist, rank, world, N, fields=min(args.fields, 128), steps=3, warmup=1)
             if rank == 0:
