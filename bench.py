@@ -234,13 +234,15 @@ def conv_inventory(model, B, H):
             skips.append(c)
     conv3(c, model.unet.out_channels, r)
     import _native as N
-    enc_dt = {N.TF32: "tf32", N.BF16: "bf16", N.F32: "f32"}[N.resolve_encoder_dtype(model.unet.compute_dtype)]
+    enc = N.resolve_encoder_dtype(model.unet.compute_dtype)
+    enc_dt = {N.TF32: "tf32", N.TF32_BF16S0: "tf32", N.BF16: "bf16", N.F32: "f32"}[enc]
     for encmod in (model.prior, model.posterior):
         rr, cc = H, encmod.input_channels
         for i, nf in enumerate(encmod.num_filters):
             if i: rr //= 2
             for k in range(3):
-                conv3(cc, nf, rr, dgrad=not (i == 0 and k == 0), dt=enc_dt); cc = nf
+                dt = "bf16" if (enc == N.TF32_BF16S0 and i == 0 and len(encmod.num_filters) > 1) else enc_dt
+                conv3(cc, nf, rr, dgrad=not (i == 0 and k == 0), dt=dt); cc = nf
     return inv
 
 

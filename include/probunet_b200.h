@@ -31,6 +31,9 @@ typedef struct CUstream_st* pub_stream_t; /* == cudaStream_t */
 #define PUB_F32 0
 #define PUB_BF16 1
 #define PUB_TF32 2 /* f32 storage whose values are rounded to tf32; convolutions use tcgen05 kind::tf32 */
+/* pub_encoder_create only: PUB_TF32 with the full-resolution stage (its three convs, their gradients) in PUB_BF16; the
+ * first max-pool converts.  Rounding in that stage barely moves log sigma, rounding behind it does. */
+#define PUB_TF32_BF16S0 3
 
 #define PUB_BACKEND_AUTO 0
 #define PUB_BACKEND_SIMT 1    /* fp32-FMA implicit GEMM (parity path, any shape)          */

@@ -15,9 +15,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libprobunet_b200.so")
 _lib = None
 
-F32, BF16, TF32 = 0, 1, 2
+F32, BF16, TF32, TF32_BF16S0 = 0, 1, 2, 3
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
-_DTYPE_NAMES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16, "tf32": TF32}
+_DTYPE_NAMES = {"fp32": F32, "float32": F32, "f32": F32, "bf16": BF16, "bfloat16": BF16, "tf32": TF32,
+                "tf32_bf16s0": TF32_BF16S0}
 _TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, TF32: torch.float32}
 
 # process-wide knobs (env vars so that the reference's drivers stay unchanged)
@@ -125,7 +126,9 @@ def resolve_dtype(name):
 def resolve_encoder_dtype(name):
     """Precision of the two Gaussian encoders.  Their log-sigma head feeds exp(): an absolute error of d in
     log sigma is a RELATIVE error d in sigma and in z = mu + sigma*eps, so with the U-Net in bf16 the encoders run
-    one notch higher (tf32 tensor cores, f32 storage) unless PROBUNET_B200_ENCODER_DTYPE overrides it."""
+    one notch higher (tf32 tensor cores, f32 storage).  PROBUNET_B200_ENCODER_DTYPE (fp32 | tf32 | tf32_bf16s0 |
+    bf16) overrides it; tf32_bf16s0 keeps only the full-resolution first stage in bf16 (forward error 2.5x tf32's, 1 %
+    faster, noisier first-stage gradients: DESIGN.md, precision policy)."""
     dt = resolve_dtype(name)
     env = os.environ.get("PROBUNET_B200_ENCODER_DTYPE")
     if env:

@@ -19,7 +19,6 @@ int g_opt_pdl = 1;
 int g_opt_gn_fuse = 1;
 int g_opt_metrics_occ = 3;
 int g_opt_wgrad_swap = 1;
-int g_opt_wgrad_rows128 = 0;
 int g_opt_fcomb_bwd_occ = 2;
 cudaStream_t g_pack_stream = nullptr;
 unsigned long long g_since_pack = 0;
@@ -111,7 +110,6 @@ int pub_debug_option(const char* name, int value) {
   if (strcmp(name, "gn_fuse") == 0) { g_opt_gn_fuse = value; return 0; }
   if (strcmp(name, "metrics_occ") == 0) { g_opt_metrics_occ = value; return 0; }
   if (strcmp(name, "wgrad_swap") == 0) { g_opt_wgrad_swap = value; return 0; }
-  if (strcmp(name, "wgrad_rows128") == 0) { g_opt_wgrad_rows128 = value; return 0; }
   if (strcmp(name, "fcomb_bwd_occ") == 0) { g_opt_fcomb_bwd_occ = value; return 0; }
   set_error("pub_debug_option: unknown option '%s'", name);
   return -1;

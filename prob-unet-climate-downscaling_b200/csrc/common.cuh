@@ -40,7 +40,6 @@ extern int g_opt_gn_fuse;  // GroupNorm work fused into the halo conv epilogues:
 // pub_advance_counters (a graph replays the same kernel ARGUMENTS every step, so per-step randomness has to come from
 // device memory).  nullptr (default): unused, the (seed, offset) arguments alone decide -- what the parity tests run.
 extern int g_opt_wgrad_swap;      // 1 (default): 3x3 weight gradients with Cout <= 64 put the x halo on the M side (see wgrad_tc_kernel)
-extern int g_opt_wgrad_rows128;   // 1: bf16 3x3 weight gradients with all channel counts % 64 == 0 use the 128-byte-row kernel (default 0: measured slower)
 extern int g_opt_metrics_occ;     // CTAs per SM the ensemble metric kernel is compiled for: 3 (168 registers) or 4 (128, some spills)
 extern int g_opt_fcomb_bwd_occ;   // CTAs per SM of fcomb_bwd_mma_kernel: 2 (237 registers) or 3 (168)
 extern const uint32_t* g_seed_salt;

@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   // Every LANE arrives, after its own loads: the lanes of a warp can leave the polling loop of mbar_wait in different
   // iterations, ptxas places no reconvergence point after it (and drops a __syncwarp() there), so a lane-0-only
   // arrive released the stage while other lanes had not read it yet -- seen as run-to-run differences of one warp's
-  // 16 bias channels when another grid kept the SMs busy (tools/wgrad128_race.py).
+  // 16 bias channels when another grid kept the SMs busy (profiles/r02_wgrad_rows128.txt, tools/wgrad_race.py).
   const bool do_bias = a.bias_part != nullptr && blockIdx.x == 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, do_bias ? 1 + 4 * 32 : 1); }
@@ -1055,168 +1055,6 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, ncols);
-}
-
-// ------------------------------------------------------------------ weight gradient, 64-channel (128-byte) rows
-// wgrad_tc_kernel loads everything as 32-channel (64-byte) rows and is bound by the TMA's rate of ROWS (~4.7 cycles
-// each): 356 rows per 64-pixel K tile for a 32 ci x 128 co block.  For bf16 layers whose channel counts are multiples
-// of 64 this kernel gives a CTA a 64 ci x 64 co block -- the same ci x co product -- from ONE 64-channel halo box of x
-// (100 rows) and ONE 64-channel box of dy (64 rows): 164 rows of 128 bytes, the same bytes in 2.2x fewer rows.
-// Operand roles as in the swapped mode above: A = x halo, MN-major SWIZZLE_128B rows [halo pixel][64 ci]; an M = 128
-// tile is two 64-channel groups 10 rows apart (two vertical taps), so the three vertical taps take two M tiles (the
-// second half padded); B = dy [64 px][64 co], N = 64.  Per 16-pixel K step: 2 M tiles x 3 dx = 6 MMAs of 32 tensor
-// cycles.  D[(dy, ci)][co] for (M tile, dx) at TMEM column (mt * 3 + dx) * 64: 384 columns.
-constexpr uint32_t W128_ROW = 128;
-constexpr uint32_t W128_DY_BYTES = 64 * W128_ROW;                 // 8 x 8 pixels x 64 co
-constexpr uint32_t W128_X_BYTES = 112 * W128_ROW;                 // 100 halo rows + the rows the padding group touches
-constexpr uint32_t W128_STAGE = W128_DY_BYTES + W128_X_BYTES;     // 22 528 B, a multiple of 1024
-
-__global__ void __launch_bounds__(NTHREADS) wgrad_tc128_kernel(const __grid_constant__ CUtensorMap tmX0,
-                                                               const __grid_constant__ CUtensorMap tmX1,
-                                                               const __grid_constant__ CUtensorMap tmDY,
-                                                               TcWgradArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
-  __shared__ uint32_t tmem_slot;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]),
-                 accbar = smem_u32(&bars[2 * MAX_STAGES]);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, split = blockIdx.z;
-  const int cin = a.c0 + a.c1;
-  const int t_beg = split * a.tiles_per_split;
-  const int t_end = min(a.tiles_total, t_beg + a.tiles_per_split);
-  const bool do_bias = a.bias_part != nullptr && blockIdx.x == 0;
-  constexpr uint32_t NCOLS = 512;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, do_bias ? 1 + 4 * 32 : 1); }
-    mbar_init(accbar, 1);
-    fence_barrier_init();
-    prefetch_tmap(&tmX0);
-    prefetch_tmap(&tmDY);
-    if (a.c1) prefetch_tmap(&tmX1);
-  }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), NCOLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  pdl_enter();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const bool src1 = ci0 >= a.c0;
-      const CUtensorMap* tmX = src1 ? &tmX1 : &tmX0;
-      const int cx = src1 ? ci0 - a.c0 : ci0;
-      int stage = 0; uint32_t phase = 0;
-      for (int t = t_beg; t < t_end; ++t) {
-        int r = t;
-        const int tx = r % a.tiles_x; r /= a.tiles_x;
-        const int ty = r % a.tiles_y; r /= a.tiles_y;
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const uint32_t sa = base + stage * W128_STAGE;
-        mbar_expect_tx(full0 + 8 * stage, W128_DY_BYTES + (uint32_t)WG_BOXROWS * W128_ROW);
-        tma_load_4d(sa, &tmDY, full0 + 8 * stage, co0, tx * 8, ty * 8, r);
-        tma_load_4d(sa + W128_DY_BYTES, tmX, full0 + 8 * stage, cx, tx * 8 - 1, ty * 8 - 1, r);   // the patch + its halo
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(128, 64, 1, 1, 1u);
-    // x: M groups (vertical taps) and K atoms (patch rows) are both 10 halo rows apart; starts at halo row 1
-    // (dy = -1, dx = 0); dx adds -1 / 0 / +1 rows, the second M tile +20 rows
-    const uint64_t xdesc0 = make_desc(base + W128_DY_BYTES + W128_ROW, 10 * W128_ROW, 10 * W128_ROW, 2u);
-    const uint64_t ydesc0 = make_desc(base, W128_DY_BYTES, 8 * W128_ROW, 2u);
-    const uint32_t sstep = W128_STAGE >> 4;
-    int stage = 0; uint32_t phase = 0;
-    uint32_t first = 1;
-    for (int t = t_beg; t < t_end; ++t) {
-      mbar_wait(full0 + 8 * stage, phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t xd = xdesc0 + (uint64_t)((uint32_t)stage * sstep);
-        const uint64_t yd = ydesc0 + (uint64_t)((uint32_t)stage * sstep);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {                       // 16 pixels = two patch rows per K step
-          const uint32_t acc = (!first || k != 0) ? 1u : 0u;
-          const uint64_t ky = (uint64_t)(k * ((16 * W128_ROW) >> 4));
-          const uint64_t kx = (uint64_t)(k * ((20 * W128_ROW) >> 4));
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-              umma_bf16(tmem_base + (uint32_t)((mt * 3 + dx) * 64),
-                        xd + kx + (uint64_t)(mt * ((20 * W128_ROW) >> 4)) + (uint64_t)((dx - 1) * (int)(W128_ROW >> 4)),
-                        yd + ky, idesc, acc);
-        }
-        umma_commit(empty0 + 8 * stage);
-      }
-      __syncwarp();
-      first = 0;
-      if (++stage == a.stages) { stage = 0; phase ^= 1; }
-    }
-    if (elect_one()) umma_commit(accbar);
-    __syncwarp();
-  } else {
-    const int q = warp & 3;
-    const bool has_work = t_end > t_beg;
-    if (do_bias) {
-      // column sums of the staged dy tiles: warp q owns the 16-byte chunks 2q, 2q+1 (8 output channels each) of every
-      // row; lane = (row % 16, chunk parity); the TMA's 128-byte swizzle puts chunk c of row r at chunk c ^ (r & 7)
-      const int chunk = q * 2 + (lane & 1), r0 = lane >> 1;
-      float bs[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bs[j] = 0.f;
-      int stage = 0; uint32_t phase = 0;
-      for (int t = t_beg; t < t_end; ++t) {
-        mbar_wait(full0 + 8 * stage, phase);
-        const uint32_t sg = base + (uint32_t)stage * W128_STAGE;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t r = (uint32_t)(r0 + 16 * k);
-          const uint32_t pos = ((uint32_t)chunk ^ (r & 7u)) << 4;
-          uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sg + r * W128_ROW + pos));
-          bs[0] += __uint_as_float(w0 << 16); bs[1] += __uint_as_float(w0 & 0xFFFF0000u);
-          bs[2] += __uint_as_float(w1 << 16); bs[3] += __uint_as_float(w1 & 0xFFFF0000u);
-          bs[4] += __uint_as_float(w2 << 16); bs[5] += __uint_as_float(w2 & 0xFFFF0000u);
-          bs[6] += __uint_as_float(w3 << 16); bs[7] += __uint_as_float(w3 & 0xFFFF0000u);
-        }
-        mbar_arrive(empty0 + 8 * stage);     // EVERY lane, after its own loads: see the note at do_bias
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int o = 2; o < 32; o <<= 1) bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], o);   // fixed tree over the rows
-      if (lane < 2) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a.bias_part[(int64_t)split * a.cout + co0 + chunk * 8 + j] = bs[j];
-      }
-    }
-    mbar_wait(accbar, 0);
-    tc_fence_after();
-    // TMEM lane = (group, ci): quarter q -> group q >> 1 (M tile 0: vertical taps -1 / 0; M tile 1: tap +1 / padding),
-    // input channel ci0 + (q & 1) * 32 + lane.  For a fixed co a warp writes 32 consecutive ci: coalesced rows.
-    const int ci = ci0 + (q & 1) * 32 + lane;
-    for (int mt = 0; mt < 2; ++mt) {
-      const int dyi = mt == 0 ? (q >> 1) : ((q >> 1) == 0 ? 2 : -1);
-      if (dyi < 0) continue;
-      for (int dx = 0; dx < 3; ++dx) {
-        const int tap = dyi * 3 + dx;
-        for (int cb = 0; cb < 64; cb += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * 3 + dx) * 64 + cb), r);
-          float* o = a.part + (((int64_t)split * 9 + tap) * a.cout + co0 + cb) * cin + ci;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[(int64_t)j * cin] = has_work ? __uint_as_float(r[j]) : 0.f;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, NCOLS);
 }
 
 // ------------------------------------------------------------------ host side: tensor maps
@@ -1513,28 +1351,6 @@ bool wgrad_plan(const WgradParams& p, int es, WgPlan& pl) {
 }
 }  // namespace
 
-namespace {
-// the 128-byte-row kernel: bf16, 3x3, 8 x 8 patches, every channel count a multiple of 64
-struct Wg128Plan { int tiles_x, tiles_y, tiles_total, nsplit, tiles_per_split, stages; size_t smem; };
-bool wgrad128_plan(const WgradParams& p, int es, Wg128Plan& pl, bool sizing = false) {
-  if (!(g_opt_wgrad_rows128 || sizing) || es != 2 || p.ks != 3 || p.H % 8 || p.W % 8) return false;
-  if (p.c0 % 64 || p.c1 % 64 || p.c0 + p.c1 < 64 || p.cout % 64) return false;
-  pl.tiles_x = p.W / 8; pl.tiles_y = p.H / 8;
-  pl.tiles_total = p.B * pl.tiles_x * pl.tiles_y;
-  const int ctas = ((p.c0 + p.c1) / 64) * (p.cout / 64);
-  pl.stages = 6;
-  pl.smem = (size_t)pl.stages * W128_STAGE + 1024;
-  int want = num_sms() / ctas;                 // one wave of one-CTA-per-SM blocks (512 TMEM columns each)
-  if (want < 1) want = 1;
-  int max_split = pl.tiles_total / 4;
-  if (max_split < 1) max_split = 1;
-  if (want > max_split) want = max_split;
-  pl.tiles_per_split = cdiv(pl.tiles_total, want);
-  pl.nsplit = cdiv(pl.tiles_total, pl.tiles_per_split);
-  return true;
-}
-}  // namespace
-
 bool wgrad_tc_supported(const WgradParams& p, int dtype) {
   if (dtype != PUB_BF16 && dtype != PUB_TF32) return false;
   const int es = esize(dtype), al = 16 / es;
@@ -1551,11 +1367,8 @@ size_t wgrad_tc_workspace(const WgradParams& p, int dtype) {
   if (!wgrad_plan(p, esize(dtype), pl)) return 0;
   const int64_t n = (int64_t)p.ks * p.ks * p.cout * (p.c0 + p.c1);
   const int64_t M = (int64_t)p.B * p.H * p.W;
-  int nsplit = pl.nsplit;
-  Wg128Plan p8;
-  if (wgrad128_plan(p, esize(dtype), p8, true)) nsplit = std::max(nsplit, p8.nsplit);   // whichever kernel runs (the option may be toggled after an engine sized its workspace)
-  return align_up((size_t)nsplit * n * sizeof(float), 256) +
-         align_up((size_t)std::max(cdiv(M, 1024), nsplit) * p.cout * 4, 256);
+  return align_up((size_t)pl.nsplit * n * sizeof(float), 256) +
+         align_up((size_t)std::max(cdiv(M, 1024), pl.nsplit) * p.cout * 4, 256);
 }
 
 int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int accumulate, cudaStream_t s) {
@@ -1564,31 +1377,6 @@ int wgrad_tc(const WgradParams& p, int dtype, void* ws, size_t ws_bytes, int acc
   PUB_REQUIRE(wgrad_tc_supported(p, dtype) && wgrad_plan(p, es, pl), "wgrad_tc: unsupported shape");
   PUB_REQUIRE(ws_bytes >= wgrad_tc_workspace(p, dtype), "wgrad_tc: workspace too small");
   const int cin = p.c0 + p.c1, taps = p.ks * p.ks;
-  Wg128Plan p8;
-  if (wgrad128_plan(p, es, p8)) {
-    TcWgradArgs a{};
-    a.c0 = p.c0; a.c1 = p.c1; a.cout = p.cout; a.taps = 9; a.ks = 3;
-    a.B = p.B; a.H = p.H; a.W = p.W; a.TW = 8; a.TH = 8;
-    a.tiles_x = p8.tiles_x; a.tiles_y = p8.tiles_y; a.tiles_total = p8.tiles_total;
-    a.tiles_per_split = p8.tiles_per_split; a.stages = p8.stages; a.box3 = 1;
-    a.part = (float*)ws;
-    float* bpart = (float*)((char*)ws + align_up((size_t)p8.nsplit * 9 * p.cout * cin * sizeof(float), 256));
-    a.bias_part = (p.dbias && g_opt_wgrad_fused_bias) ? bpart : nullptr;
-    CUtensorMap tmX0, tmX1, tmDY;
-    PUB_TRY(make_act_map(&tmX0, p.x0, 2, p.c0, p.ld0, p.B, p.H, p.W, 64, 10, 10, 1, CU_TENSOR_MAP_SWIZZLE_128B));
-    if (p.c1) PUB_TRY(make_act_map(&tmX1, p.x1, 2, p.c1, p.ld1, p.B, p.H, p.W, 64, 10, 10, 1, CU_TENSOR_MAP_SWIZZLE_128B));
-    else tmX1 = tmX0;
-    PUB_TRY(make_act_map(&tmDY, p.dy, 2, p.cout, p.ld_dy, p.B, p.H, p.W, 64, 8, 8, 1, CU_TENSOR_MAP_SWIZZLE_128B));
-    static bool attr8 = false;
-    if (!attr8) { PUB_TRY(set_smem_attr(wgrad_tc128_kernel, 220 * 1024)); attr8 = true; }
-    dim3 grid(cin / 64, p.cout / 64, p8.nsplit);
-    launch_pdl(wgrad_tc128_kernel, grid, NTHREADS, p8.smem, s, tmX0, tmX1, tmDY, a);
-    PUB_LAUNCH_CHECK();
-    int nchunk = p8.nsplit;
-    if (p.dbias && !a.bias_part)
-      PUB_TRY(colsum(p.dy, p.ld_dy, p.cout, (int64_t)p.B * p.H * p.W, dtype, bpart, nullptr, 0, s, &nchunk));
-    return wgrad_finish(a.part, p.dw, p8.nsplit, 9, p.cout, cin, bpart, nchunk, p.dbias, accumulate, s);
-  }
   TcWgradArgs a{};
   a.c0 = p.c0; a.c1 = p.c1; a.cout = p.cout; a.taps = taps; a.ks = p.ks;
   a.B = p.B; a.H = p.H; a.W = p.W; a.TW = pl.tw; a.TH = pl.th;

@@ -96,8 +96,9 @@ __global__ void add_kernel(const T* __restrict__ a, int lda, const T* __restrict
   }
 }
 
-template <typename T>
-__global__ void maxpool_kernel(const T* __restrict__ x, int C, T* __restrict__ y, int B, int H, int W) {
+// TI / TO differ where the Gaussian encoder's bf16 first stage hands over to its tf32 stages (bf16 values are tf32 values)
+template <typename T, typename TO = T>
+__global__ void maxpool_kernel(const T* __restrict__ x, int C, TO* __restrict__ y, int B, int H, int W) {
   pdl_enter();
   const int V = C / 8, Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)B * Ho * Wo * V;
@@ -113,14 +114,14 @@ __global__ void maxpool_kernel(const T* __restrict__ x, int C, T* __restrict__ y
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = d == 0 ? f[j] : fmaxf(o[j], f[j]);
     }
-    Vec8<T>::store(y + q * C + v * 8, o);
+    Vec8<TO>::store(y + q * C + v * 8, o);
   }
 }
 
 // x is the post-ReLU pre-pool activation.  dx = dy routed to the first maximum of each 2x2 window
 // (scan order (0,0),(0,1),(1,0),(1,1) like ATen) and gated by the ReLU (x > 0).
-template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int C,
+template <typename T, typename TG = T>     // TG: type of the incoming (pooled-resolution) gradient
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const TG* __restrict__ dy, T* __restrict__ dx, int C,
                                    int B, int H, int W) {
   pdl_enter();
   const int V = C / 8, Ho = H / 2, Wo = W / 2;
@@ -130,7 +131,7 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
     const int64_t q = i / V;
     const int xo = (int)(q % Wo), yo = (int)((q / Wo) % Ho), b = (int)(q / ((int64_t)Wo * Ho));
     float f[4][8], g[8];
-    Vec8<T>::load(dy + q * C + v * 8, g);
+    Vec8<TG>::load(dy + q * C + v * 8, g);
 #pragma unroll
     for (int d = 0; d < 4; ++d)
       Vec8<T>::load(x + (((int64_t)b * H + yo * 2 + (d >> 1)) * W + xo * 2 + (d & 1)) * C + v * 8, f[d]);
@@ -228,19 +229,25 @@ int add_views(const void* a, int lda, const void* b, int ldb, void* y, int ldy, 
   return 0;
 }
 
-int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cudaStream_t s) {
+int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cudaStream_t s, int out_dtype) {
   PUB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2: C %% 8 and even H, W required");
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
-  if (dtype == PUB_BF16) launch_pdl(maxpool_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, C, (bf16*)y, B, H, W);
+  if (out_dtype >= 0 && (out_dtype == PUB_BF16) != (dtype == PUB_BF16)) {
+    PUB_REQUIRE(dtype == PUB_BF16, "maxpool2: the only mixed form is bf16 in, f32 out");
+    launch_pdl(maxpool_kernel<bf16, float>, grid_for(n), NT, 0, s, (const bf16*)x, C, (float*)y, B, H, W);
+  } else if (dtype == PUB_BF16) launch_pdl(maxpool_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, C, (bf16*)y, B, H, W);
   else launch_pdl(maxpool_kernel<float>, grid_for(n), NT, 0, s, (const float*)x, C, (float*)y, B, H, W);
   PUB_LAUNCH_CHECK();
   return 0;
 }
 
 int maxpool2_bwd(const void* x, const void* /*yp*/, const void* dy, void* dx, int C, int B, int H, int W, int dtype,
-                 cudaStream_t s) {
+                 cudaStream_t s, int dy_dtype) {
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
-  if (dtype == PUB_BF16) launch_pdl(maxpool_bwd_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, (const bf16*)dy, (bf16*)dx, C, B, H, W);
+  if (dy_dtype >= 0 && (dy_dtype == PUB_BF16) != (dtype == PUB_BF16)) {
+    PUB_REQUIRE(dtype == PUB_BF16, "maxpool2_bwd: the only mixed form is bf16 activations / dx with an f32 incoming gradient");
+    launch_pdl(maxpool_bwd_kernel<bf16, float>, grid_for(n), NT, 0, s, (const bf16*)x, (const float*)dy, (bf16*)dx, C, B, H, W);
+  } else if (dtype == PUB_BF16) launch_pdl(maxpool_bwd_kernel<bf16>, grid_for(n), NT, 0, s, (const bf16*)x, (const bf16*)dy, (bf16*)dx, C, B, H, W);
   else launch_pdl(maxpool_bwd_kernel<float>, grid_for(n), NT, 0, s, (const float*)x, (const float*)dy, (float*)dx, C, B, H, W);
   PUB_LAUNCH_CHECK();
   return 0;

@@ -11,6 +11,8 @@
 
 struct pub_encoder {
   int in_ch = 0, latent = 0, dtype = PUB_BF16;
+  int s0_bf16 = 0;   // PUB_TF32_BF16S0: the full-resolution stage (3 convs) in bf16, everything behind its pooling in tf32
+  int layer_dtype(int k) const { return (s0_bf16 && k < 3) ? PUB_BF16 : dtype; }
   std::vector<int> filters;
   int nconv = 0, nparams = 0;
 };
@@ -33,9 +35,9 @@ struct EPlan {
 
 int build(const pub_encoder* e, int B, int H, int W, void* base, size_t cap, EPlan& pl) {
   Arena ar(base, cap);
-  const size_t es = dtype_size(e->dtype);
+  const size_t es = dtype_size(e->dtype);          // widest storage type of the network (scratch / pooled buffers)
   pl.B = B; pl.H = H; pl.W = W; pl.es = es;
-  pl.x_in = ar.take((size_t)B * H * W * 8 * es);
+  pl.x_in = ar.take((size_t)B * H * W * 8 * dtype_size(e->layer_dtype(0)));
   pl.act.clear(); pl.pooled.clear(); pl.ch.clear(); pl.hh.clear(); pl.ww.clear(); pl.wp.clear();
   int h = H, w = W, cin = e->in_ch;
   size_t max_act = (size_t)B * H * W * 8 * es, max_w = 0, max_wg = 0;
@@ -50,14 +52,15 @@ int build(const pub_encoder* e, int B, int H, int W, void* base, size_t cap, EPl
     }
     for (int k = 0; k < 3; ++k) {
       PUB_REQUIRE(f % 8 == 0, "encoder: filter counts must be multiples of 8");
-      pl.act.push_back(ar.take((size_t)B * h * w * f * es));
-      pl.wp.push_back(ar.take((size_t)9 * f * cin * es));
+      const int ldt = e->layer_dtype((int)st * 3 + k);
+      pl.act.push_back(ar.take((size_t)B * h * w * f * dtype_size(ldt)));
+      pl.wp.push_back(ar.take((size_t)9 * f * cin * dtype_size(ldt)));
       pl.ch.push_back(f); pl.hh.push_back(h); pl.ww.push_back(w);
       max_act = std::max(max_act, (size_t)B * h * w * std::max(f, cin) * es);
       max_w = std::max(max_w, (size_t)9 * f * std::max(cin, 8) * es);
       WgradParams wp{};
       wp.c0 = cin; wp.cout = f; wp.B = B; wp.H = h; wp.W = w; wp.ks = 3; wp.ld0 = cin; wp.ld_dy = f;
-      max_wg = std::max(max_wg, wgrad_workspace(wp, e->dtype, PUB_BACKEND_AUTO));
+      max_wg = std::max(max_wg, wgrad_workspace(wp, ldt, PUB_BACKEND_AUTO));
       max_wg = std::max(max_wg, wgrad_simt_workspace(wp));
       cin = f;
     }
@@ -140,7 +143,11 @@ int pub_encoder_create(int in_channels, const int32_t* filters, int n_stages, in
   PUB_REQUIRE(filters && out && n_stages > 0 && latent_dim > 0, "pub_encoder_create: bad arguments");
   PUB_REQUIRE(in_channels >= 1 && in_channels <= 8, "pub_encoder_create: in_channels must be in [1, 8]");
   pub_encoder* e = new pub_encoder();
-  e->in_ch = in_channels; e->latent = latent_dim; e->dtype = dtype;
+  PUB_REQUIRE(dtype == PUB_F32 || dtype == PUB_BF16 || dtype == PUB_TF32 || dtype == PUB_TF32_BF16S0,
+              "pub_encoder_create: bad dtype %d", dtype);
+  e->in_ch = in_channels; e->latent = latent_dim;
+  e->s0_bf16 = dtype == PUB_TF32_BF16S0 && n_stages > 1;
+  e->dtype = dtype == PUB_TF32_BF16S0 ? PUB_TF32 : dtype;
   e->filters.assign(filters, filters + n_stages);
   e->nconv = 3 * n_stages;
   e->nparams = 2 * e->nconv + 4;
@@ -165,26 +172,30 @@ int pub_encoder_forward(pub_encoder* e, int B, int H, int W, const float* x_nchw
   EPlan pl;
   PUB_TRY(build(e, B, H, W, ws, ws_bytes, pl));
   const int dt = e->dtype;
-  PUB_TRY(nchw_to_nhwc(x_nchw, cx, t_nchw, t_nchw ? ct : 0, pl.x_in, 8, B, H, W, dt, s));
+  PUB_TRY(nchw_to_nhwc(x_nchw, cx, t_nchw, t_nchw ? ct : 0, pl.x_in, 8, B, H, W, e->layer_dtype(0), s));
   {
-    std::vector<PackEntry> pe;
+    std::vector<PackEntry> pe[2];   // [0]: layers stored in e->dtype, [1]: the bf16 first stage of the mixed form
     int ci = e->in_ch;
-    for (int k = 0; k < e->nconv; ++k) { pe.push_back({P[2 * k], pl.wp[k], pl.ch[k], ci, 3, 0}); ci = pl.ch[k]; }
-    PUB_TRY(pack_weights_batched(pe.data(), (int)pe.size(), dt, s));
+    for (int k = 0; k < e->nconv; ++k) {
+      pe[e->layer_dtype(k) != dt].push_back({P[2 * k], pl.wp[k], pl.ch[k], ci, 3, 0});
+      ci = pl.ch[k];
+    }
+    PUB_TRY(pack_weights_batched(pe[0].data(), (int)pe[0].size(), dt, s));
+    if (!pe[1].empty()) PUB_TRY(pack_weights_batched(pe[1].data(), (int)pe[1].size(), PUB_BF16, s));
   }
   const void* cur = pl.x_in;
   int cin = e->in_ch, ld = 8, h = H, w = W;
   for (int k = 0; k < e->nconv; ++k) {
-    const int st = k / 3, f = pl.ch[k];
+    const int st = k / 3, f = pl.ch[k], ldt = e->layer_dtype(k);
     if (k % 3 == 0 && st > 0) {
-      PUB_TRY(maxpool2(cur, cin, pl.pooled[st], B, h, w, dt, s));
+      PUB_TRY(maxpool2(cur, cin, pl.pooled[st], B, h, w, e->layer_dtype(k - 1), s, ldt));
       cur = pl.pooled[st]; h /= 2; w /= 2;
     }
     ConvParams c{};
     c.x0 = cur; c.c0 = cin; c.ld0 = ld; c.w = pl.wp[k]; c.bias = P[2 * k + 1];
     c.y = pl.act[k]; c.ldy = f; c.B = B; c.H = h; c.W = w; c.cout = f; c.ks = 3; c.relu = 1;
     c.w_settled = 1;
-    PUB_TRY(conv_forward(c, dt, backend, s));
+    PUB_TRY(conv_forward(c, ldt, backend, s));
     cur = pl.act[k]; cin = f; ld = f;
   }
   const int F = e->filters.back(), L = e->latent;
@@ -209,15 +220,17 @@ int pub_encoder_backward(pub_encoder* e, int B, int H, int W, const float* dmu, 
                                       hg[3], pl.dgap);
   PUB_LAUNCH_CHECK();
   {
-    std::vector<PackEntry> pe;
-    for (int k = 1; k < n; ++k) pe.push_back({P[2 * k], pl.wp[k], pl.ch[k], pl.ch[k - 1], 3, 1});
-    PUB_TRY(pack_weights_batched(pe.data(), (int)pe.size(), dt, s));
+    std::vector<PackEntry> pe[2];
+    for (int k = 1; k < n; ++k) pe[e->layer_dtype(k) != dt].push_back({P[2 * k], pl.wp[k], pl.ch[k], pl.ch[k - 1], 3, 1});
+    PUB_TRY(pack_weights_batched(pe[0].data(), (int)pe[0].size(), dt, s));
+    if (!pe[1].empty()) PUB_TRY(pack_weights_batched(pe[1].data(), (int)pe[1].size(), PUB_BF16, s));
   }
   void* ga = pl.ga;
   void* gb = pl.gb;
   PUB_TRY(global_mean_bwd(pl.dgap, pl.act[n - 1], F, B, (int64_t)pl.hh[n - 1] * pl.ww[n - 1], ga, dt, s));
   for (int k = n - 1; k >= 0; --k) {
     const int st = k / 3, f = pl.ch[k], h = pl.hh[k], w = pl.ww[k];
+    const int ldt = e->layer_dtype(k);            // type of this layer's tensors, gradients and packed weights
     const bool pooled_in = (k % 3 == 0 && st > 0);
     const void* in_k; int cin, ld;
     if (k == 0) { in_k = pl.x_in; cin = e->in_ch; ld = 8; }
@@ -226,16 +239,16 @@ int pub_encoder_backward(pub_encoder* e, int B, int H, int W, const float* dmu, 
     WgradParams wp{};
     wp.x0 = in_k; wp.c0 = cin; wp.ld0 = ld; wp.dy = ga; wp.ld_dy = f; wp.dw = G[2 * k]; wp.dbias = G[2 * k + 1];
     wp.B = B; wp.H = h; wp.W = w; wp.cout = f; wp.ks = 3;
-    PUB_TRY(wgrad(wp, dt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
+    PUB_TRY(wgrad(wp, ldt, backend, pl.wg_ws, pl.wg_ws_bytes, 0, s));
     if (k == 0) break;
     ConvParams c{};
     c.x0 = ga; c.c0 = f; c.ld0 = f; c.w = pl.wp[k]; c.y = gb; c.ldy = cin; c.B = B; c.H = h; c.W = w; c.cout = cin; c.ks = 3;
     c.w_settled = 1;
     if (!pooled_in) { c.mask = pl.act[k - 1]; c.ld_mask = cin; }
-    PUB_TRY(conv_forward(c, dt, backend, s));
+    PUB_TRY(conv_forward(c, ldt, backend, s));
     if (pooled_in) {
-      // gb = d pooled  ->  ga = d pre-activation of conv k-1 at the finer resolution
-      PUB_TRY(maxpool2_bwd(pl.act[k - 1], nullptr, gb, ga, cin, B, pl.hh[k - 1], pl.ww[k - 1], dt, s));
+      // gb = d pooled (this layer's type)  ->  ga = d pre-activation of conv k-1 at the finer resolution (its type)
+      PUB_TRY(maxpool2_bwd(pl.act[k - 1], nullptr, gb, ga, cin, B, pl.hh[k - 1], pl.ww[k - 1], e->layer_dtype(k - 1), s, ldt));
     } else {
       std::swap(ga, gb);
     }

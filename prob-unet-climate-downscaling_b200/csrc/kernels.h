@@ -107,10 +107,11 @@ int resample2x(const void* x, int ld, int C, void* y, int B, int H, int W, int m
 int resample2x_bwd(const void* dy, int ld, int C, void* dx, int B, int H, int W, int mode, int dtype, cudaStream_t s);
 int add_views(const void* a, int lda, const void* b, int ldb, void* y, int ldy, int C, int64_t M, int dtype,
               cudaStream_t s);
-int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cudaStream_t s);
+// out_dtype >= 0 and of another width than dtype: bf16 in, f32 out (the encoder's bf16 -> tf32 stage boundary)
+int maxpool2(const void* x, int C, void* y, int B, int H, int W, int dtype, cudaStream_t s, int out_dtype = -1);
 // dx[b,y,x,c] = dy[b,y/2,x/2,c] if x is the (first) argmax of its window and mask_src>0 ... see elementwise.cu
 int maxpool2_bwd(const void* x, const void* yp, const void* dy, void* dx, int C, int B, int H, int W, int dtype,
-                 cudaStream_t s);
+                 cudaStream_t s, int dy_dtype = -1);   // dy_dtype: as out_dtype above (f32 gradient in, bf16 x / dx)
 int relu_mask_inplace(void* dy, const void* y, int64_t n, int dtype, cudaStream_t s);
 int global_mean(const void* x, int C, int B, int64_t HW, float* out, float* partial, int dtype, cudaStream_t s);
 int global_mean_bwd(const float* dmean, const void* y_mask, int C, int B, int64_t HW, void* dx, int dtype,

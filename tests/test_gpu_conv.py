@@ -101,23 +101,9 @@ def test_conv_forward(case, mode):
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] * c[1] * c[2] <= 4096 * 4])
-@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16", "tc_tf32", "tc_bf16_rows128"])
+@pytest.mark.parametrize("mode", ["simt_f32", "simt_bf16", "tc_bf16", "tc_tf32"])
 def test_conv_wgrad(case, mode):
-    """tc_bf16_rows128: the 64-channel-row kernel (debug option wgrad_rows128, off by default) on the shapes it takes."""
     N = _setup()
-    B, H, W, c0, c1, cout, ks = case
-    if mode == "tc_bf16_rows128":
-        if ks != 3 or c0 % 64 or c1 % 64 or cout % 64 or H % 8 or W % 8:
-            pytest.skip("not a shape of the 128-byte-row kernel")
-        N.lib().pub_debug_option(b"wgrad_rows128", 1)
-        try:
-            return _wgrad_case(N, case, "tc_bf16")
-        finally:
-            N.lib().pub_debug_option(b"wgrad_rows128", 0)
-    return _wgrad_case(N, case, mode)
-
-
-def _wgrad_case(N, case, mode):
     B, H, W, c0, c1, cout, ks = case
     dt = torch.bfloat16 if mode.endswith("bf16") else torch.float32
     backend = N.BACKEND_TCGEN05 if mode.startswith("tc") else N.BACKEND_SIMT

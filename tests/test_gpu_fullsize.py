@@ -62,32 +62,28 @@ def test_wgrad_two_producers_agree_and_bias_is_column_sum(cin, cout, res):
     assert torch.equal(again[0], out[1][0]) and torch.equal(again[1], out[1][1])
 
 
-@pytest.mark.parametrize("rows128", [0, 1])
-def test_wgrad_is_repeatable_while_another_stream_keeps_the_sms_busy(rows128):
-    """The bias sums inside the weight-gradient kernels read the staged dy tiles with ordinary shared-memory loads and
+def test_wgrad_is_repeatable_while_another_stream_keeps_the_sms_busy():
+    """The bias sums inside the weight-gradient kernel read the staged dy tiles with ordinary shared-memory loads and
     then release the stage.  With a lane-0-only release a lane that left the mbarrier polling loop late could read a
-    stage the TMA was already refilling: 3 % of the runs of the 128-byte-row kernel differed in one warp's 16 bias
-    channels when a second stream ran the same kernel (every lane releases now; tools/wgrad128_race.py)."""
+    stage the TMA was already refilling (found with an experimental kernel variant: 3 % of its runs differed in one
+    warp's 16 bias channels while a second stream ran the same kernel; profiles/r02_wgrad_rows128.txt).  Every lane
+    releases now; this keeps watching the shipped kernel under the same conditions."""
     import _native as N
     g = _gen(4)
     mk = lambda: torch.randn(B, 64, 64, 64, device="cuda", generator=g).bfloat16()
     x, dy, sx, sdy = mk(), mk(), mk(), mk()
     side = torch.cuda.Stream()
-    N.lib().pub_debug_option(b"wgrad_rows128", rows128)
-    try:
-        ref = N.conv2d_wgrad_nhwc(x, dy, 3)
+    ref = N.conv2d_wgrad_nhwc(x, dy, 3)
+    torch.cuda.synchronize()
+    bad = 0
+    for _ in range(100):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(6):
+                N.conv2d_wgrad_nhwc(sx, sdy, 3)
+        outs = [N.conv2d_wgrad_nhwc(x, dy, 3) for _ in range(4)]
         torch.cuda.synchronize()
-        bad = 0
-        for _ in range(100):
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(6):
-                    N.conv2d_wgrad_nhwc(sx, sdy, 3)
-            outs = [N.conv2d_wgrad_nhwc(x, dy, 3) for _ in range(4)]
-            torch.cuda.synchronize()
-            bad += sum(not (torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1])) for o in outs)
-    finally:
-        N.lib().pub_debug_option(b"wgrad_rows128", 0)
+        bad += sum(not (torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1])) for o in outs)
     assert bad == 0, f"{bad}/400 runs differ"
 
 

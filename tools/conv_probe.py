@@ -23,8 +23,8 @@ for kind, cin, cout, r in SHAPES:
     else:
         dy = torch.randn(B, r, r, cout, device="cuda", generator=g).bfloat16()
         fn = lambda: N.conv2d_wgrad_nhwc(x, dy, 3, want_bias=False)
-    for box3 in ((0, 1) if kind == "wgrad" else (1,)):       # A/B of the 128-byte-row weight-gradient kernel
-        N.lib().pub_debug_option(b"wgrad_rows128", box3)
+    for box3 in ((0, 1) if kind == "wgrad" else (1,)):
+        N.lib().pub_debug_option(b"wgrad_box3", box3)
         fn(); ts = []
         for _ in range(reps):
             flush.zero_()
@@ -32,5 +32,5 @@ for kind, cin, cout, r in SHAPES:
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         t = sorted(ts)[len(ts) // 2]
-        tag = f" rows128={box3}" if kind == "wgrad" else ""
+        tag = f" box3={box3}" if kind == "wgrad" else ""
         print(f"{kind:6s} {cin:4d}->{cout:4d} @{r:3d}^2  {t:8.1f} us  {fl / t / 1e6:7.1f} TFLOP/s{tag}", flush=True)
