@@ -64,6 +64,24 @@ def test_prior_posterior_heads_and_kl(setup, golden):
         assert rel_err(kl, kl_t) < 1e-5
 
 
+def test_lazy_elbo_scalars_match_the_synchronous_ones(golden):
+    """sync_scalars = "lazy": the reconstruction term comes back as a LazyScalar whose device -> pinned-host copy was
+    enqueued inside elbo(); same value as the .item() float, gradients untouched."""
+    from lazy_scalar import LazyScalar
+    x, y, eps = _inputs(golden)
+    m = canonical_model(compute_dtype="fp32", device="cuda")
+    out = {}
+    for mode in (True, "lazy", False):
+        m.sync_scalars = mode
+        m.zero_grad(set_to_none=True)
+        total, recon, kl = m.elbo(x, y, None, M=eps.shape[0], eps=eps)
+        total.backward()
+        out[mode] = (float(total), recon[0], m.fcomb.layers[4].bias.grad.clone())
+    assert isinstance(out[True][1], float) and isinstance(out["lazy"][1], LazyScalar) and torch.is_tensor(out[False][1])
+    assert float(out["lazy"][1]) == out[True][1] == float(out[False][1])
+    assert out["lazy"][0] == out[True][0] and torch.equal(out["lazy"][2], out[True][2])
+
+
 def test_encoder_precision_policy(golden, monkeypatch):
     """The Gaussian encoders of a bf16 model run in tf32 (f32 storage).  Measured against the golden mu / sigma of the
     real reference: all-bf16 encoders miss the 1e-2 bar (1.3e-2); tf32 behind a bf16 full-resolution stage

@@ -226,3 +226,20 @@ def test_reference_arm_of_bench_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert abs(d["e2e"]["value"] - d["value"]) < 1e-9 * max(1.0, d["value"])
+
+
+def test_lazy_scalar_behaves_like_the_float_the_reference_returns():
+    """lazy_scalar.LazyScalar stands in for the Python floats of the reference's elbo() (recon_list[0], per-variable L1
+    list): conversions, arithmetic, comparisons, formatting, and numpy reductions over lists of them."""
+    import numpy as np
+    from lazy_scalar import LazyScalar, lazy_list
+    vals = lazy_list(torch.tensor([1.5, 2.5, -3.0]))
+    assert [float(v) for v in vals] == [1.5, 2.5, -3.0] and vals[0].item() == 1.5
+    assert np.mean(vals) == pytest.approx(1.0 / 3) and np.asarray(vals).dtype == np.float64
+    assert float(np.mean(vals + [1.0])) == 0.5 and sum(vals) == 1.0 and max(vals) == 2.5
+    assert vals[0] + 1 == 2.5 and 2 * vals[1] == 5.0 and vals[1] / 2 == 1.25 and 1 - vals[0] == -0.5 and -vals[2] == 3.0
+    assert vals[2] < 0 < vals[0] <= 1.5 and vals[0] == 1.5 and vals[0] != vals[1] and abs(vals[2]) == 3.0
+    assert f"{vals[0]:.3f}" == "1.500" and str(vals[1]) == "2.5" and round(vals[1]) == 2 and int(vals[2]) == -3
+    assert np.float64(2.0) * vals[0] == 3.0 and isinstance(vals[0] + vals[1], float)
+    single = LazyScalar(torch.tensor(4.0))
+    assert float(single) == 4.0 and bool(single) and hash(single) == hash(4.0)

@@ -117,10 +117,14 @@ def _loader(n_batches, B, res):
     return L(batches)
 
 
-def test_reference_train_eval_and_sample_loops_drive_the_mirror(reference_train_module, monkeypatch):
+@pytest.mark.parametrize("scalars", [True, "lazy"])
+def test_reference_train_eval_and_sample_loops_drive_the_mirror(reference_train_module, monkeypatch, scalars):
+    """scalars="lazy": elbo returns float-like LazyScalars instead of .item() floats (no host sync between forward and
+    backward); the reference's loops -- list.append + np.mean per epoch -- must not notice."""
     tm = reference_train_module
     torch.set_num_threads(8)
     model = canonical_model(latent_dim=16)                      # afcrps is the default loss_type (src/main.py:1,136)
+    model.sync_scalars = scalars
     _FakeBackend(model, monkeypatch)
     loader = _loader(2, 2, 32)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)        # src/main.py:103
@@ -158,3 +162,14 @@ def test_elbo_return_arity_follows_the_loss_type_like_the_three_reference_varian
     assert len(out) == 3 and isinstance(out[1][0], float) and out[2].shape == (2,)
     with pytest.raises(ValueError):
         model.elbo(f["inputs"], f["targets"], None, M=1)                          # src/prob_unet.py:282-283
+    # the lazy policy returns the same numbers as float-likes
+    from lazy_scalar import LazyScalar
+    torch.manual_seed(3)
+    strict = model.elbo(f["inputs"], f["targets"], None, M=2)[1][0]
+    model.sync_scalars = "lazy"
+    torch.manual_seed(3)
+    lazy = model.elbo(f["inputs"], f["targets"], None, M=2)[1][0]
+    assert isinstance(lazy, LazyScalar) and float(lazy) == strict
+    model.loss_type = "l1"
+    out = model.elbo(f["inputs"], f["targets"], None)
+    assert len(out[1]) == 3 and all(isinstance(v, LazyScalar) for v in out[1]) and np.isfinite(np.mean(out[1]))
