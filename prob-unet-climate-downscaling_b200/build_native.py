@@ -26,6 +26,7 @@ def _digest():
     for f in sorted(glob.glob(os.path.join(CSRC, "*")) + [os.path.join(HERE, "..", "include", "probunet_b200.h")]):
         h.update(open(f, "rb").read())
     h.update(" ".join(FLAGS).encode())
+    h.update(open(os.path.abspath(__file__), "rb").read())      # compile / link recipe changes rebuild too
     return h.hexdigest()
 
 
@@ -49,7 +50,9 @@ def build(force=False, verbose=False):
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(cc, srcs))
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    # the SHARED runtime: the process already holds torch's libcudart.so.12 (same major version), so the library and torch
+    # share one runtime instance, and the .so that travels to the GPU box carries no copy of the runtime's symbol table
+    cmd = [NVCC, "-shared", "--cudart", "shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
